@@ -1,0 +1,136 @@
+// Small device helpers of the GCG driver: residual norms for CheckConvergence and the
+// element-wise assembly kernels of the projected (N x N) problem.
+#include "b200_reduce.cuh"
+
+// ax <- ax - lam[c]*bx ; res[c] = ||ax[:,c]||_2   (reference src/ops_eig_sol_gcg.c:214-224)
+template <int CPT>
+__global__ void __launch_bounds__(RED_THREADS)
+residual_kernel(long long n, int k, long long rows_per_chunk, double *ax, int ldax, const double *bx, int ldbx,
+                const double *__restrict__ lam, double *res, double *part, unsigned *ticket)
+{
+	extern __shared__ double sm[];
+	const int cx = blockDim.x, ry = blockDim.y;
+	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[1][CPT], l[CPT];
+#pragma unroll
+	for (int i = 0; i < CPT; ++i) {
+		const int c = threadIdx.x + i * cx;
+		acc[0][i] = 0.0; l[i] = (c < k) ? lam[c] : 0.0;
+	}
+	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
+#pragma unroll
+		for (int i = 0; i < CPT; ++i) {
+			const int c = threadIdx.x + i * cx;
+			if (c < k) {
+				// lambda*Bx is rounded first, then subtracted: the reference scales Bx (dscal) and
+				// then forms Ax - (lambda Bx) (daxpy), src/ops_eig_sol_gcg.c:214-220
+				const double v = ax[(size_t)row * ldax + c] - __dmul_rn(l[i], bx[(size_t)row * ldbx + c]);
+				ax[(size_t)row * ldax + c] = v;
+				acc[0][i] = fma(v, v, acc[0][i]);
+			}
+		}
+	}
+	if (!red_block_and_elect<CPT, 1>(acc, k, sm, part, ticket)) return;
+	const int tid = threadIdx.y * cx + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	for (int c = warp; c < k; c += RED_THREADS / 32) {
+		const double s = red_total<1>(part, gridDim.x, k, 0, c);
+		if (lane == 0) res[c] = sqrt(s);
+	}
+}
+
+extern "C" int b200k_residual_norms(long long n, int k, double *ax, int ldax, const double *bx, int ldbx,
+                                    const double *lam_dev, double *res_dev)
+{
+	if (k <= 0) return 0;
+	B200_CHECK(k <= 128, "residual norms: %d columns (<=128 per call)", k);
+	const RedGeom g = red_geometry(n, k);
+	char *base = (char *)b200_scratch(0, sizeof(double) * (size_t)(g.chunks + 1) * k + 64);
+	if (!base) return 1;
+	double *part = (double *)base;
+	unsigned *ticket = (unsigned *)(part + (size_t)(g.chunks + 1) * k);
+	B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), g_b200.stream));
+	const size_t smem = sizeof(double) * (size_t)g.ry * k;
+	if (k <= 32)      residual_kernel<1><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
+	else if (k <= 64) residual_kernel<2><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
+	else              residual_kernel<4><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// ---- small strided matrix helpers (N x N objects; latency-bound, one launch each) ----------
+__global__ void copy2d_kernel(int rows, int cols, const double *src, int s_rs, int s_cs, double *dst, int d_rs, int d_cs)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= rows * cols) return;
+	const int r = idx / cols, c = idx - r * cols;
+	dst[(size_t)r * d_rs + (size_t)c * d_cs] = src[(size_t)r * s_rs + (size_t)c * s_cs];
+}
+extern "C" int b200k_copy2d(int rows, int cols, const double *src, int s_rs, int s_cs, double *dst, int d_rs, int d_cs)
+{
+	if (rows <= 0 || cols <= 0) return 0;
+	copy2d_kernel<<<b200_ceil_div((long long)rows * cols, 256), 256, 0, g_b200.stream>>>(rows, cols, src, s_rs, s_cs, dst, d_rs, d_cs);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+__global__ void set_diag_kernel(int n, double *a, int lda, const double *d, double shift)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	a[(size_t)i * lda + i] = (d ? d[i] : a[(size_t)i * lda + i]) + shift;
+}
+extern "C" int b200k_set_diag(int n, double *a, int lda, const double *d, double shift)
+{
+	if (n <= 0) return 0;
+	set_diag_kernel<<<b200_ceil_div(n, 128), 128, 0, g_b200.stream>>>(n, a, lda, d, shift);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+__global__ void zero_rows_kernel(int nidx, const int *idx, int cols, double *a, int rs, int cs)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nidx * cols) return;
+	const int i = t / cols, c = t - i * cols;
+	a[(size_t)idx[i] * rs + (size_t)c * cs] = 0.0;
+}
+extern "C" int b200k_zero_rows(int nidx, const int *idx_dev, int cols, double *a, int rs, int cs)
+{
+	if (nidx <= 0 || cols <= 0) return 0;
+	zero_rows_kernel<<<b200_ceil_div((long long)nidx * cols, 256), 256, 0, g_b200.stream>>>(nidx, idx_dev, cols, a, rs, cs);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+__global__ void gather_cols_kernel(int rows, int nidx, const int *idx, const double *src, int s_rs, int s_cs,
+                                   double *dst, int d_rs, int d_cs)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= rows * nidx) return;
+	const int r = t / nidx, i = t - r * nidx;
+	dst[(size_t)r * d_rs + (size_t)i * d_cs] = src[(size_t)r * s_rs + (size_t)idx[i] * s_cs];
+}
+extern "C" int b200k_gather_cols(int rows, int nidx, const int *idx_dev, const double *src, int s_rs, int s_cs,
+                                 double *dst, int d_rs, int d_cs)
+{
+	if (rows <= 0 || nidx <= 0) return 0;
+	gather_cols_kernel<<<b200_ceil_div((long long)rows * nidx, 256), 256, 0, g_b200.stream>>>(rows, nidx, idx_dev, src, s_rs, s_cs, dst, d_rs, d_cs);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+__global__ void symmetrize_upper_kernel(int n, double *a, int lda)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n * n) return;
+	const int i = idx / n, j = idx - i * n;
+	if (i > j) a[(size_t)i * lda + j] = a[(size_t)j * lda + i];
+}
+extern "C" int b200k_symmetrize_upper(int n, double *a, int lda)
+{
+	if (n <= 1) return 0;
+	symmetrize_upper_kernel<<<b200_ceil_div((long long)n * n, 256), 256, 0, g_b200.stream>>>(n, a, lda);
+	B200_KERNEL_CHECK();
+	return 0;
+}

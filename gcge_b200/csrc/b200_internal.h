@@ -1,0 +1,64 @@
+// Internal declarations shared by the CUDA translation units of libgcge_b200.so.
+// Public surface: include/gcge_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <cstdarg>
+#include "gcge_b200.h"
+
+#include "../host/b200_dev.h"
+
+struct b200_ctx {
+	int initialised;
+	int device;
+	int num_sms;
+	cudaStream_t stream;
+	// growable device scratch: [0] reduction partials, [1] coefficient staging,
+	// [2] host<->device column-major staging, [3] small results
+	void *scratch[6];
+	size_t scratch_bytes[6];
+	// pinned host staging for small results / coefficients
+	void *pinned[2];
+	size_t pinned_bytes[2];
+	long long launches;
+	char err[512];
+};
+
+extern b200_ctx g_b200;
+
+#define B200_CUDA(call)                                                            \
+	do {                                                                           \
+		cudaError_t e_ = (call);                                                   \
+		if (e_ != cudaSuccess)                                                     \
+			return b200_fail("%s:%d %s: %s", __FILE__, __LINE__, #call,           \
+			                 cudaGetErrorString(e_));                              \
+	} while (0)
+
+#define B200_REQUIRE_INIT()                                                        \
+	do {                                                                           \
+		if (!g_b200.initialised) {                                                 \
+			int rc_ = b200_init(-1);                                               \
+			if (rc_) return rc_;                                                   \
+		}                                                                          \
+	} while (0)
+
+#define B200_CHECK(cond, ...)                                                      \
+	do {                                                                           \
+		if (!(cond)) return b200_fail(__VA_ARGS__);                                \
+	} while (0)
+
+#define B200_LAUNCHED() (++g_b200.launches)
+#define B200_KERNEL_CHECK()                                                        \
+	do {                                                                           \
+		B200_LAUNCHED();                                                           \
+		cudaError_t e_ = cudaGetLastError();                                       \
+		if (e_ != cudaSuccess)                                                     \
+			return b200_fail("%s:%d kernel launch: %s", __FILE__, __LINE__,        \
+			                 cudaGetErrorString(e_));                              \
+	} while (0)
+
+static inline int b200_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+

@@ -1,0 +1,247 @@
+// Device multi-vector store (row-major n x ld) and the HBM-bound elementwise kernels:
+// axpby / scale / copy on column ranges, column-major <-> row-major staging, RNG fill.
+#include "b200_internal.h"
+
+static int mv_ld_for(int ncols)
+{
+	// rows start on 32-byte sector boundaries once there are enough columns to matter
+	if (ncols <= 2) return ncols < 1 ? 1 : ncols;
+	return (ncols + 3) & ~3;
+}
+
+extern "C" int b200_mv_create(int nrows, int ncols, b200_mv **out)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(out && nrows >= 0 && ncols >= 0, "b200_mv_create: bad arguments");
+	b200_mv *x = (b200_mv *)calloc(1, sizeof(b200_mv));
+	x->nrows = nrows; x->ncols = ncols; x->ld = mv_ld_for(ncols); x->owner = 1;
+	size_t bytes = sizeof(double) * (size_t)(nrows > 0 ? nrows : 1) * (size_t)x->ld;
+	cudaError_t e = cudaMalloc(&x->d, bytes);
+	if (e != cudaSuccess) {
+		free(x);
+		return b200_fail("b200_mv_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	}
+	B200_CUDA(cudaMemsetAsync(x->d, 0, bytes, g_b200.stream));
+	*out = x;
+	return 0;
+}
+
+extern "C" int b200_mv_destroy(b200_mv *x)
+{
+	if (!x) return 0;
+	if (x->owner) {
+		if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
+		cudaFree(x->d);
+	}
+	free(x);
+	return 0;
+}
+
+extern "C" int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view)
+{
+	B200_CHECK(x && view && start >= 0 && start <= end && end <= x->ncols, "b200_mv_view: bad arguments");
+	b200_mv *v = (b200_mv *)calloc(1, sizeof(b200_mv));
+	v->nrows = x->nrows; v->ncols = end - start; v->ld = x->ld; v->d = x->d + start; v->owner = 0;
+	*view = v;
+	return 0;
+}
+
+extern "C" int b200_mv_shape(const b200_mv *x, int *nrows, int *ncols)
+{
+	B200_CHECK(x, "b200_mv_shape: NULL multi-vector");
+	if (nrows) *nrows = x->nrows;
+	if (ncols) *ncols = x->ncols;
+	return 0;
+}
+
+// ------------------------------------------------------------------ transposes
+// cm: column-major with leading dimension ld_cm (elements); rm: row-major with ld_rm.
+// 32x32 tiles through shared memory so both sides are coalesced.
+__global__ void cm_to_rm_kernel(long long n, int k, const double *__restrict__ cm, long long ld_cm,
+                                double *__restrict__ rm, int ld_rm)
+{
+	__shared__ double tile[32][33];
+	const long long r0 = (long long)blockIdx.x * 32;
+	const int c0 = blockIdx.y * 32;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const long long r = r0 + threadIdx.x; const int c = c0 + j;
+		if (r < n && c < k) tile[j][threadIdx.x] = cm[(size_t)c * ld_cm + r];
+	}
+	__syncthreads();
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const long long r = r0 + j; const int c = c0 + threadIdx.x;
+		if (r < n && c < k) rm[(size_t)r * ld_rm + c] = tile[threadIdx.x][j];
+	}
+}
+
+__global__ void rm_to_cm_kernel(long long n, int k, const double *__restrict__ rm, int ld_rm,
+                                double *__restrict__ cm, long long ld_cm)
+{
+	__shared__ double tile[32][33];
+	const long long r0 = (long long)blockIdx.x * 32;
+	const int c0 = blockIdx.y * 32;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const long long r = r0 + j; const int c = c0 + threadIdx.x;
+		if (r < n && c < k) tile[j][threadIdx.x] = rm[(size_t)r * ld_rm + c];
+	}
+	__syncthreads();
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const long long r = r0 + threadIdx.x; const int c = c0 + j;
+		if (r < n && c < k) cm[(size_t)c * ld_cm + r] = tile[threadIdx.x][j];
+	}
+}
+
+int b200k_cm_to_rm(long long n, int k, const double *cm, long long ld_cm, double *rm, int ld_rm)
+{
+	if (n <= 0 || k <= 0) return 0;
+	dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32)), block(32, 8);
+	cm_to_rm_kernel<<<grid, block, 0, g_b200.stream>>>(n, k, cm, ld_cm, rm, ld_rm);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+int b200k_rm_to_cm(long long n, int k, const double *rm, int ld_rm, double *cm, long long ld_cm)
+{
+	if (n <= 0 || k <= 0) return 0;
+	dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32)), block(32, 8);
+	rm_to_cm_kernel<<<grid, block, 0, g_b200.stream>>>(n, k, rm, ld_rm, cm, ld_cm);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// host column-major <-> device, staged through scratch[2] in column chunks
+static const size_t kStageBytes = (size_t)256 << 20;
+
+extern "C" int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	           "b200_mv_upload: bad arguments");
+	const long long n = x->nrows;
+	if (n == 0 || end == start) return 0;
+	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));
+	if (chunk < 1) chunk = 1;
+	for (int c0 = start; c0 < end; c0 += chunk) {
+		const int k = (end - c0 < chunk) ? end - c0 : chunk;
+		double *stage = (double *)b200_scratch(2, sizeof(double) * (size_t)n * k);
+		if (!stage) return 1;
+		B200_CUDA(cudaMemcpy2DAsync(stage, sizeof(double) * n, host + (size_t)(c0 - start) * ld,
+		                            sizeof(double) * (size_t)ld, sizeof(double) * n, k,
+		                            cudaMemcpyHostToDevice, g_b200.stream));
+		if (b200k_cm_to_rm(n, k, stage, n, x->d + c0, x->ld)) return 1;
+		// the staging buffer is reused by the next chunk and host memory is pageable
+		B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	}
+	return 0;
+}
+
+extern "C" int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	           "b200_mv_download: bad arguments");
+	const long long n = x->nrows;
+	if (n == 0 || end == start) return 0;
+	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));
+	if (chunk < 1) chunk = 1;
+	for (int c0 = start; c0 < end; c0 += chunk) {
+		const int k = (end - c0 < chunk) ? end - c0 : chunk;
+		double *stage = (double *)b200_scratch(2, sizeof(double) * (size_t)n * k);
+		if (!stage) return 1;
+		if (b200k_rm_to_cm(n, k, x->d + c0, x->ld, stage, n)) return 1;
+		B200_CUDA(cudaMemcpy2DAsync(host + (size_t)(c0 - start) * ld, sizeof(double) * (size_t)ld, stage,
+		                            sizeof(double) * n, sizeof(double) * n, k, cudaMemcpyDeviceToHost,
+		                            g_b200.stream));
+		B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	}
+	return 0;
+}
+
+// glibc rand() stream, column-major order (reference app/app_lapack.c:322-333).  The values
+// are produced on the host, in the reference's order, from the process-wide generator the
+// reference's drivers seed with srand(0) (reference test/test_eig_sol_gcg.c:87), then staged.
+extern "C" int b200_mv_set_random(b200_mv *x, int start, int end)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && start >= 0 && end <= x->ncols && start <= end, "b200_mv_set_random: bad arguments");
+	const long long n = x->nrows;
+	if (n == 0 || end == start) return 0;
+	int chunk = (int)(((size_t)64 << 20) / (sizeof(double) * (size_t)n));
+	if (chunk < 1) chunk = 1;
+	for (int c0 = start; c0 < end; c0 += chunk) {
+		const int k = (end - c0 < chunk) ? end - c0 : chunk;
+		double *h = (double *)b200_pinned(1, sizeof(double) * (size_t)n * k);
+		double *stage = (double *)b200_scratch(2, sizeof(double) * (size_t)n * k);
+		if (!h || !stage) return 1;
+		const size_t tot = (size_t)n * k;
+		for (size_t i = 0; i < tot; ++i) h[i] = ((double)rand()) / ((double)RAND_MAX + 1);
+		B200_CUDA(cudaMemcpyAsync(stage, h, sizeof(double) * tot, cudaMemcpyHostToDevice, g_b200.stream));
+		if (b200k_cm_to_rm(n, k, stage, n, x->d + c0, x->ld)) return 1;
+		B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------ axpby
+// One CTA handles ROWS_PER_CTA consecutive rows of the n x k block; threads walk the
+// block's elements in memory order (column fastest), so each row contributes one
+// contiguous k*8-byte segment per warp request.
+template <bool HAS_X, bool HAS_Y>
+__global__ void axpby_kernel(long long n, int k, int rows_per_cta, double alpha, const double *x, int ldx,
+                             double beta, double *y, int ldy)
+{
+	const long long r0 = (long long)blockIdx.x * rows_per_cta;
+	long long nr = n - r0; if (nr > rows_per_cta) nr = rows_per_cta;
+	const int total = (int)nr * k;
+	for (int i = threadIdx.x; i < total; i += blockDim.x) {
+		const int r = i / k, c = i - r * k;
+		const size_t yo = (size_t)(r0 + r) * ldy + c;
+		double v = 0.0;
+		if (HAS_Y) { v = y[yo]; if (beta != 1.0) v *= beta; }
+		if (HAS_X) v = fma(alpha, x[(size_t)(r0 + r) * ldx + c], v);
+		y[yo] = v;
+	}
+}
+
+int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx, double beta, double *y, int ldy)
+{
+	if (n <= 0 || k <= 0) return 0;
+	const bool has_x = (x != nullptr);
+	const bool has_y = (beta != 0.0);
+	if (!has_x && has_y && beta == 1.0) return 0;
+	int rows = 4096 / k; if (rows < 1) rows = 1;
+	const unsigned grid = (unsigned)((n + rows - 1) / rows);
+	const int threads = 256;
+	cudaStream_t st = g_b200.stream;
+	if (has_x && has_y)       axpby_kernel<true, true><<<grid, threads, 0, st>>>(n, k, rows, alpha, x, ldx, beta, y, ldy);
+	else if (has_x && !has_y) axpby_kernel<true, false><<<grid, threads, 0, st>>>(n, k, rows, alpha, x, ldx, beta, y, ldy);
+	else if (!has_x && has_y) axpby_kernel<false, true><<<grid, threads, 0, st>>>(n, k, rows, alpha, x, ldx, beta, y, ldy);
+	else                      axpby_kernel<false, false><<<grid, threads, 0, st>>>(n, k, rows, alpha, x, ldx, beta, y, ldy);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+extern "C" int b200_mv_axpby(double alpha, const b200_mv *x, double beta, b200_mv *y,
+                             const int *start, const int *end)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(y && start && end, "b200_mv_axpby: bad arguments");
+	const int k = end[1] - start[1];
+	B200_CHECK(end[0] - start[0] == k, "b200_mv_axpby: column counts differ (%d vs %d)", end[0] - start[0], k);
+	if (k == 0 || y->nrows == 0) return 0;
+	B200_CHECK(start[1] >= 0 && end[1] <= y->ncols, "b200_mv_axpby: y range [%d,%d) outside %d columns",
+	           start[1], end[1], y->ncols);
+	if (x) {
+		B200_CHECK(x->nrows == y->nrows, "b200_mv_axpby: row counts differ");
+		B200_CHECK(start[0] >= 0 && end[0] <= x->ncols, "b200_mv_axpby: x range [%d,%d) outside %d columns",
+		           start[0], end[0], x->ncols);
+		if (x == y) {
+			// same multi-vector: ranges must not overlap unless identical (reference uses
+			// disjoint column copies, src/ops_orth.c:70,302)
+			const bool overlap = start[0] < end[1] && start[1] < end[0];
+			B200_CHECK(!overlap || start[0] == start[1], "b200_mv_axpby: overlapping column ranges on one multi-vector");
+		}
+	}
+	return b200k_axpby(y->nrows, k, alpha, x ? x->d + start[0] : nullptr, x ? x->ld : 0, beta,
+	                   y->d + start[1], y->ld);
+}

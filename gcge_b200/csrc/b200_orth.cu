@@ -1,0 +1,90 @@
+// K6 (panel part): the self-orthogonalisation recurrence of the reference's OrthSelf
+// (src/ops_orth.c:45-118) carried out on the k x k Gram matrix instead of on the n x k
+// panel.  OrthSelf walks the columns one by one -- norm, scale, project out of the later
+// columns -- and every step streams the panel through memory.  The same recurrence applied
+// to G = X^T B X is a right-looking Cholesky factorisation; it yields the k x k map T with
+// X_orth = X T, so the panel is read once for G and once for the update.  The drop rule is
+// the reference's: r_k < orth_zero_tol => the last live column is swapped in and the block
+// shrinks (src/ops_orth.c:64-73).  One CTA; k <= 128.
+#include "b200_internal.h"
+
+__global__ void __launch_bounds__(256)
+chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out)
+{
+	extern __shared__ double sm[];
+	const int S = k + 1;
+	double *G = sm, *T = sm + (size_t)k * S, *cv = T + (size_t)k * S;
+	const int tid = threadIdx.x, nt = blockDim.x;
+	for (int i = tid; i < k * k; i += nt) {
+		const int r = i / k, c = i - r * k;
+		G[r * S + c] = g[i];
+		T[r * S + c] = (r == c) ? 1.0 : 0.0;
+	}
+	__syncthreads();
+	int pos = 0, n_live = k;
+	while (pos < n_live) {
+		const double gkk = G[pos * S + pos];
+		const double rk = gkk > 0.0 ? sqrt(gkk) : 0.0;
+		if (rk < zero_tol) {
+			const int last = n_live - 1;
+			if (pos < last) {
+				__syncthreads();
+				for (int i = tid; i < k; i += nt) {      // swap rows pos,last of G
+					const double a = G[pos * S + i]; G[pos * S + i] = G[last * S + i]; G[last * S + i] = a;
+				}
+				__syncthreads();
+				for (int i = tid; i < k; i += nt) {      // swap columns of G and of T
+					double a = G[i * S + pos]; G[i * S + pos] = G[i * S + last]; G[i * S + last] = a;
+					a = T[i * S + pos]; T[i * S + pos] = T[i * S + last]; T[i * S + last] = a;
+				}
+			}
+			--n_live;
+			__syncthreads();
+			continue;
+		}
+		const double inv = 1.0 / rk;
+		__syncthreads();                                 // everyone has read G[pos][pos]
+		for (int i = tid; i < k; i += nt) {
+			T[i * S + pos] *= inv;
+			if (i != pos) { G[pos * S + i] *= inv; G[i * S + pos] *= inv; }
+		}
+		if (tid == 0) G[pos * S + pos] = 1.0;
+		__syncthreads();
+		const int m = n_live - pos - 1;
+		for (int i = tid; i < m; i += nt) cv[i] = G[pos * S + pos + 1 + i];     // q^T B x_j
+		__syncthreads();
+		for (int i = tid; i < k * m; i += nt) {          // T[:, j] -= T[:, pos] c_j
+			const int r = i / m, j = i - r * m;
+			T[r * S + pos + 1 + j] -= T[r * S + pos] * cv[j];
+		}
+		for (int i = tid; i < m * m; i += nt) {          // G[i][j] -= c_i c_j
+			const int r = i / m, j = i - r * m;
+			G[(pos + 1 + r) * S + pos + 1 + j] -= cv[r] * cv[j];
+		}
+		__syncthreads();
+		for (int i = tid; i < k; i += nt)
+			if (i != pos) { G[pos * S + i] = 0.0; G[i * S + pos] = 0.0; }
+		__syncthreads();
+		++pos;
+	}
+	__syncthreads();
+	for (int i = tid; i < k * k; i += nt) {
+		const int r = i / k, c = i - r * k;
+		t[i] = T[r * S + c];
+	}
+	if (tid == 0) *n_live_out = n_live;
+}
+
+extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev)
+{
+	B200_CHECK(k >= 1 && k <= 128, "orth panel: %d columns (1..128 supported)", k);
+	const size_t smem = sizeof(double) * ((size_t)2 * k * (k + 1) + k);
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(chol_drop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+		attr_set = true;
+	}
+	chol_drop_kernel<<<1, 256, smem, g_b200.stream>>>(k, g_dev, zero_tol, t_dev, n_live_dev);
+	B200_KERNEL_CHECK();
+	return 0;
+}

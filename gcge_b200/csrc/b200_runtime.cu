@@ -1,0 +1,163 @@
+// Runtime: device selection, library stream, growable scratch, error reporting.
+#include "b200_internal.h"
+#include <chrono>
+
+b200_ctx g_b200 = {};
+
+extern "C" int b200_fail(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_b200.err, sizeof(g_b200.err), fmt, ap);
+	va_end(ap);
+	return 1;
+}
+
+extern "C" const char *b200_last_error(void) { return g_b200.err; }
+
+extern "C" int b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" int b200_init(int device)
+{
+	if (g_b200.initialised && (device < 0 || device == g_b200.device)) return 0;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return b200_fail("b200_init: no CUDA device (%s); this library has no CPU fallback",
+		                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		device = lr ? atoi(lr) % n : 0;
+	}
+	B200_CHECK(device < n, "b200_init: device %d out of range (%d visible)", device, n);
+	B200_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	B200_CUDA(cudaGetDeviceProperties(&prop, device));
+	B200_CHECK(prop.major >= 10, "b200_init: device %d is sm_%d%d; this library is built for sm_100a only",
+	           device, prop.major, prop.minor);
+	if (g_b200.initialised) b200_finalize();
+	g_b200.device = device;
+	g_b200.num_sms = prop.multiProcessorCount;
+	B200_CUDA(cudaStreamCreateWithFlags(&g_b200.stream, cudaStreamNonBlocking));
+	g_b200.launches = 0;
+	g_b200.initialised = 1;
+	return 0;
+}
+
+extern "C" void b200_finalize(void)
+{
+	if (!g_b200.initialised) return;
+	cudaStreamSynchronize(g_b200.stream);
+	for (int i = 0; i < 6; ++i) {
+		if (g_b200.scratch[i]) cudaFree(g_b200.scratch[i]);
+		g_b200.scratch[i] = nullptr; g_b200.scratch_bytes[i] = 0;
+	}
+	for (int i = 0; i < 2; ++i) {
+		if (g_b200.pinned[i]) cudaFreeHost(g_b200.pinned[i]);
+		g_b200.pinned[i] = nullptr; g_b200.pinned_bytes[i] = 0;
+	}
+	cudaStreamDestroy(g_b200.stream);
+	g_b200.initialised = 0;
+}
+
+extern "C" void *b200_scratch(int slot, size_t bytes)
+{
+	if (bytes <= g_b200.scratch_bytes[slot]) return g_b200.scratch[slot];
+	// growing a slot: every kernel that used the old buffer must be done first
+	cudaStreamSynchronize(g_b200.stream);
+	if (g_b200.scratch[slot]) cudaFree(g_b200.scratch[slot]);
+	g_b200.scratch[slot] = nullptr; g_b200.scratch_bytes[slot] = 0;
+	size_t want = bytes + bytes / 4 + 4096;
+	cudaError_t e = cudaMalloc(&g_b200.scratch[slot], want);
+	if (e != cudaSuccess) {
+		b200_fail("scratch[%d]: cudaMalloc(%zu) failed: %s", slot, want, cudaGetErrorString(e));
+		return nullptr;
+	}
+	g_b200.scratch_bytes[slot] = want;
+	return g_b200.scratch[slot];
+}
+
+extern "C" void *b200_pinned(int slot, size_t bytes)
+{
+	if (bytes <= g_b200.pinned_bytes[slot]) return g_b200.pinned[slot];
+	cudaStreamSynchronize(g_b200.stream);
+	if (g_b200.pinned[slot]) cudaFreeHost(g_b200.pinned[slot]);
+	g_b200.pinned[slot] = nullptr; g_b200.pinned_bytes[slot] = 0;
+	size_t want = bytes + bytes / 4 + 4096;
+	cudaError_t e = cudaMallocHost(&g_b200.pinned[slot], want);
+	if (e != cudaSuccess) {
+		b200_fail("pinned[%d]: cudaMallocHost(%zu) failed: %s", slot, want, cudaGetErrorString(e));
+		return nullptr;
+	}
+	g_b200.pinned_bytes[slot] = want;
+	return g_b200.pinned[slot];
+}
+
+extern "C" int b200_sync(void)
+{
+	B200_REQUIRE_INIT();
+	B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	return 0;
+}
+
+extern "C" double b200_wtime(void)
+{
+	if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
+	using clk = std::chrono::steady_clock;
+	return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
+}
+
+extern "C" long long b200_kernel_launches(void) { return g_b200.launches; }
+
+extern "C" int b200k_num_sms(void) { return g_b200.num_sms; }
+
+extern "C" int b200k_d2h(void *host, const void *dev, size_t bytes)
+{
+	if (bytes == 0) return 0;
+	void *pin = b200_pinned(0, bytes);
+	if (!pin) return 1;
+	B200_CUDA(cudaMemcpyAsync(pin, dev, bytes, cudaMemcpyDeviceToHost, g_b200.stream));
+	B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	memcpy(host, pin, bytes);
+	return 0;
+}
+
+extern "C" int b200k_h2d(void *dev, const void *host, size_t bytes)
+{
+	if (bytes == 0) return 0;
+	B200_CUDA(cudaStreamSynchronize(g_b200.stream));   // pinned staging may still be in flight
+	void *pin = b200_pinned(0, bytes);
+	if (!pin) return 1;
+	memcpy(pin, host, bytes);
+	B200_CUDA(cudaMemcpyAsync(dev, pin, bytes, cudaMemcpyHostToDevice, g_b200.stream));
+	return 0;
+}
+
+extern "C" int b200k_memset(void *dev, int value, size_t bytes)
+{
+	if (bytes == 0) return 0;
+	B200_CUDA(cudaMemsetAsync(dev, value, bytes, g_b200.stream));
+	return 0;
+}
+
+extern "C" int b200k_malloc(void **dev, size_t bytes)
+{
+	B200_REQUIRE_INIT();
+	cudaError_t e = cudaMalloc(dev, bytes ? bytes : 8);
+	if (e != cudaSuccess) return b200_fail("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	B200_CUDA(cudaMemsetAsync(*dev, 0, bytes ? bytes : 8, g_b200.stream));
+	return 0;
+}
+
+extern "C" int b200k_free(void *dev)
+{
+	if (!dev) return 0;
+	if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
+	cudaFree(dev);
+	return 0;
+}

@@ -1,0 +1,103 @@
+// K1: CSR SpMM  y[:, 0:k] = A x[:, 0:k]  on row-major multi-vector blocks.
+//
+// Replaces the reference's column-parallel CCS scatter loop (app/app_ccs.c:116-131), which
+// streams the whole matrix once PER COLUMN.  Here the matrix is read once for all k columns:
+// a group of G lanes owns one row, lane l accumulates columns l, l+G, ... so every gathered
+// x row is one contiguous k*8-byte segment (row-major store) and the matrix entry is a
+// broadcast load inside the group.  HBM-bound: algorithmic bytes per launch are
+//   nnz*(8+4) + (n+1)*4 + 8*n*k (x, read once) + 8*n*k (y, written once)       
+//
+// Arithmetic: separate multiply and add (no FMA contraction), entries of a row visited in
+// ascending column order -- the same operation sequence as the reference's serial scatter,
+// so the result is bit-identical to the reference on every input.
+#include "b200_internal.h"
+
+template <int G, int CPL>
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
+                const double *__restrict__ va, const double *x, int ldx, double *y, int ldy, int k,
+                const int *__restrict__ gate)
+{
+	if (gate != nullptr && *gate == 0) return;
+	const int gl = threadIdx.x % G;                          // lane inside the row group
+	const int groups_per_cta = 256 / G;
+	const long long row = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;
+	if (row >= nrows) return;
+	const int e0 = __ldg(rp + row), e1 = __ldg(rp + row + 1);
+	for (int cbase = 0; cbase < k; cbase += G * CPL) {
+		double acc[CPL];
+		bool on[CPL];
+#pragma unroll
+		for (int i = 0; i < CPL; ++i) { acc[i] = 0.0; on[i] = (cbase + gl + i * G) < k; }
+		for (int e = e0; e < e1; ++e) {
+			const double a = __ldg(va + e);
+			const double *xr = x + (size_t)__ldg(ci + e) * ldx + cbase + gl;
+#pragma unroll
+			for (int i = 0; i < CPL; ++i)
+				if (on[i]) acc[i] = __dadd_rn(acc[i], __dmul_rn(a, xr[i * G]));
+		}
+		double *yr = y + (size_t)row * ldy + cbase + gl;
+#pragma unroll
+		for (int i = 0; i < CPL; ++i)
+			if (on[i]) yr[i * G] = acc[i];
+	}
+}
+
+template <int G, int CPL>
+static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va,
+                       const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const int groups_per_cta = 256 / G;
+	const unsigned grid = (unsigned)(((long long)nrows + groups_per_cta - 1) / groups_per_cta);
+	spmm_csr_kernel<G, CPL><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+int b200k_spmm(int nrows, const int *rp, const int *ci, const double *va,
+               const double *x, int ldx, double *y, int ldy, int k)
+{
+	return b200k_spmm_gated(nrows, rp, ci, va, x, ldx, y, ldy, k, nullptr);
+}
+
+int b200k_spmm_gated(int nrows, const int *rp, const int *ci, const double *va,
+                     const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	if (nrows <= 0 || k <= 0) return 0;
+	if (k == 1)       return launch_spmm<1, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k == 2)  return launch_spmm<2, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 4)  return launch_spmm<4, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 8)  return launch_spmm<8, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 16) return launch_spmm<16, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 32) return launch_spmm<32, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 64) return launch_spmm<32, 2>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	return launch_spmm<32, 4>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+}
+
+extern "C" int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv *x, b200_mv *y,
+                                     const int *start, const int *end)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && y && start && end, "b200_mat_dot_multivec: bad arguments");
+	const int k = end[0] - start[0];
+	B200_CHECK(k == end[1] - start[1], "b200_mat_dot_multivec: column counts differ (%d vs %d)", k,
+	           end[1] - start[1]);
+	if (k == 0) return 0;
+	B200_CHECK(start[0] >= 0 && end[0] <= x->ncols && start[1] >= 0 && end[1] <= y->ncols,
+	           "b200_mat_dot_multivec: column range out of bounds");
+	if (!A) {
+		// reference app/app_ccs.c:134-137: NULL matrix means copy
+		B200_CHECK(x->nrows == y->nrows, "b200_mat_dot_multivec: row counts differ");
+		return b200k_axpby(y->nrows, k, 1.0, x->d + start[0], x->ld, 0.0, y->d + start[1], y->ld);
+	}
+	const int out_rows = trans ? A->ncols : A->nrows, in_rows = trans ? A->nrows : A->ncols;
+	B200_CHECK(x->nrows == in_rows && y->nrows == out_rows,
+	           "b200_mat_dot_multivec: shapes do not match the matrix (%d x %d)", A->nrows, A->ncols);
+	if (x == y) {
+		const bool overlap = start[0] < end[1] && start[1] < end[0];
+		B200_CHECK(!overlap, "b200_mat_dot_multivec: x and y column ranges overlap on one multi-vector");
+	}
+	if (trans)
+		return b200k_spmm(A->ncols, A->t_rp, A->t_ci, A->t_va, x->d + start[0], x->ld, y->d + start[1], y->ld, k);
+	return b200k_spmm(A->nrows, A->rp, A->ci, A->va, x->d + start[0], x->ld, y->d + start[1], y->ld, k);
+}

@@ -1,0 +1,127 @@
+/* b200_dev.h -- the thin C layer between the host-side C drivers (b200_orth.c,
+ * b200_bpcg.c, b200_gcg.c) and the CUDA kernels.  Everything here takes raw DEVICE
+ * pointers to row-major blocks (pointer to the first element, leading dimension) and
+ * only enqueues work on the library stream; nothing synchronises unless it says so.
+ * Public, reference-facing surface: include/gcge_b200.h.
+ */
+#ifndef B200_DEV_H_
+#define B200_DEV_H_
+
+#include <stddef.h>
+#include "gcge_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct b200_mat_ {
+	int nrows, ncols, nnz;
+	/* CSR of A: row r holds entries rp[r]..rp[r+1] in ascending column order -- the order
+	 * in which the reference's CCS scatter loop (app/app_ccs.c:116-131) adds into y[r]. */
+	int *rp; int *ci; double *va;
+	/* the caller's CCS arrays verbatim (== CSR of A^T): A^T x and the bit-exact round
+	 * trip; shares storage with the CSR image when the two coincide (t_shared). */
+	int *t_rp; int *t_ci; double *t_va;
+	int t_shared;
+	int row0;
+};
+
+struct b200_mv_ {
+	int nrows, ncols, ld;
+	double *d;
+	int owner;          /* 0: view into another multi-vector's storage */
+};
+
+int  b200_fail(const char *fmt, ...);
+void *b200_scratch(int slot, size_t bytes);   /* growable device scratch; NULL on failure */
+void *b200_pinned(int slot, size_t bytes);    /* growable pinned host staging */
+int  b200k_num_sms(void);
+
+/* synchronising small transfers */
+int b200k_d2h(void *host, const void *dev, size_t bytes);
+int b200k_h2d(void *dev, const void *host, size_t bytes);
+int b200k_memset(void *dev, int value, size_t bytes);
+int b200k_malloc(void **dev, size_t bytes);
+int b200k_free(void *dev);
+
+/* y = A x for k columns; separate multiply and add in CSR column order (bit-exact with
+ * the reference's scatter loop).  x, y may live in one multi-vector (disjoint columns). */
+int b200k_spmm(int nrows, const int *rp, const int *ci, const double *va,
+               const double *x, int ldx, double *y, int ldy, int k);
+/* same, but the kernel returns immediately when *gate_dev == 0 (device-side loop control) */
+int b200k_spmm_gated(int nrows, const int *rp, const int *ci, const double *va,
+                     const double *x, int ldx, double *y, int ldy, int k, const int *gate_dev);
+/* y = alpha x + beta y over n x k; x may be NULL (scale); beta == 0 overwrites. */
+int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx,
+                double beta, double *y, int ldy);
+/* C(p x q, device, element (i,j) at c[i*c_rs + j*c_cs]) = alpha X^T Y over n rows;
+ * mode 'N', 'S' (lower triangle mirrored) or 'D' (dots: c[i*(c_rs+c_cs)]... see .cu). */
+int b200k_gram(char mode, long long n, int p, int q, double alpha, const double *x, int ldx,
+               const double *y, int ldy, double *c_dev, int c_rs, int c_cs);
+/* Y(n x q) = X(n x p) C + Y diag(beta); C device, element (k,j) at c[k*c_rs + j*c_cs];
+ * beta_dev NULL => 0 (overwrite) else beta_dev[incb*col]; x or c NULL => scaling only. */
+int b200k_lincomb(long long n, int p, int q, const double *x, int ldx,
+                  const double *c_dev, int c_rs, int c_cs,
+                  const double *beta_dev, int incb, double *y, int ldy);
+/* column scaling y[:,j] *= s_dev[j] (or by 1/s_dev[j] when invert != 0) */
+int b200k_colscale(long long n, int q, const double *s_dev, int invert, double *y, int ldy);
+/* column-major (ld_cm) <-> row-major (ld_rm) transposes of an n x k block, on device */
+int b200k_cm_to_rm(long long n, int k, const double *cm, long long ld_cm, double *rm, int ld_rm);
+int b200k_rm_to_cm(long long n, int k, const double *rm, int ld_rm, double *cm, long long ld_cm);
+
+/* ---- orthogonalisation panel (b200_orth.cu) ----------------------------------------
+ * Right-looking Cholesky of the k x k Gram matrix g (row-major, ld k, destroyed) with the
+ * reference's drop rule (r_k < zero_tol: swap the last live column in, shrink; reference
+ * src/ops_orth.c:64-73).  Writes T (k x k, element (i,j) at t[i*k+j]) with
+ * X_new[:, 0:n_live] = X T[:, 0:n_live], and n_live to *n_live_dev. */
+int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev);
+
+/* ---- BlockPCG (b200_bpcg.cu): device-resident scalars and masks ----------------------- */
+typedef struct b200_bpcg_state_ {
+	int k;
+	double *norm_b, *rho1, *rho2, *ptw, *init_res, *last_res;   /* k doubles each (device) */
+	int *active;        /* k ints (device): 1 while the column is unconverged */
+	int *counters;      /* [0] number of active columns, [1] iterations done (device) */
+	double *partials;   /* reduction scratch */
+	unsigned *tickets;  /* last-block election counters */
+} b200_bpcg_state;
+int b200k_bpcg_state(int k, b200_bpcg_state *st);               /* carve state out of scratch */
+/* r = b - r (r holds A x on entry); rho2 = diag(r^T r); norm_b = 1 or ||b||; then decide the
+ * initial active set: init_res > tol*norm_b (reference src/ops_lin_sol.c:221-247) */
+int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const double *b, int ldb,
+                     double *r, int ldr, double tol, int rel);
+/* p = r + (rho2/rho1) p on active columns (beta = 0 on the first iteration) */
+int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const double *r, int ldr,
+                        double *p, int ldp, int first);
+/* w += shift * z (optional), ptw = diag(p^T w) */
+int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const double *p, int ldp,
+                   double *w, int ldw, double shift, const double *z, int ldz);
+/* alpha = rho2/ptw; x += alpha p; r -= alpha w; rho1 = rho2; rho2 = diag(r^T r);
+ * then the per-column stop test (reference src/ops_lin_sol.c:383-394) and ++iterations */
+int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, const double *p, int ldp,
+                         const double *w, int ldw, double *x, int ldx, double *r, int ldr,
+                         double rate, double tol);
+
+/* ---- projected eigenproblem (b200_syev.cu) --------------------------------------------
+ * All eigenpairs of the symmetric n x n device matrix a (element (i,j) at a[i*lda+j]; both
+ * triangles must be filled), ascending in w_dev; eigenvector j in column j of z (element
+ * (i,j) at z[i*ldz+j]).  a is destroyed.  Parallel-order cyclic Jacobi, cooperative grid. */
+int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
+                      int *sweeps_host);
+
+/* ---- GCG helpers (b200_gcgk.cu) --------------------------------------------------------- */
+/* res[j] = || ax[:,j] - lam[j] * bx[:,j] ||_2 ; ax is overwritten with the residual */
+int b200k_residual_norms(long long n, int k, double *ax, int ldax, const double *bx, int ldbx,
+                         const double *lam_dev, double *res_dev);
+/* generic small elementwise helpers on device matrices */
+int b200k_copy2d(int rows, int cols, const double *src, int s_rs, int s_cs, double *dst, int d_rs, int d_cs);
+int b200k_set_diag(int n, double *a, int lda, const double *d, double shift);   /* a[i,i] = d[i]+shift (d NULL: += shift) */
+int b200k_symmetrize_upper(int n, double *a, int lda);                          /* a[i,j] = a[j,i] for i > j */
+int b200k_zero_rows(int nidx, const int *idx_dev, int cols, double *a, int rs, int cs); /* a[idx[i], 0:cols] = 0 */
+int b200k_gather_cols(int rows, int nidx, const int *idx_dev, const double *src, int s_rs, int s_cs,
+                      double *dst, int d_rs, int d_cs);                         /* dst[:, i] = src[:, idx[i]] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,452 @@
+/* b200_gcg.c -- host driver of the device-resident block GCG eigensolver (C-ABI b200_gcg_solve).
+ *
+ * Follows GCG() of the reference (src/ops_eig_sol_gcg.c:1253-1558) phase by phase --
+ * InitializeX :101, ComputeRayleighRitz :925, ComputeRitzVec :159, CheckConvergence :195,
+ * ComputeP :316, ComputeX :458, ComputeW :472 -- with the same state variables
+ * (V = [X | P | W], sizeC/sizeN/sizeX/sizeP/sizeW, startN/endN ...), the same parameters
+ * (GCGSolver, src/ops_eig_sol_gcg.h:26-52) and the same stopping logic.  What changes is
+ * where the data lives: the projected matrix ss_matA, the Ritz coefficients ss_evec, the
+ * P coefficients and every Gram block stay in HBM; the projected eigenproblem is solved by
+ * the device Jacobi kernel; BlockPCG and the orthogonalisation are the fused device
+ * providers.  Per outer iteration the host reads back only the Ritz values (N doubles), the
+ * residual norms of the checked columns and a few block sizes -- it needs them to steer the
+ * loop exactly like the reference does.
+ *
+ * Small dense objects are ROW-major on device with a fixed leading dimension ldE
+ * (element (i,j) at base[i*ldE + j]), so an N x N coefficient matrix is at the same time a
+ * row-major "multi-vector" with N rows: the projected-space orthogonalisation of ComputeP
+ * (reference :371-414, done there on the host through lapack_ops) reuses b200_mv_orth.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#include "b200_dev.h"
+
+#define TRY(call) do { if ((call) != 0) return 1; } while (0)
+
+typedef struct {
+	const b200_mat *A, *B;
+	const b200_gcg_params *p;
+	b200_mv *V, *ritz, *ws[3];
+	int own_ws;
+	long long n;
+	/* reference file-scope state, src/ops_eig_sol_gcg.c:44-54 */
+	int sizeN, startN, endN, sizeP, startP, endP, sizeW, startW, endW, sizeC, sizeX, sizeV, endX;
+	/* device small dense */
+	int ldE, Nmax;
+	double *eval_d;      /* nevMax + 2 bs */
+	double *matA_d;      /* Nmax x ldE, symmetric, both triangles */
+	double *evec_d;      /* Nmax x ldE */
+	double *t1_d;        /* Nmax x bsp   (matA * Pc) */
+	double *ptap_d;      /* bs x bs */
+	double *wsE_d;       /* Nmax x bsp   (orth workspace in coefficient space) */
+	double *res_d;       /* bs */
+	double *scal_d;      /* bs  (lambda + sigma) */
+	int    *idx_d;       /* bs */
+	int bsp;
+	/* host mirrors */
+	double *eval_h, *res_h;
+	int *offP, *offW;    /* [0] = count, then pairs; reference offsetP/offsetW */
+	b200_gcg_stats st;
+	int timing;
+} gcg_t;
+
+static double tick(gcg_t *g) { return g->timing ? b200_wtime() : 0.0; }
+
+static int spmm_mv(const b200_mat *M, const double *x, int ldx, double *y, int ldy, long long n, int k)
+{
+	if (M) return b200k_spmm(M->nrows, M->rp, M->ci, M->va, x, ldx, y, ldy, k);
+	return b200k_axpby(n, k, 1.0, x, ldx, 0.0, y, ldy);      /* NULL matrix == identity, reference app/app_ccs.c:134-137 */
+}
+
+/* ---- ComputeRayleighRitz, reference :925-1252 ------------------------------------------- */
+static int rayleigh_ritz(gcg_t *g, int nevConv)
+{
+	const b200_gcg_params *p = g->p;
+	const int ldE = g->ldE, bs = p->block_size;
+	double t0 = tick(g);
+	if (g->sizeP > 0) {
+		/* P^T (old projected matrix) P, reference :936-949 */
+		const int Nold = g->sizeV - g->sizeC, c0 = g->sizeX - g->sizeC;
+		TRY(b200k_lincomb(Nold, Nold, g->sizeP, g->matA_d, ldE, g->evec_d + c0, ldE, 1, NULL, 0, g->t1_d, g->bsp));
+		TRY(b200k_gram('N', Nold, g->sizeP, g->sizeP, 1.0, g->evec_d + c0, ldE, g->t1_d, g->bsp, g->ptap_d, bs, 1));
+	}
+	g->sizeV  = g->sizeX + g->sizeP + g->sizeW;
+	g->startN = g->startN + (nevConv - g->sizeC);
+	g->endN   = g->endN + (nevConv - g->sizeC);
+	if (g->endN > g->endX) g->endN = g->endX;
+	g->sizeN  = g->endN - g->startN;
+	g->sizeC  = nevConv;
+	const int N = g->sizeV - g->sizeC;
+	TRY(b200k_memset(g->matA_d, 0, sizeof(double) * (size_t)N * ldE));
+	if (g->sizeW > 0) {
+		/* V[:,startN:endW]^T A V[:,startW:endW]: one SpMM + one Gram, reference :970-987 */
+		const int c0 = g->sizeX + g->sizeP - g->sizeC;
+		TRY(spmm_mv(g->A, g->V->d + g->startW, g->V->ld, g->ws[0]->d, g->ws[0]->ld, g->n, g->sizeW));
+		TRY(b200k_gram('N', g->n, N, g->sizeW, 1.0, g->V->d + g->startN, g->V->ld, g->ws[0]->d, g->ws[0]->ld,
+		               g->matA_d + c0, ldE, 1));
+	}
+	if (g->sizeX == g->sizeV) {
+		/* first call: full X^T A X by block_size-wide panels, reference :989-1011 */
+		int length = g->sizeX - g->sizeC, c = g->sizeC;
+		while (length > 0) {
+			const int w = bs < length ? bs : length;
+			TRY(spmm_mv(g->A, g->V->d + c, g->V->ld, g->ws[0]->d, g->ws[0]->ld, g->n, w));
+			TRY(b200k_gram('N', g->n, g->sizeX - g->sizeC, w, 1.0, g->V->d + g->sizeC, g->V->ld,
+			               g->ws[0]->d, g->ws[0]->ld, g->matA_d + (c - g->sizeC), ldE, 1));
+			c += w; length -= w;
+		}
+	} else {
+		/* diag(X part) = Ritz values, P^T A P block, reference :1013-1033 */
+		const int nx = g->sizeX - g->sizeC;
+		TRY(b200k_set_diag(nx, g->matA_d, ldE, g->eval_d + g->sizeC, 0.0));
+		if (g->sizeP > 0)
+			TRY(b200k_copy2d(g->sizeP, g->sizeP, g->ptap_d, bs, 1, g->matA_d + (size_t)nx * ldE + nx, ldE, 1));
+	}
+	/* the reference hands dsyevx the UPPER triangle (UPLO='U', :1186): make both triangles agree */
+	TRY(b200k_symmetrize_upper(N, g->matA_d, ldE));
+	double t2 = tick(g);
+	/* projected eigenproblem on device (replaces dsyevx, reference :1201); optional shift :1043-1050 */
+	if (p->compW_cg_shift != 0.0) TRY(b200k_set_diag(N, g->matA_d, ldE, NULL, p->compW_cg_shift));
+	TRY(b200k_syev_jacobi(N, g->matA_d, ldE, g->eval_d + g->sizeC, g->evec_d, ldE, NULL));
+	if (p->compW_cg_shift != 0.0) TRY(b200k_set_diag(N, g->matA_d, ldE, NULL, -p->compW_cg_shift));
+	TRY(b200k_d2h(g->eval_h + g->sizeC, g->eval_d + g->sizeC, sizeof(double) * (size_t)N));
+	if (p->compW_cg_shift != 0.0)
+		for (int i = 0; i < N; ++i) g->eval_h[g->sizeC + i] -= p->compW_cg_shift;
+	/* reference :1353-1355 / :1488-1490 */
+	for (int i = g->sizeV; i < p->nevMax + 2 * bs; ++i) g->eval_h[i] = g->eval_h[g->sizeV - 1];
+	TRY(b200k_h2d(g->eval_d, g->eval_h, sizeof(double) * (size_t)(p->nevMax + 2 * bs)));
+	double t3 = tick(g);
+	g->st.compRR += t3 - t0; g->st.rr_eig += t3 - t2;
+	return 0;
+}
+
+/* ---- ComputeRitzVec, reference :159-194 ------------------------------------------------------ */
+static int compute_ritz_vec(gcg_t *g)
+{
+	double t0 = tick(g);
+	const int N = g->sizeV - g->sizeC;
+	TRY(b200k_lincomb(g->n, N, g->endX - g->startN, g->V->d + g->startN, g->V->ld, g->evec_d, g->ldE, 1,
+	                  NULL, 0, g->ritz->d + g->startN, g->ritz->ld));
+	g->st.compRV += tick(g) - t0;
+	return 0;
+}
+
+/* ---- CheckConvergence, reference :195-315 ------------------------------------------------------ */
+static int check_convergence(gcg_t *g, int numCheck, int *offset, int *nevConv_out)
+{
+	const b200_gcg_params *p = g->p;
+	const double *tol = p->tol, *ev = g->eval_h;
+	double *res = g->res_h;
+	double t0 = tick(g);
+	if (numCheck > 0) {
+		const double *x = g->ritz->d + g->startN;
+		TRY(spmm_mv(g->A, x, g->ritz->ld, g->ws[0]->d, g->ws[0]->ld, g->n, numCheck));
+		const double *bx = x; int ldbx = g->ritz->ld;
+		if (g->B) {
+			TRY(spmm_mv(g->B, x, g->ritz->ld, g->ws[1]->d, g->ws[1]->ld, g->n, numCheck));
+			bx = g->ws[1]->d; ldbx = g->ws[1]->ld;
+		}
+		TRY(b200k_residual_norms(g->n, numCheck, g->ws[0]->d, g->ws[0]->ld, bx, ldbx, g->eval_d + g->startN, g->res_d));
+		TRY(b200k_d2h(res, g->res_d, sizeof(double) * (size_t)numCheck));
+	}
+	int idx;
+	for (idx = 0; idx < numCheck; ++idx) {
+		const double lam = fabs(ev[g->startN + idx]);
+		if (lam > tol[1]) {
+			if (res[idx] > tol[0] || res[idx] > lam * tol[1]) break;
+		} else if (res[idx] > tol[0]) break;
+	}
+	if (p->verbose && idx < numCheck)
+		printf("GCG: [%d] %6.14e (%6.4e, %6.4e)\n", g->startN + idx, ev[g->startN + idx], res[idx],
+		       res[idx] / fabs(ev[g->startN + idx]));
+	for (; idx > 0; --idx) {      /* never split a cluster, reference :253-259 */
+		if (fabs((ev[g->startN + idx - 1] - ev[g->startN + idx]) / ev[g->startN + idx - 1]) > p->gapMin) break;
+	}
+	const int nevConv = g->sizeC + idx;
+	/* blocks of unconverged indices, reference :262-302 */
+	int state = 1, num_unconv = 0;
+	offset[0] = 0;
+	for (idx = 0; idx < numCheck; ++idx) {
+		if (res[idx] > tol[0] || res[idx] > fabs(ev[g->startN + idx]) * tol[1]) {
+			if (state) { offset[offset[0] * 2 + 1] = g->startN + idx; state = 0; }
+			++num_unconv;
+			if (num_unconv == g->sizeN) { offset[offset[0] * 2 + 2] = g->startN + idx + 1; ++offset[0]; break; }
+		} else if (!state) {
+			offset[offset[0] * 2 + 2] = g->startN + idx; ++offset[0]; state = 1;
+		}
+	}
+	if (num_unconv < g->sizeN) {
+		if (state == 1) offset[offset[0] * 2 + 1] = g->startN + numCheck;
+		int hi = g->startN + numCheck + g->sizeN - num_unconv;
+		if (hi > g->endX) hi = g->endX;
+		offset[offset[0] * 2 + 2] = hi;
+		if (!(offset[offset[0] * 2 + 1] < hi)) return b200_fail("gcg: empty unconverged block (reference assert :297)");
+		++offset[0];
+	}
+	if (offset[0] <= 0) return b200_fail("gcg: no unconverged block (reference assert :313)");
+	*nevConv_out = nevConv;
+	g->st.checkconv += tick(g) - t0;
+	return 0;
+}
+
+/* ---- ComputeP, reference :316-457 ------------------------------------------------------------------ */
+static int compute_p(gcg_t *g, const int *offset)
+{
+	const b200_gcg_params *p = g->p;
+	const int ldE = g->ldE;
+	double t0 = tick(g);
+	const int N = g->sizeV - g->sizeC, c0 = g->sizeX - g->sizeC;
+	int idx_h[512], np = 0;
+	for (int b = 0; b < offset[0]; ++b)
+		for (int o = offset[b * 2 + 1]; o < offset[b * 2 + 2]; ++o) idx_h[np++] = o - g->sizeC;
+	TRY(b200k_h2d(g->idx_d, idx_h, sizeof(int) * (size_t)np));
+	/* copy the Ritz coefficient columns of the unconverged block behind the X part and zero
+	 * their N-part rows, reference :329-352 */
+	TRY(b200k_gather_cols(N, np, g->idx_d, g->evec_d, ldE, 1, g->evec_d + c0, ldE, 1));
+	TRY(b200k_zero_rows(np, g->idx_d, np, g->evec_d + c0, ldE, 1));
+	/* orthonormalise them against the X coefficient columns and themselves (B = I) in
+	 * coefficient space, reference :371-414 */
+	b200_mv E, W;
+	E.nrows = N; E.ncols = c0 + np; E.ld = ldE; E.d = g->evec_d; E.owner = 0;
+	W.nrows = N; W.ncols = g->bsp; W.ld = g->bsp; W.d = g->wsE_d; W.owner = 0;
+	b200_orth_params op;
+	op.block_size = p->compP_orth_block_size; op.max_reorth = p->compP_orth_max_reorth;
+	op.orth_zero_tol = p->compP_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
+	int endP = c0 + np;
+	TRY(b200_mv_orth(&E, c0, &endP, NULL, &op, &W));
+	g->sizeP = endP - c0;
+	g->startP = g->sizeX; g->endP = g->startP + g->sizeP;
+	/* P = V[:,startN:endW] * coef, through the workspace (V is source and destination), :425-436 */
+	if (g->sizeP > 0) {
+		TRY(b200k_lincomb(g->n, N, g->sizeP, g->V->d + g->startN, g->V->ld, g->evec_d + c0, ldE, 1, NULL, 0,
+		                  g->ws[0]->d, g->ws[0]->ld));
+		TRY(b200k_axpby(g->n, g->sizeP, 1.0, g->ws[0]->d, g->ws[0]->ld, 0.0, g->V->d + g->startP, g->V->ld));
+	}
+	g->st.compP += tick(g) - t0;
+	return 0;
+}
+
+/* ---- ComputeW, reference :472-696 -------------------------------------------------------------------- */
+static int compute_w(gcg_t *g, const int *offset)
+{
+	const b200_gcg_params *p = g->p;
+	double t0 = tick(g);
+	double sigma = 0.0;
+	if (p->compW_cg_auto_shift == 1)
+		sigma = -g->eval_h[g->sizeC] + (g->eval_h[g->sizeC + 1] - g->eval_h[g->sizeC]) * 0.01;
+	sigma += p->compW_cg_shift;
+	g->startW = g->endP;
+	double scal_h[512];
+	int acc = 0;
+	for (int b = 0; b < offset[0]; ++b)
+		for (int o = offset[b * 2 + 1]; o < offset[b * 2 + 2]; ++o) scal_h[acc++] = g->eval_h[o] + sigma;
+	TRY(b200k_h2d(g->scal_d, scal_h, sizeof(double) * (size_t)acc));
+	acc = 0;
+	const int b0 = offset[1];
+	for (int b = 0; b < offset[0]; ++b) {
+		const int o1 = offset[b * 2 + 1], len = offset[b * 2 + 2] - o1;
+		/* initial guess: the Ritz vectors, :500-503 */
+		TRY(b200k_axpby(g->n, len, 1.0, g->ritz->d + o1, g->ritz->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
+		/* right-hand side (lambda+sigma) B x, stored in the Ritz-vector block like the reference, :516-534 */
+		TRY(spmm_mv(g->B, g->V->d + o1, g->V->ld, g->ritz->d + b0 + acc, g->ritz->ld, g->n, len));
+		TRY(b200k_colscale(g->n, len, g->scal_d + acc, 0, g->ritz->d + b0 + acc, g->ritz->ld));
+		acc += len;
+	}
+	g->endW = g->startW + acc;
+	double t1 = tick(g);
+	b200_bpcg_params bp;
+	bp.max_iter = p->compW_cg_max_iter; bp.rate = p->compW_cg_rate; bp.tol = p->compW_cg_tol;
+	bp.tol_type = p->compW_cg_tol_type; bp.shift = sigma;
+	int s[2], e[2];
+	s[0] = b0; e[0] = b0 + acc; s[1] = g->startW; e[1] = g->endW;
+	TRY(b200_block_pcg(g->A, g->B, g->ritz, g->V, s, e, &bp, g->ws[0], g->ws[1], g->ws[2], NULL, NULL));
+	double t2 = tick(g);
+	b200_orth_params op;
+	op.block_size = p->compW_orth_block_size; op.max_reorth = p->compW_orth_max_reorth;
+	op.orth_zero_tol = p->compW_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
+	TRY(b200_mv_orth(g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
+	g->sizeW = g->endW - g->startW;
+	double t3 = tick(g);
+	g->st.compW += t3 - t0; g->st.linsol += t2 - t1;
+	return 0;
+}
+
+void b200_gcg_default_params(int nevConv, b200_gcg_params *p)
+{
+	/* reference test/test_eig_sol_gcg.c:33-115 */
+	memset(p, 0, sizeof(*p));
+	p->nevMax = 2 * nevConv;
+	p->multiMax = 1; p->gapMin = 1e-5;
+	p->block_size = nevConv < 30 ? (p->nevMax - nevConv) : nevConv / 5;
+	p->nevInit = p->nevMax;
+	p->numIterMax = 500; p->tol[0] = 1e-1; p->tol[1] = 1e-8;
+	p->check_conv_max_num = 50;
+	p->initX_orth_block_size = 80; p->initX_orth_max_reorth = 2; p->initX_orth_zero_tol = 2 * DBL_EPSILON;
+	p->compP_orth_block_size = -1; p->compP_orth_max_reorth = 2; p->compP_orth_zero_tol = 2 * DBL_EPSILON;
+	p->compW_orth_block_size = 80; p->compW_orth_max_reorth = 2; p->compW_orth_zero_tol = 2 * DBL_EPSILON;
+	p->compW_cg_max_iter = 30; p->compW_cg_rate = 1e-2; p->compW_cg_tol = 1e-14; p->compW_cg_tol_type = 0;
+	p->compW_cg_auto_shift = 0; p->compW_cg_shift = 0.0;
+	p->compRR_tol = 2 * DBL_EPSILON;
+	p->verbose = 0;
+}
+
+static void gcg_release(gcg_t *g)
+{
+	b200k_free(g->eval_d); b200k_free(g->matA_d); b200k_free(g->evec_d); b200k_free(g->t1_d);
+	b200k_free(g->ptap_d); b200k_free(g->wsE_d); b200k_free(g->res_d); b200k_free(g->scal_d);
+	b200k_free(g->idx_d);
+	free(g->eval_h); free(g->res_h); free(g->offP); free(g->offW);
+	if (g->own_ws) {
+		b200_mv_destroy(g->V);
+		for (int i = 0; i < 3; ++i) b200_mv_destroy(g->ws[i]);
+	}
+}
+
+static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
+{
+	const b200_gcg_params *p = g->p;
+	const int bs = p->block_size, nevMax = p->nevMax, nevInit = p->nevInit;
+	/* reference asserts :1275-1280 */
+	if (!(nevInit >= nevGiven && nevInit <= nevMax && (nevInit >= 3 * bs || nevInit == nevMax) &&
+	      nevMax >= *nevConv + bs && nevMax <= *nevConv + nevInit && p->multiMax <= bs))
+		return b200_fail("gcg: inconsistent sizes nevConv=%d nevMax=%d nevInit=%d block_size=%d (reference asserts src/ops_eig_sol_gcg.c:1275-1280)",
+		                 *nevConv, nevMax, nevInit, bs);
+	int numIterMax = p->numIterMax;
+	g->sizeC = 0; g->sizeN = bs; g->sizeX = nevInit; g->sizeP = 0; g->sizeW = 0;
+	g->sizeV = g->sizeX; g->startN = 0; g->endN = bs; g->endX = g->sizeX;
+	g->startP = g->endX; g->endP = g->startP; g->startW = g->endP; g->endW = g->startW;
+	for (int i = 0; i < nevMax + 2 * bs; ++i) g->eval_h[i] = 1.0;
+	TRY(b200k_h2d(g->eval_d, g->eval_h, sizeof(double) * (size_t)(nevMax + 2 * bs)));
+
+	/* InitializeX, reference :101-158 */
+	double t0 = tick(g);
+	{
+		b200_orth_params op;
+		op.block_size = p->initX_orth_block_size; op.max_reorth = p->initX_orth_max_reorth;
+		op.orth_zero_tol = p->initX_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
+		int ng = nevGiven;
+		if (ng > 0) {
+			TRY(b200k_axpby(g->n, ng, 1.0, g->ritz->d, g->ritz->ld, 0.0, g->V->d, g->V->ld));
+			TRY(b200_mv_orth(g->V, 0, &ng, g->B, &op, g->ritz));
+		}
+		TRY(b200_mv_set_random(g->V, ng, g->sizeX));
+		TRY(b200_mv_orth(g->V, ng, &g->endX, g->B, &op, g->ritz));
+		if (g->endX != g->sizeX) return b200_fail("gcg: initial block is rank deficient (%d of %d), reference assert :143", g->endX, g->sizeX);
+	}
+	g->st.initX += tick(g) - t0;
+
+	TRY(rayleigh_ritz(g, 0));
+	TRY(compute_ritz_vec(g));
+
+	if (*nevConv > nevMax) *nevConv = nevMax;
+	const int nev0 = *nevConv; *nevConv = 0;
+	int nev = nevInit < nevMax ? 2 * bs : nev0;
+	if (nev > nev0) nev = nev0;
+	int numIter = 0, numCheck;
+	int *offsetP = g->offP, *offsetW = g->offW;
+	if (p->verbose) printf("------------------------------\nnumIter\tnevConv\n");
+	do {
+		if (numIter <= 0) numCheck = 0;
+		else numCheck = (g->startN + g->sizeN < g->endX) ? g->sizeN : (g->endX - g->startN);
+		if (numCheck > p->check_conv_max_num) numCheck = p->check_conv_max_num;
+		TRY(check_convergence(g, numCheck, offsetW, nevConv));
+		if (p->verbose) printf("%d\t%d\n", numIter, *nevConv);
+		if (*nevConv >= nev) {
+			if (*nevConv >= nev0) break;
+			/* grow X by P and W, reference :1400-1428 */
+			nev += g->sizeP + g->sizeW; if (nev > nev0) nev = nev0;
+			int newX = g->sizeX + g->sizeP + g->sizeW; if (newX > nevMax) newX = nevMax;
+			const int N = g->sizeV - g->sizeC;
+			TRY(b200k_lincomb(g->n, N, newX - g->endX, g->V->d + g->startN, g->V->ld,
+			                  g->evec_d + (g->endX - g->sizeC), g->ldE, 1, NULL, 0,
+			                  g->ritz->d + g->endX, g->ritz->ld));
+			g->sizeX = newX;
+			g->sizeP = 0; g->sizeW = 0; g->sizeV = g->sizeX;
+			g->startP = g->endX; g->endP = g->startP; g->startW = g->endP; g->endW = g->startW;
+			g->endX = g->sizeX;
+			g->endN = g->startN + bs; if (g->endN > g->endX) g->endN = g->endX;
+			g->sizeN = g->endN - g->startN;
+			numIterMax -= numIter; numIter = 0;
+		}
+		if (numIter == 0) { g->sizeP = 0; g->startP = g->endX; g->endP = g->startP; }
+		else TRY(compute_p(g, offsetP));
+		/* ComputeX, reference :458-471 */
+		t0 = tick(g);
+		TRY(b200k_axpby(g->n, g->endX - g->startN, 1.0, g->ritz->d + g->startN, g->ritz->ld, 0.0,
+		                g->V->d + g->startN, g->V->ld));
+		g->st.compX += tick(g) - t0;
+		TRY(compute_w(g, offsetW));
+		{ int *tmp = offsetP; offsetP = offsetW; offsetW = tmp; }
+		TRY(rayleigh_ritz(g, *nevConv));
+		TRY(compute_ritz_vec(g));
+		++numIter;
+	} while (numIter < numIterMax);
+	g->st.numIter = numIter + (p->numIterMax - numIterMax);
+	g->st.nevConv = *nevConv;
+	memcpy(eval, g->eval_h, sizeof(double) * (size_t)g->sizeX);      /* reference :1508 */
+	return 0;
+}
+
+int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *evec,
+                   int nevGiven, int *nevConv, const b200_gcg_params *prm, b200_mv **mv_ws,
+                   b200_gcg_stats *stats)
+{
+	if (!A || !eval || !evec || !nevConv || !prm) return b200_fail("b200_gcg_solve: bad arguments");
+	if (A->nrows != A->ncols || evec->nrows != A->nrows) return b200_fail("b200_gcg_solve: shape mismatch");
+	if (B && (B->nrows != A->nrows || B->ncols != A->ncols)) return b200_fail("b200_gcg_solve: B shape mismatch");
+	const int bs = prm->block_size, nevMax = prm->nevMax;
+	if (bs < 1 || bs > 128) return b200_fail("b200_gcg_solve: block_size %d (1..128 supported)", bs);
+	if (evec->ncols < nevMax) return b200_fail("b200_gcg_solve: evec has %d columns, nevMax = %d", evec->ncols, nevMax);
+	gcg_t g; memset(&g, 0, sizeof(g));
+	g.A = A; g.B = B; g.p = prm; g.n = A->nrows; g.ritz = evec; g.timing = 1;
+	const int sizeVmax = nevMax + 2 * bs;
+	int rc = 1;
+	if (mv_ws) {
+		g.V = mv_ws[0]; g.ws[0] = mv_ws[1]; g.ws[1] = mv_ws[2]; g.ws[2] = mv_ws[3];
+		if (!g.V || g.V->ncols < sizeVmax || g.V->nrows != A->nrows) return b200_fail("b200_gcg_solve: mv_ws[0] needs %d columns", sizeVmax);
+		for (int i = 0; i < 3; ++i)
+			if (!g.ws[i] || g.ws[i]->ncols < bs || g.ws[i]->nrows != A->nrows) return b200_fail("b200_gcg_solve: mv_ws[%d] needs %d columns", i + 1, bs);
+	} else {
+		g.own_ws = 1;
+		if (b200_mv_create(A->nrows, sizeVmax, &g.V)) return 1;
+		for (int i = 0; i < 3; ++i) if (b200_mv_create(A->nrows, bs, &g.ws[i])) goto done;
+	}
+	g.Nmax = prm->nevInit + 2 * bs; if (g.Nmax < sizeVmax) g.Nmax = sizeVmax;
+	g.ldE = (g.Nmax + 3) & ~3;
+	g.bsp = (bs + 3) & ~3;
+	if (b200k_malloc((void **)&g.eval_d, sizeof(double) * (size_t)(sizeVmax + 8))) goto done;
+	if (b200k_malloc((void **)&g.matA_d, sizeof(double) * (size_t)g.Nmax * g.ldE)) goto done;
+	if (b200k_malloc((void **)&g.evec_d, sizeof(double) * (size_t)g.Nmax * g.ldE)) goto done;
+	if (b200k_malloc((void **)&g.t1_d, sizeof(double) * (size_t)g.Nmax * g.bsp)) goto done;
+	if (b200k_malloc((void **)&g.wsE_d, sizeof(double) * (size_t)g.Nmax * g.bsp)) goto done;
+	if (b200k_malloc((void **)&g.ptap_d, sizeof(double) * (size_t)bs * bs)) goto done;
+	if (b200k_malloc((void **)&g.res_d, sizeof(double) * (size_t)(bs + 64))) goto done;
+	if (b200k_malloc((void **)&g.scal_d, sizeof(double) * (size_t)(bs + 64))) goto done;
+	if (b200k_malloc((void **)&g.idx_d, sizeof(int) * (size_t)(bs + 64))) goto done;
+	g.eval_h = (double *)calloc((size_t)sizeVmax + 8, sizeof(double));
+	g.res_h = (double *)calloc((size_t)bs + 64, sizeof(double));
+	g.offP = (int *)calloc(2 * (size_t)bs + 16, sizeof(int));
+	g.offW = (int *)calloc(2 * (size_t)bs + 16, sizeof(int));
+	{
+		const double t0 = b200_wtime();
+		const long long l0 = b200_kernel_launches();
+		rc = gcg_run(&g, eval, nevGiven, nevConv);
+		g.st.time_total = b200_wtime() - t0;
+		g.st.launches = b200_kernel_launches() - l0;
+	}
+	if (rc == 0 && prm->verbose) {
+		const b200_gcg_stats *s = &g.st;
+		printf("|--GCG (B200)---------------------\n|Total Time = %.3f, Avg Time per Iteration = %.4f, kernel launches = %lld\n",
+		       s->time_total, s->time_total / (s->numIter > 0 ? s->numIter : 1), s->launches);
+		printf("|checkconv   compP   compRR   (eig)   compRV   compW   (linsol)   compX   initX\n");
+		printf("|%.3f\t%.3f\t%.3f\t(%.3f)\t%.3f\t%.3f\t(%.3f)\t%.3f\t%.3f\n", s->checkconv, s->compP, s->compRR,
+		       s->rr_eig, s->compRV, s->compW, s->linsol, s->compX, s->initX);
+	}
+	if (stats) *stats = g.st;
+done:
+	gcg_release(&g);
+	return rc;
+}

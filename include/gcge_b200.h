@@ -1,0 +1,165 @@
+/* gcge_b200.h -- C ABI of the B200-native GCG hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * C++ or torch types.  Every entry point names the reference interface it
+ * replaces (file:line under the reference tree).  The OPS adaptor
+ * gcge_b200/app/app_b200.c fills the reference's `struct OPS_`
+ * (reference src/ops.h:43-152) with thin wrappers over these functions, so the
+ * reference's GCG, ops_orth.c and ops_lin_sol.c can drive them unchanged
+ * (INTEGRATION.md).
+ *
+ * Conventions (same as the reference's slots, reference src/ops.h:78-103):
+ *   - start[0],end[0] index columns of the first multi-vector argument,
+ *     start[1],end[1] of the second; half-open ranges.
+ *   - inner_prod / qAp / coef / beta / eval are HOST pointers, column-major,
+ *     owned by the caller; they are valid on return (the call synchronises).
+ *   - matrices are borrowed, multi-vectors are created/destroyed by the caller.
+ *   - all arithmetic is FP64, all indices are 32-bit int.
+ * Multi-vectors live in HBM row-major (n x ld doubles, ld >= ncols); the
+ * layout is never exposed: hosts see column-major through upload/download.
+ *
+ * Return value: 0 on success, non-zero on failure with a message available
+ * from b200_last_error().  The reference's slots return void and abort() on
+ * failure (reference app/app_ccs.c:53-55); the OPS adaptor reproduces that.
+ * There is NO CPU fallback: without a CUDA device every call fails loudly.
+ */
+#ifndef GCGE_B200_H_
+#define GCGE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_mat_ b200_mat; /* device CSR image of a CCSMAT (reference app/app_ccs.h:20-24) */
+typedef struct b200_mv_  b200_mv;  /* device multi-vector; replaces LAPACKVEC (reference app/app_lapack.h:17-20) */
+
+/* ---- runtime ------------------------------------------------------------ */
+int  b200_init(int device);            /* select device, create streams/workspaces; idempotent */
+void b200_finalize(void);
+const char *b200_last_error(void);
+int  b200_device_count(void);
+int  b200_sync(void);                  /* cudaStreamSynchronize on the library stream */
+double b200_wtime(void);               /* synchronising wall clock; replaces DefaultGetWtime, reference src/ops_multi_vec.c:45-56 */
+long long b200_kernel_launches(void);  /* number of kernels this library launched since init */
+
+/* ---- matrix: replaces the host CCSMAT the reference's drivers build directly
+ *      (reference test/test_app_ccs.c:99-102, :142-184) ------------------------ */
+int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, const int *i_row,
+                             const double *data, b200_mat **out);
+int b200_mat_destroy(b200_mat *A);
+int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nnz);
+/* gather the device matrix back to CCS arrays; bit-exact round trip */
+int b200_mat_to_ccs(const b200_mat *A, int *j_col, int *i_row, double *data);
+/* Y = alpha X + beta Y on identical sparsity patterns; slot MatAxpby, reference src/ops.h:52 */
+int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200_mat *Y);
+
+/* ---- multi-vector life cycle: reference app/app_ccs.c:40-49 (MultiVecCreateByMat),
+ *      app/app_lapack.c:230-286 (create/destroy) ------------------------------ */
+int b200_mv_create(int nrows, int ncols, b200_mv **out);   /* zero-filled */
+int b200_mv_destroy(b200_mv *x);
+int b200_mv_shape(const b200_mv *x, int *nrows, int *ncols);
+/* non-owning view of columns [start,end); destroy with b200_mv_destroy.  Replaces
+ * GetVecFromMultiVec / RestoreVecForMultiVec, reference app/app_lapack.c:262-286 */
+int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view);
+/* host column-major (ld >= nrows) <-> device columns [start,end) */
+int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld);
+int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld);
+/* x[row,col] = rand()/(RAND_MAX+1.0), column-major fill order, consuming the process's
+ * glibc rand() stream exactly like reference app/app_lapack.c:322-333 */
+int b200_mv_set_random(b200_mv *x, int start, int end);
+
+/* ---- slots --------------------------------------------------------------- */
+/* y[:,s1:e1] = A x[:,s0:e0]; A == NULL => copy.  Replaces MatDotMultiVec,
+ * reference app/app_ccs.c:50-139 (kernel :116-131); also serves MatTransDotMultiVec
+ * (reference app/app_ccs.c:140-150, symmetry assumed there; here `trans` != 0
+ * multiplies by the true transpose). */
+int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv *x, b200_mv *y,
+                          const int *start, const int *end);
+/* y[:,s1:e1] = alpha x[:,s0:e0] + beta y[:,s1:e1]; x == NULL => scale; beta == 0 =>
+ * overwrite.  Replaces MultiVecAxpby, reference app/app_lapack.c:334-395 */
+int b200_mv_axpby(double alpha, const b200_mv *x, double beta, b200_mv *y,
+                  const int *start, const int *end);
+/* y[:,s1:e1] = x[:,s0:e0] coef + y diag(beta).  coef host col-major (e0-s0)x(e1-s1), ldc;
+ * beta == NULL => 0, incb == 0 => one scalar, else beta[incb*col]; x == NULL or
+ * coef == NULL => scaling only.  Replaces MultiVecLinearComb, reference app/app_lapack.c:463-534 */
+int b200_mv_linear_comb(const b200_mv *x, b200_mv *y, const int *start, const int *end,
+                        const double *coef, int ldc, const double *beta, int incb);
+/* inner_prod = x[:,s0:e0]^T y[:,s1:e1]; nsd: 'N' full, 'S' symmetric (computed once,
+ * mirrored), 'D' diagonal only into inner_prod[ld*idx].  Replaces
+ * MultiVecLocalInnerProd / MultiVecInnerProd, reference app/app_lapack.c:299-321 (via
+ * DenseMatQtAP :24-183) and src/ops_multi_vec.c:202-230. */
+int b200_mv_inner_prod(char nsd, const b200_mv *x, const b200_mv *y,
+                       const int *start, const int *end, double *inner_prod, int ld);
+/* qAp = Q[:,s0:e0]^T A P[:,s1:e1]; leaves A P[:,s1:e1] in ws[:,0:e1-s1] (callers rely on
+ * it, reference src/ops_orth.c:315-323); ntsdQAP 'T' stores the transpose.  A == NULL =>
+ * plain inner product, ws untouched.  Replaces DefaultMultiVecQtAP, reference
+ * src/ops_multi_vec.c:351-411. */
+int b200_mv_qtap(char ntsA, char ntsdQAP, const b200_mv *Q, const b200_mat *A, const b200_mv *P,
+                 const int *start, const int *end, double *qAp, int ldQAP, b200_mv *ws);
+
+/* ---- fused L3 providers (SURVEY §7 tier B) -------------------------------- */
+/* B-orthonormalise x[:,start_x:*end_x] against x[:,0:start_x] and itself, dropping
+ * dependent columns (shrinks *end_x).  Replaces ModifiedGramSchmidt, reference
+ * src/ops_orth.c:203-393 (+ OrthSelf :45-118).  ws: at least min(block,*end_x-start_x)
+ * columns of workspace. */
+typedef struct b200_orth_params_ {
+	int    block_size;     /* <=0: half of the block, reference src/ops_orth.c:275-278 */
+	int    max_reorth;
+	double orth_zero_tol;
+	double reorth_tol;     /* reference default 50*DBL_EPSILON, src/ops_orth.c:401-404 */
+} b200_orth_params;
+int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
+                 const b200_orth_params *prm, b200_mv *ws);
+
+/* Block CG on A x = b for columns b[:,s0:e0], x[:,s1:e1], per-column convergence
+ * masks, device-resident scalars.  shift != 0 solves (A + shift*B) x = b (B may be
+ * NULL => identity).  Replaces BlockPCG, reference src/ops_lin_sol.c:140-437, and the
+ * shifted operator MatDotMultiVecShift, reference src/ops_eig_sol_gcg.c:63-96. */
+typedef struct b200_bpcg_params_ {
+	int    max_iter;
+	double rate;
+	double tol;
+	int    tol_type;       /* 0 "abs", 1 "rel" (reference src/ops_lin_sol.c:175-200) */
+	double shift;
+} b200_bpcg_params;
+int b200_block_pcg(const b200_mat *A, const b200_mat *B, const b200_mv *b, b200_mv *x,
+                   const int *start, const int *end, const b200_bpcg_params *prm,
+                   b200_mv *ws_r, b200_mv *ws_p, b200_mv *ws_w, int *niter, double *residual);
+
+/* All eigenpairs of the symmetric n x n host matrix a (column-major, lda; upper or lower
+ * triangle both read), ascending; on-device parallel-order Jacobi.  Replaces the dsyevx
+ * call of the projected problem, reference src/ops_eig_sol_gcg.c:1201-1204. */
+int b200_dense_syev(int n, const double *a, int lda, double *w, double *z, int ldz,
+                    int *sweeps);
+
+/* Whole GCG solve (reference src/ops_eig_sol_gcg.c:1253-1558) with the parameters of
+ * GCGSolver (reference src/ops_eig_sol_gcg.h:26-52).  evec: n x nevMax multi-vector. */
+typedef struct b200_gcg_params_ {
+	int    nevMax, multiMax, nevInit, block_size, numIterMax;
+	double gapMin;
+	double tol[2];
+	int    check_conv_max_num;
+	int    initX_orth_block_size, initX_orth_max_reorth; double initX_orth_zero_tol;
+	int    compP_orth_block_size, compP_orth_max_reorth; double compP_orth_zero_tol;
+	int    compW_orth_block_size, compW_orth_max_reorth; double compW_orth_zero_tol;
+	int    compW_cg_max_iter; double compW_cg_rate, compW_cg_tol; int compW_cg_tol_type;
+	int    compW_cg_auto_shift; double compW_cg_shift;
+	double compRR_tol;
+	int    verbose;
+} b200_gcg_params;
+typedef struct b200_gcg_stats_ {
+	int    numIter, nevConv;
+	double time_total, initX, checkconv, compP, compRR, rr_eig, compRV, compW, linsol, compX;
+	long long launches;
+} b200_gcg_stats;
+void b200_gcg_default_params(int nevConv, b200_gcg_params *prm); /* defaults of reference test/test_eig_sol_gcg.c:33-115 */
+/* mv_ws: NULL, or the four workspaces of EigenSolverSetup_GCG (reference
+ * src/ops_eig_sol_gcg.c:1561: [0] nevMax+2*block_size columns, [1..3] block_size columns) */
+int  b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *evec,
+                    int nevGiven, int *nevConv, const b200_gcg_params *prm, b200_mv **mv_ws,
+                    b200_gcg_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCGE_B200_H_ */
