@@ -123,6 +123,20 @@ def kernel_launches() -> int:
     return lib().b200_kernel_launches()
 
 
+def timer_start():
+    _chk(lib().b200_timer_start())
+
+
+def timer_stop() -> float:
+    ms = C.c_double(0)
+    _chk(lib().b200_timer_stop(C.byref(ms)))
+    return ms.value
+
+
+def flush_l2():
+    _chk(lib().b200_flush_l2())
+
+
 def libc_srand(seed: int = 0):
     """srand() of the process's glibc -- the generator b200_mv_set_random consumes, exactly as
     the reference's drivers do (reference test/test_eig_sol_gcg.c:87)."""

@@ -161,3 +161,39 @@ extern "C" int b200k_free(void *dev)
 	cudaFree(dev);
 	return 0;
 }
+
+static cudaEvent_t g_ev[2];
+static bool g_ev_ok = false;
+
+extern "C" int b200_timer_start(void)
+{
+	B200_REQUIRE_INIT();
+	if (!g_ev_ok) {
+		B200_CUDA(cudaEventCreate(&g_ev[0]));
+		B200_CUDA(cudaEventCreate(&g_ev[1]));
+		g_ev_ok = true;
+	}
+	B200_CUDA(cudaEventRecord(g_ev[0], g_b200.stream));
+	return 0;
+}
+
+extern "C" int b200_timer_stop(double *ms)
+{
+	B200_CHECK(g_ev_ok && ms, "b200_timer_stop: timer not started");
+	B200_CUDA(cudaEventRecord(g_ev[1], g_b200.stream));
+	B200_CUDA(cudaEventSynchronize(g_ev[1]));
+	float f = 0.f;
+	B200_CUDA(cudaEventElapsedTime(&f, g_ev[0], g_ev[1]));
+	*ms = f;
+	return 0;
+}
+
+extern "C" int b200_flush_l2(void)
+{
+	B200_REQUIRE_INIT();
+	const size_t bytes = (size_t)256 << 20;      // 2 x the 126 MB L2
+	static void *buf = nullptr;
+	if (!buf) B200_CUDA(cudaMalloc(&buf, bytes));
+	B200_CUDA(cudaMemsetAsync(buf, 1, bytes, g_b200.stream));
+	return 0;
+}

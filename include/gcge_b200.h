@@ -41,6 +41,12 @@ int  b200_device_count(void);
 int  b200_sync(void);                  /* cudaStreamSynchronize on the library stream */
 double b200_wtime(void);               /* synchronising wall clock; replaces DefaultGetWtime, reference src/ops_multi_vec.c:45-56 */
 long long b200_kernel_launches(void);  /* number of kernels this library launched since init */
+/* CUDA-event stopwatch on the library stream (the stream every kernel is launched on):
+ * start records an event, stop records a second one, synchronises and returns milliseconds */
+int  b200_timer_start(void);
+int  b200_timer_stop(double *ms);
+/* overwrite a buffer larger than L2 so the next timed kernel starts cold */
+int  b200_flush_l2(void);
 
 /* ---- matrix: replaces the host CCSMAT the reference's drivers build directly
  *      (reference test/test_app_ccs.c:99-102, :142-184) ------------------------ */

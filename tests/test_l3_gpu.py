@@ -1,0 +1,148 @@
+"""GPU parity of the fused L3 providers: orthogonalisation (reference test/test_orth.c:21-178
+turned into assertions), BlockPCG (reference test/test_lin_sol.c:58-116) and the projected
+eigen-solve that replaces dsyevx."""
+import numpy as np
+import pytest
+
+from gcge_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def gram_err(v, Bd, k):
+    g = v[:, :k].T @ (Bd @ v[:, :k]) if Bd is not None else v[:, :k].T @ v[:, :k]
+    return np.abs(g - np.eye(k)).max()
+
+
+@pytest.mark.parametrize("with_B", [False, True])
+def test_orth_rank_deficient_like_reference_TestOrth(b200, with_B):
+    """reference test/test_orth.c:44-111: 10 vectors, columns 5-9 duplicated from 0-4;
+    orthogonalise from 0 and from 2; X^T B X must be the identity on the surviving columns and
+    the dependent ones must be dropped."""
+    pen = P.p1_fem_kuhn(8)
+    n = pen.A.ncols
+    Bm = b200.Mat(pen.B) if with_B else None
+    Bd = pen.B.to_scipy() if with_B else None
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.random((n, 10)))
+    x[:, 5:10] = x[:, 0:5]
+    for start in (0, 2):
+        X = b200.MultiVec.from_numpy(x)
+        if start == 2:     # the first two must already be orthonormal
+            e0 = b200.orth(X, 0, 2, B=Bm, block_size=8, max_reorth=5, orth_zero_tol=1e-8)
+            assert e0 == 2
+        end = b200.orth(X, start, 10, B=Bm, block_size=8, max_reorth=5, orth_zero_tol=1e-8)
+        assert end == 5
+        assert gram_err(X.numpy(), Bd, end) < 1e-12
+
+
+@pytest.mark.parametrize("k,start", [(1, 0), (10, 0), (40, 60), (80, 100), (100, 20)])
+def test_orth_against_previous_block(b200, k, start):
+    pen = P.p1_fem_kuhn(10)
+    n = pen.A.ncols
+    Bm = b200.Mat(pen.B); Bd = pen.B.to_scipy()
+    rng = np.random.default_rng(k + start)
+    x = np.asfortranarray(rng.random((n, start + k)))
+    X = b200.MultiVec.from_numpy(x)
+    if start:
+        assert b200.orth(X, 0, start, B=Bm, block_size=80) == start
+    ws = b200.MultiVec(n, 80)
+    end = b200.orth(X, start, start + k, B=Bm, ws=ws, block_size=80)
+    assert end == start + k
+    v = X.numpy()
+    assert gram_err(v, Bd, end) < 1e-12
+    # the span is preserved: the new columns reproduce the old ones
+    old = x[:, start:start + k]
+    coef = v.T @ (Bd @ old)
+    assert np.abs(v @ coef - old).max() < 1e-10 * np.abs(old).max()
+
+
+def test_orth_tiny_and_scaled_columns(b200):
+    """Columns that are almost inside span(X0) (remainder 1e-12): the case the reference's
+    absolute re-orthogonalisation test mishandles (tests/test_oracle.py)."""
+    rng = np.random.default_rng(8)
+    n = 4000
+    q, _ = np.linalg.qr(rng.standard_normal((n, 30)))
+    x = np.zeros((n, 30), order="F")
+    x[:, :20] = q[:, :20]
+    x[:, 20:] = q[:, :20] @ rng.standard_normal((20, 10)) + 1e-12 * q[:, 20:] * (10.0 ** rng.integers(-3, 3, 10))
+    X = b200.MultiVec.from_numpy(x)
+    end = b200.orth(X, 20, 30, block_size=80)
+    assert end == 30
+    assert gram_err(X.numpy(), None, 30) < 1e-10
+
+
+def test_block_pcg_like_reference_TestMultiLinearSolver(b200, refmod):
+    """reference test/test_lin_sol.c:58-116: manufactured right-hand side b = A x, 4 columns,
+    "abs" 1e-8; and the GCG use: 30 iterations max, rate 1e-2 (per-column stop)."""
+    from gcge_b200 import api
+    pen = P.laplace3d_7pt(12)
+    n = pen.A.ncols
+    A = b200.Mat(pen.A); Ad = pen.A.to_scipy()
+    rng = np.random.default_rng(6)
+    xs = np.asfortranarray(rng.random((n, 4)))
+    bh = np.asfortranarray(Ad @ xs)
+    Bv = b200.MultiVec.from_numpy(np.hstack([np.zeros((n, 1)), bh]))
+    X = b200.MultiVec(n, 6)
+    niter, res = b200.block_pcg(A, Bv, X, (1, 2), (5, 6), max_iter=500, rate=1e-30, tol=1e-8)
+    sol = X.numpy()[:, 2:6]
+    assert np.abs(Ad @ sol - bh).max() < 1e-7
+    assert niter < 200
+    if refmod is not None:
+        b2 = np.asfortranarray(np.hstack([np.zeros((n, 1)), bh])); x2 = np.zeros((n, 6), order="F")
+        it_ref, _ = refmod.block_pcg(pen.A, b2, x2, (1, 2), (5, 6), max_iter=500, rate=1e-30, tol=1e-8)
+        assert abs(niter - it_ref) <= 1
+        assert np.abs(sol - x2[:, 2:6]).max() < 1e-6
+        # the GCG setting: few iterations, rate stop, per-column masks -- same iterate
+        for k in (1, 4):
+            X = b200.MultiVec(n, 6); x3 = np.zeros((n, 6), order="F")
+            it_dev, _ = b200.block_pcg(A, Bv, X, (1, 2), (1 + k, 2 + k), max_iter=30, rate=1e-2, tol=1e-14)
+            it_ref, _ = refmod.block_pcg(pen.A, b2, x3, (1, 2), (1 + k, 2 + k), max_iter=30, rate=1e-2, tol=1e-14)
+            assert it_dev == it_ref
+            got = X.numpy()
+            assert np.abs(got - x3).max() < 1e-11 * np.abs(x3).max()
+
+
+def test_block_pcg_shifted_operator(b200):
+    """(A + sigma B) x = b, the operator of reference src/ops_eig_sol_gcg.c:63-96."""
+    pen = P.p1_fem_kuhn(8)
+    n = pen.A.ncols
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    Ad = pen.A.to_scipy(); Bd = pen.B.to_scipy()
+    rng = np.random.default_rng(16)
+    xs = rng.random((n, 3))
+    for sigma, Bm, Bdd in ((2.5, B, Bd), (0.5, None, None)):
+        op = Ad + sigma * (Bdd if Bdd is not None else 1.0 * np.eye(n))
+        bh = np.asfortranarray(op @ xs)
+        X = b200.MultiVec(n, 3)
+        niter, res = b200.block_pcg(A, b200.MultiVec.from_numpy(bh), X, (0, 0), (3, 3), B=Bm, shift=sigma,
+                                    max_iter=400, rate=1e-30, tol=1e-10)
+        assert np.abs(op @ X.numpy() - bh).max() < 1e-8
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 33, 120, 241])
+def test_dense_syev_vs_lapack(b200, n):
+    """Replaces dsyevx (reference src/ops_eig_sol_gcg.c:1201): eigenvalues to 1e-13 of the
+    spectral radius, eigenvectors orthonormal and A z = w z to the same level."""
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n)); a = a + a.T
+    if n > 8:       # a degenerate cluster and a near-diagonal block, as the projected matrix has
+        a[:4, :4] = np.diag([1.0, 1.0, 1.0, 1.0]) * 3.0
+        a[:4, 4:] *= 1e-9; a[4:, :4] *= 1e-9
+    w, z, sweeps = b200.dense_syev(a)
+    wl = np.linalg.eigvalsh(a)
+    scale = max(np.abs(wl).max(), 1e-300)
+    assert np.abs(w - wl).max() < 1e-13 * scale
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(z.T @ z - np.eye(n)).max() < 1e-13
+    assert np.abs(a @ z - z * w).max() < 1e-12 * scale
+    assert 1 <= sweeps <= 15
+
+
+def test_dense_syev_uses_upper_triangle_like_dsyevx(b200):
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((20, 20)); s = np.triu(a) + np.triu(a, 1).T
+    junk = np.triu(a) + np.tril(rng.standard_normal((20, 20)), -1)
+    w, _, _ = b200.dense_syev(junk)
+    assert np.abs(w - np.linalg.eigvalsh(s)).max() < 1e-13 * np.abs(s).max() * 20

@@ -1,0 +1,308 @@
+"""GPU parity of the OPS slot kernels, through the C ABI, against the reference
+(oracle/_ref when it travelled) and the plain-C oracle.  The call sequences follow the
+reference's own drivers TestMultiVec (reference test/test_multi_vec.c:19-228) turned into
+assertions.  Bit-exact where the reference's arithmetic order is reproducible (SpMM, copies,
+RNG, CCS round trip); 1e-13 relative for BLAS-ordered reductions (tolerance stated per test)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gcge_b200 import problems as P
+from oracle import gcg_numpy as G
+
+pytestmark = pytest.mark.gpu
+dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def oracle_spmm(M, x):
+    n, k = x.shape
+    y = np.zeros((n, k), order="F")
+    xx = np.asfortranarray(x)
+    G.clib().oracle_ccs_spmm(n, ip(M.j_col), ip(M.i_row), dp(M.data), dp(xx), dp(y), k)
+    return y
+
+
+@pytest.fixture(scope="module")
+def pencil():
+    return P.p1_fem_kuhn(9)      # n = 729, 15 nnz/row, A and B
+
+
+def test_ccs_round_trip_bitexact(b200):
+    rng = np.random.default_rng(0)
+    for pen in (P.laplace1d_pencil(57), P.p1_fem_kuhn(5)):
+        for M in (pen.A, pen.B):
+            d = b200.Mat(M)
+            j, i, v = d.to_ccs()
+            assert np.array_equal(j, M.j_col) and np.array_equal(i, M.i_row) and np.array_equal(v, M.data)
+    # non-symmetric, unsorted rows inside a column, an empty column, an empty row
+    j_col = np.array([0, 3, 3, 5, 6], np.int32)
+    i_row = np.array([2, 0, 3, 1, 0, 2], np.int32)
+    data = rng.standard_normal(6)
+    M = P.CCS(4, 4, j_col, i_row, data)
+    d = b200.Mat(M)
+    j, i, v = d.to_ccs()
+    assert np.array_equal(j, j_col) and np.array_equal(i, i_row) and np.array_equal(v, data)
+    x = np.asfortranarray(rng.standard_normal((4, 3)))
+    X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec(4, 3)
+    from gcge_b200 import api
+    api.mat_dot_multivec(d, X, Y, (0, 0), (3, 3))
+    assert np.array_equal(Y.numpy(), oracle_spmm(M, x))
+    api.mat_dot_multivec(d, X, Y, (0, 0), (3, 3), trans=True)
+    assert np.allclose(Y.numpy(), P.ccs_to_dense(M).T @ x, rtol=1e-14, atol=1e-14)
+
+
+def test_upload_download_and_views(b200):
+    rng = np.random.default_rng(1)
+    for n, k in ((1, 1), (33, 2), (1000, 7), (257, 40)):
+        a = np.asfortranarray(rng.standard_normal((n, k)))
+        mv = b200.MultiVec.from_numpy(a)
+        assert np.array_equal(mv.numpy(), a)
+        assert np.array_equal(mv.numpy(1 if k > 1 else 0, k), a[:, (1 if k > 1 else 0):])
+    empty = b200.MultiVec(0, 3)
+    assert empty.numpy().shape == (0, 3)
+
+
+def test_set_random_is_glibc_stream(b200, refmod):
+    n, k = 501, 6
+    mv = b200.MultiVec(n, k)
+    b200.libc_srand(0)
+    mv.set_random(1, 5)
+    got = mv.numpy()
+    want = np.zeros((n, k), order="F")
+    G.srand(0); G.fill_random(want, 1, 5)
+    assert np.array_equal(got, want)
+    assert got[0, 1] == 1804289383 / 2147483648.0
+    if refmod is not None:
+        r = np.zeros((n, k), order="F")
+        refmod.srand(0); refmod.multivec_set_random(r, 1, 5)
+        assert np.array_equal(got, r)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 10, 16, 31, 40, 70])
+def test_spmm_bitexact(b200, refmod, pencil, k):
+    """MatDotMultiVec (reference app/app_ccs.c:50-139): identical bits, any block width."""
+    from gcge_b200 import api
+    rng = np.random.default_rng(k)
+    n = pencil.A.ncols
+    x = np.asfortranarray(rng.standard_normal((n, k + 3)))
+    A = b200.Mat(pencil.A)
+    X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec(n, k + 5)
+    api.mat_dot_multivec(A, X, Y, (2, 4), (2 + k, 4 + k))
+    got = Y.numpy()
+    want = oracle_spmm(pencil.A, x[:, 2:2 + k])
+    assert np.array_equal(got[:, 4:4 + k], want)
+    assert not got[:, :4].any() and not got[:, 4 + k:].any()      # neighbours untouched
+    if refmod is not None:
+        yr = np.zeros((n, k + 5), order="F")
+        refmod.mat_dot_multivec(pencil.A, x, yr, (2, 4), (2 + k, 4 + k))
+        assert np.array_equal(got, yr)
+    # NULL matrix == copy (reference app/app_ccs.c:134-137)
+    api.mat_dot_multivec(None, X, Y, (0, 0), (k, k))
+    assert np.array_equal(Y.numpy()[:, :k], x[:, :k])
+
+
+def test_axpby_semantics(b200, refmod):
+    """MultiVecAxpby (reference app/app_lapack.c:334-395; call shapes of
+    reference test/test_multi_vec.c:103-116)."""
+    from gcge_b200 import api
+    rng = np.random.default_rng(3)
+    n = 777
+    x = np.asfortranarray(rng.standard_normal((n, 6))); y = np.asfortranarray(rng.standard_normal((n, 9)))
+    for alpha, beta, s, e in ((1.0, 0.0, (1, 2), (4, 5)), (0.5, 1.0, (0, 0), (6, 6)), (-2.0, 3.0, (2, 7), (4, 9)),
+                              (1.0, -1.0, (0, 3), (1, 4))):
+        X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec.from_numpy(y)
+        api.multivec_axpby(alpha, X, beta, Y, s, e)
+        want = y.copy(order="F")
+        k = e[0] - s[0]
+        blk = np.ascontiguousarray(want[:, s[1]:s[1] + k].T).T
+        want[:, s[1]:s[1] + k] = alpha * x[:, s[0]:e[0]] + (0.0 if beta == 0.0 else beta * blk)
+        got = Y.numpy()
+        assert rel(got, want) < 1e-15
+        if beta == 0.0 and alpha == 1.0:
+            assert np.array_equal(got[:, s[1]:e[1]], x[:, s[0]:e[0]])       # copies are exact
+        if refmod is not None:
+            yr = y.copy(order="F")
+            refmod.multivec_axpby(alpha, x, beta, yr, s, e)
+            assert rel(got, yr) < 1e-15
+    # x == NULL: scale only; beta == 0 overwrites NaNs (memset in the reference)
+    ynan = y.copy(order="F"); ynan[3, 2] = np.nan
+    Y = b200.MultiVec.from_numpy(ynan)
+    api.multivec_axpby(0.0, None, 2.0, Y, (0, 0), (2, 2))
+    assert np.array_equal(Y.numpy()[:, :2], 2.0 * y[:, :2])
+    api.multivec_axpby(1.0, b200.MultiVec.from_numpy(x), 0.0, Y, (0, 2), (1, 3))
+    assert np.array_equal(Y.numpy()[:, 2], x[:, 0])
+    # same multi-vector, disjoint ranges: column copy (reference src/ops_orth.c:70,302)
+    Y = b200.MultiVec.from_numpy(y)
+    api.multivec_axpby(1.0, Y, 0.0, Y, (7, 1), (9, 3))
+    assert np.array_equal(Y.numpy()[:, 1:3], y[:, 7:9])
+
+
+@pytest.mark.parametrize("shape", [(2, 5), (1, 1), (17, 3), (40, 40), (100, 37), (70, 130)])
+def test_inner_prod_modes(b200, refmod, shape):
+    """MultiVecInnerProd N / S / D (reference app/app_lapack.c:24-183 via :299-321;
+    reference test/test_multi_vec.c:40-102).  Tolerance 1e-13 relative to the block's
+    largest entry: summation order differs from BLAS."""
+    from gcge_b200 import api
+    p, q = shape
+    rng = np.random.default_rng(p * 131 + q)
+    n = 2311
+    x = np.asfortranarray(rng.standard_normal((n, p + 2))); y = np.asfortranarray(rng.standard_normal((n, q + 1)))
+    X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec.from_numpy(y)
+    ld = p + 3
+    got = np.full((ld, q), 7.0, order="F")
+    api.multivec_inner_prod("N", X, Y, (1, 1), (1 + p, 1 + q), got, ld)
+    want = x[:, 1:1 + p].T @ y[:, 1:1 + q]
+    assert rel(got[:p], want) < 1e-13
+    assert np.all(got[p:] == 7.0)                    # rows beyond the block untouched (ldIP)
+    if refmod is not None:
+        r = np.zeros((ld, q), order="F")
+        refmod.multivec_inner_prod("N", x, y, (1, 1), (1 + p, 1 + q), r, ld)
+        assert rel(got[:p], r[:p]) < 1e-13
+    m = min(p, q)
+    d = np.zeros(m)
+    api.multivec_inner_prod("D", X, Y, (0, 0), (m, m), d, 1)
+    assert rel(d, np.einsum("ij,ij->j", x[:, :m], y[:, :m])) < 1e-13
+    s = np.zeros((p, p), order="F")
+    api.multivec_inner_prod("S", X, X, (0, 0), (p, p), s, p)
+    assert rel(s, x[:, :p].T @ x[:, :p]) < 1e-13
+    assert np.array_equal(s, s.T)
+
+
+def test_inner_prod_deterministic(b200):
+    from gcge_b200 import api
+    rng = np.random.default_rng(9)
+    x = np.asfortranarray(rng.standard_normal((50000, 24)))
+    X = b200.MultiVec.from_numpy(x)
+    a = np.zeros((24, 24), order="F"); b = np.zeros((24, 24), order="F")
+    api.multivec_inner_prod("N", X, X, (0, 0), (24, 24), a, 24)
+    api.multivec_inner_prod("N", X, X, (0, 0), (24, 24), b, 24)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("modes", [("S", "S"), ("S", "D"), ("S", "N"), ("N", "N"), ("S", "T")])
+def test_qtap_modes_and_workspace_side_effect(b200, refmod, pencil, modes):
+    """MultiVecQtAP (reference src/ops_multi_vec.c:351-411; reference
+    test/test_multi_vec.c:139-197), including A*P left in mv_ws, which ops_orth.c relies on
+    (reference src/ops_orth.c:315-323)."""
+    from gcge_b200 import api
+    ntsA, out = modes
+    rng = np.random.default_rng(11)
+    n = pencil.A.ncols
+    q = np.asfortranarray(rng.standard_normal((n, 6))); p = np.asfortranarray(rng.standard_normal((n, 5)))
+    A = b200.Mat(pencil.A)
+    Q = b200.MultiVec.from_numpy(q); Pm = b200.MultiVec.from_numpy(p); W = b200.MultiVec(n, 5)
+    Ad = pencil.A.to_scipy()
+    if out in ("S", "D"):
+        s, e = (1, 1), (4, 4)
+        Pm = Q; pp = q
+    else:
+        s, e = (1, 0), (6, 4)
+        pp = p
+    nr, nc = e[0] - s[0], e[1] - s[1]
+    AP = Ad @ pp[:, s[1]:e[1]]
+    full = q[:, s[0]:e[0]].T @ AP
+    if out == "D":
+        got = np.zeros(nr)
+        api.multivec_qtap(ntsA, out, Q, A, Pm, s, e, got, 1, W)
+        assert rel(got, np.diag(full)) < 1e-13
+    elif out == "T":
+        got = np.zeros((nc, nr), order="F")
+        api.multivec_qtap(ntsA, out, Q, A, Pm, s, e, got, nc, W)
+        assert rel(got, full.T) < 1e-13
+    else:
+        got = np.zeros((nr, nc), order="F")
+        api.multivec_qtap(ntsA, out, Q, A, Pm, s, e, got, nr, W)
+        assert rel(got, full) < 1e-13
+    assert np.array_equal(W.numpy()[:, :nc], oracle_spmm(pencil.A, pp[:, s[1]:e[1]]))
+    # A == NULL: plain inner product
+    g2 = np.zeros((nr, nc), order="F")
+    if out in ("N",):
+        api.multivec_qtap("N", "N", Q, None, Pm, s, e, g2, nr, None)
+        assert rel(g2, q[:, s[0]:e[0]].T @ pp[:, s[1]:e[1]]) < 1e-13
+
+
+@pytest.mark.parametrize("shape", [(1, 4), (5, 2), (16, 16), (33, 70), (120, 40), (7, 129)])
+def test_linear_comb(b200, refmod, shape):
+    """MultiVecLinearComb (reference app/app_lapack.c:463-534; reference
+    test/test_multi_vec.c:199-222): beta NULL / scalar / per column, scaling-only forms and the
+    same-multi-vector update used by OrthSelf."""
+    from gcge_b200 import api
+    p, q = shape
+    rng = np.random.default_rng(p + 1000 * q)
+    n = 1234
+    x = np.asfortranarray(rng.standard_normal((n, p + 1))); y = np.asfortranarray(rng.standard_normal((n, q + 2)))
+    ldc = p + 2
+    coef = np.asfortranarray(rng.standard_normal((ldc, q)))
+    X = b200.MultiVec.from_numpy(x)
+    base = x[:, 1:1 + p] @ coef[:p]
+    # beta == NULL: overwrite, even over NaNs
+    ynan = y.copy(order="F"); ynan[0, 1] = np.nan
+    Y = b200.MultiVec.from_numpy(ynan)
+    api.multivec_linear_comb(X, Y, (1, 1), (1 + p, 1 + q), coef, ldc, None, 0)
+    got = Y.numpy()
+    assert rel(got[:, 1:1 + q], base) < 1e-13
+    assert np.array_equal(got[:, 0], y[:, 0]) and np.array_equal(got[:, 1 + q:], y[:, 1 + q:])
+    # one scalar beta (incb == 0)
+    Y = b200.MultiVec.from_numpy(y)
+    b1 = np.array([0.75])
+    api.multivec_linear_comb(X, Y, (1, 1), (1 + p, 1 + q), coef, ldc, b1, 0)
+    assert rel(Y.numpy()[:, 1:1 + q], base + 0.75 * y[:, 1:1 + q]) < 1e-13
+    # per-column beta with stride
+    Y = b200.MultiVec.from_numpy(y)
+    bv = rng.standard_normal(2 * q)
+    api.multivec_linear_comb(X, Y, (1, 1), (1 + p, 1 + q), coef, ldc, bv, 2)
+    want = base + y[:, 1:1 + q] * bv[::2]
+    assert rel(Y.numpy()[:, 1:1 + q], want) < 1e-13
+    if refmod is not None:
+        yr = y.copy(order="F")
+        refmod.multivec_linear_comb(x, yr, (1, 1), (1 + p, 1 + q), coef, ldc, bv, 2)
+        assert rel(Y.numpy(), yr) < 1e-13
+    # scaling only (x == NULL), as CheckConvergence does (reference src/ops_eig_sol_gcg.c:217-218)
+    Y = b200.MultiVec.from_numpy(y)
+    api.multivec_linear_comb(None, Y, (0, 1), (q, 1 + q), None, 0, bv, 2)
+    assert rel(Y.numpy()[:, 1:1 + q], y[:, 1:1 + q] * bv[::2]) < 1e-15
+    # x == NULL and beta == NULL: nothing happens (reference app/app_lapack.c:476-505)
+    api.multivec_linear_comb(None, Y, (0, 1), (q, 1 + q), None, 0, None, 0)
+    assert rel(Y.numpy()[:, 1:1 + q], y[:, 1:1 + q] * bv[::2]) < 1e-15
+
+
+def test_linear_comb_in_place_disjoint_columns(b200):
+    from gcge_b200 import api
+    rng = np.random.default_rng(21)
+    n = 999
+    v = np.asfortranarray(rng.standard_normal((n, 12)))
+    V = b200.MultiVec.from_numpy(v)
+    coef = np.asfortranarray(rng.standard_normal((4, 8)))
+    one = np.array([1.0])
+    api.multivec_linear_comb(V, V, (0, 4), (4, 12), coef, 4, one, 0)
+    want = v.copy()
+    want[:, 4:] += v[:, :4] @ coef
+    assert rel(V.numpy(), want) < 1e-13
+
+
+def test_mat_axpby(b200, pencil):
+    from gcge_b200 import api
+    A = b200.Mat(pencil.A); B = b200.Mat(pencil.B)
+    A.axpby(0.25, B, 1.0)        # A += 0.25 B, the in-place shift of reference src/ops_eig_sol_gcg.c:594-602
+    _, _, v = A.to_ccs()
+    assert rel(v, pencil.A.data + 0.25 * pencil.B.data) < 1e-15
+    A.axpby(-0.25, B, 1.0)
+    _, _, v = A.to_ccs()
+    assert rel(v, pencil.A.data) < 1e-15
+
+
+def test_argument_errors_are_loud(b200):
+    from gcge_b200 import api
+    X = b200.MultiVec(10, 3); Y = b200.MultiVec(11, 3)
+    with pytest.raises(api.B200Error):
+        api.multivec_axpby(1.0, X, 0.0, Y, (0, 0), (2, 2))       # row counts differ
+    with pytest.raises(api.B200Error):
+        api.multivec_axpby(1.0, X, 0.0, X, (0, 1), (2, 3))       # overlapping ranges
+    with pytest.raises(api.B200Error):
+        api.multivec_axpby(1.0, X, 0.0, X, (0, 0), (2, 5))       # out of range
