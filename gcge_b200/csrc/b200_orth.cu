@@ -9,12 +9,14 @@
 #include "b200_internal.h"
 
 __global__ void __launch_bounds__(256)
-chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out)
+chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out, const double *scale_in,
+                 double *scale_out)
 {
 	extern __shared__ double sm[];
 	const int S = k + 1;
-	double *G = sm, *T = sm + (size_t)k * S, *cv = T + (size_t)k * S;
+	double *G = sm, *T = sm + (size_t)k * S, *cv = T + (size_t)k * S, *sc = cv + k;
 	const int tid = threadIdx.x, nt = blockDim.x;
+	for (int i = tid; i < k; i += nt) sc[i] = scale_in ? scale_in[i] : 1.0;
 	for (int i = tid; i < k * k; i += nt) {
 		const int r = i / k, c = i - r * k;
 		G[r * S + c] = g[i];
@@ -25,10 +27,13 @@ chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out)
 	while (pos < n_live) {
 		const double gkk = G[pos * S + pos];
 		const double rk = gkk > 0.0 ? sqrt(gkk) : 0.0;
-		if (rk < zero_tol) {
+		// sc[pos] is the factor by which earlier passes already scaled this column up, so
+		// rk*sc[pos] is its remaining norm in the caller's original scaling
+		if (rk * sc[pos] < zero_tol) {
 			const int last = n_live - 1;
 			if (pos < last) {
 				__syncthreads();
+				if (tid == 0) { const double a = sc[pos]; sc[pos] = sc[last]; sc[last] = a; }
 				for (int i = tid; i < k; i += nt) {      // swap rows pos,last of G
 					const double a = G[pos * S + i]; G[pos * S + i] = G[last * S + i]; G[last * S + i] = a;
 				}
@@ -48,7 +53,7 @@ chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out)
 			T[i * S + pos] *= inv;
 			if (i != pos) { G[pos * S + i] *= inv; G[i * S + pos] *= inv; }
 		}
-		if (tid == 0) G[pos * S + pos] = 1.0;
+		if (tid == 0) { G[pos * S + pos] = 1.0; sc[pos] *= rk; }
 		__syncthreads();
 		const int m = n_live - pos - 1;
 		for (int i = tid; i < m; i += nt) cv[i] = G[pos * S + pos + 1 + i];     // q^T B x_j
@@ -72,19 +77,21 @@ chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out)
 		const int r = i / k, c = i - r * k;
 		t[i] = T[r * S + c];
 	}
+	if (scale_out) for (int i = tid; i < k; i += nt) scale_out[i] = sc[i];
 	if (tid == 0) *n_live_out = n_live;
 }
 
-extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev)
+extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev,
+                               const double *scale_in, double *scale_out)
 {
 	B200_CHECK(k >= 1 && k <= 128, "orth panel: %d columns (1..128 supported)", k);
-	const size_t smem = sizeof(double) * ((size_t)2 * k * (k + 1) + k);
+	const size_t smem = sizeof(double) * ((size_t)2 * k * (k + 1) + 2 * k);
 	static bool attr_set = false;
 	if (!attr_set) {
 		B200_CUDA(cudaFuncSetAttribute(chol_drop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 		attr_set = true;
 	}
-	chol_drop_kernel<<<1, 256, smem, g_b200.stream>>>(k, g_dev, zero_tol, t_dev, n_live_dev);
+	chol_drop_kernel<<<1, 256, smem, g_b200.stream>>>(k, g_dev, zero_tol, t_dev, n_live_dev, scale_in, scale_out);
 	B200_KERNEL_CHECK();
 	return 0;
 }

@@ -73,8 +73,13 @@ int b200k_rm_to_cm(long long n, int k, const double *rm, int ld_rm, double *cm, 
  * Right-looking Cholesky of the k x k Gram matrix g (row-major, ld k, destroyed) with the
  * reference's drop rule (r_k < zero_tol: swap the last live column in, shrink; reference
  * src/ops_orth.c:64-73).  Writes T (k x k, element (i,j) at t[i*k+j]) with
- * X_new[:, 0:n_live] = X T[:, 0:n_live], and n_live to *n_live_dev. */
-int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev);
+ * X_new[:, 0:n_live] = X T[:, 0:n_live], and n_live to *n_live_dev.
+ * scale_in (NULL = ones): factors by which earlier passes scaled each column up; the drop
+ * test is r_k*scale_in[k] < zero_tol, so a second pass still judges a column by its norm
+ * in the caller's scaling (the Cholesky pivot alone cannot resolve r_k below ~1e-8 |x_k|).
+ * scale_out (NULL ok): the accumulated factors of the surviving columns, in final order. */
+int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev,
+                    const double *scale_in, double *scale_out);
 
 /* ---- BlockPCG (b200_bpcg.cu): device-resident scalars and masks ----------------------- */
 typedef struct b200_bpcg_state_ {

@@ -26,7 +26,8 @@
 #define ORTH_MAX_BLOCK 128
 
 static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *B, double *ws, int ldws,
-                      double zero_tol, double *g_dev, double *t_dev, int *nlive_dev, int *n_live)
+                      double zero_tol, double *g_dev, double *t_dev, int *nlive_dev, int *n_live,
+                      const double *scale_in, double *scale_out)
 {
 	const double *y = x1; int ldy = ldx;
 	if (B) {
@@ -34,7 +35,7 @@ static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *
 		y = ws; ldy = ldws;
 	}
 	if (b200k_gram('S', n, kb, kb, 1.0, x1, ldx, y, ldy, g_dev, kb, 1)) return 1;
-	if (b200k_chol_drop(kb, g_dev, zero_tol, t_dev, nlive_dev)) return 1;
+	if (b200k_chol_drop(kb, g_dev, zero_tol, t_dev, nlive_dev, scale_in, scale_out)) return 1;
 	/* X1 <- X1 T through the workspace (T: element (i,j) at t[i*kb+j]) */
 	if (b200k_lincomb(n, kb, kb, x1, ldx, t_dev, kb, 1, NULL, 0, ws, ldws)) return 1;
 	if (b200k_axpby(n, kb, 1.0, ws, ldws, 0.0, x1, ldx)) return 1;
@@ -65,10 +66,11 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 	/* device scratch: coefficient block (<= ncols x block), G, T, ones, n_live */
 	const size_t ncoef = (size_t)x->ncols * ORTH_MAX_BLOCK;
 	const size_t npan = (size_t)ORTH_MAX_BLOCK * ORTH_MAX_BLOCK;
-	double *base = (double *)b200_scratch(1, sizeof(double) * (ncoef + 2 * npan + 8) + 64);
+	double *base = (double *)b200_scratch(1, sizeof(double) * (ncoef + 2 * npan + 2 * ORTH_MAX_BLOCK + 8) + 64);
 	if (!base) return 1;
 	double *c_dev = base, *g_dev = base + ncoef, *t_dev = g_dev + npan, *one_dev = t_dev + npan;
-	int *nlive_dev = (int *)(one_dev + 4);
+	double *sc0_dev = one_dev + 4, *sc1_dev = sc0_dev + ORTH_MAX_BLOCK;
+	int *nlive_dev = (int *)(sc1_dev + ORTH_MAX_BLOCK);
 	const double one = 1.0;
 	if (b200k_h2d(one_dev, &one, sizeof(double))) return 1;
 
@@ -89,7 +91,8 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 				if (b200k_lincomb(n, s1, kb, x->d, x->ld, c_dev, kb, 1, one_dev, 0, x1, x->ld)) return 1;
 			}
 			int n_live = kb;
-			if (orth_panel(n, x1, x->ld, kb, B, ws->d, ws->ld, prm->orth_zero_tol, g_dev, t_dev, nlive_dev, &n_live))
+			if (orth_panel(n, x1, x->ld, kb, B, ws->d, ws->ld, prm->orth_zero_tol, g_dev, t_dev, nlive_dev, &n_live,
+			               round == 0 ? NULL : sc0_dev, round == 0 ? sc0_dev : sc1_dev))
 				return 1;
 			e1 = s1 + n_live;
 		}

@@ -157,26 +157,31 @@ def orth_self_panel(x, start, end, B, max_reorth, zero_tol, reorth_tol):
     return end
 
 
-def _panel_once(x, start, end, B, zero_tol):
-    """One Gram + Cholesky-with-drops + update pass of orth_self_panel."""
+def _panel_once(x, start, end, B, zero_tol, scale=None):
+    """One Gram + Cholesky-with-drops + update pass of orth_self_panel.  ``scale`` carries the
+    factors by which earlier passes scaled each column up, so the drop test judges a column
+    by its norm in the caller's scaling (gcge_b200/csrc/b200_orth.cu).  Returns (end, scale)."""
     k = end - start
     if k <= 0:
-        return end
+        return end, np.ones(0)
     X = x[:, start:end]
     G = X.T @ _matdot(B, X)
     Tm = np.eye(k)
+    sc = np.ones(k) if scale is None else scale.copy()
     pos, n_live = 0, k
     while pos < n_live:
         gkk = G[pos, pos]
         rk = np.sqrt(gkk) if gkk > 0 else 0.0
-        if rk < zero_tol:
+        if rk * sc[pos] < zero_tol:
             last = n_live - 1
             if pos < last:
                 G[[pos, last], :] = G[[last, pos], :]
                 G[:, [pos, last]] = G[:, [last, pos]]
                 Tm[:, [pos, last]] = Tm[:, [last, pos]]
+                sc[[pos, last]] = sc[[last, pos]]
             n_live -= 1
             continue
+        sc[pos] *= rk
         Tm[:, pos] /= rk
         G[pos, :] /= rk
         G[:, pos] /= rk
@@ -187,7 +192,7 @@ def _panel_once(x, start, end, B, zero_tol):
         G[pos + 1:, pos] = 0.0
         pos += 1
     x[:, start:start + n_live] = X @ Tm[:, :n_live]
-    return start + n_live
+    return start + n_live, sc[:n_live]
 
 
 def orth_bcgs2(x, start_x, end_x, B, prm: OrthParams, rounds=2):
@@ -207,11 +212,12 @@ def orth_bcgs2(x, start_x, end_x, B, prm: OrthParams, rounds=2):
     block = min(block, end_x - init_start)
     while block > 0:
         s1, e1 = init_start, init_start + block
+        sc = None
         for _ in range(rounds):
             if s1 > 0 and e1 > s1:
                 bx = _matdot(B, x[:, s1:e1])
                 x[:, s1:e1] -= x[:, :s1] @ (x[:, :s1].T @ bx)
-            e1 = _panel_once(x, s1, e1, B, prm.orth_zero_tol)
+            e1, sc = _panel_once(x, s1, e1, B, prm.orth_zero_tol, sc)
         init_end = e1
         length = block - (e1 - s1)
         length = min(length, end_x - e1 - length)

@@ -135,7 +135,7 @@ def test_dense_syev_vs_lapack(b200, n):
     scale = max(np.abs(wl).max(), 1e-300)
     assert np.abs(w - wl).max() < 1e-13 * scale
     assert np.all(np.diff(w) >= 0)
-    assert np.abs(z.T @ z - np.eye(n)).max() < 1e-13
+    assert np.abs(z.T @ z - np.eye(n)).max() < 1e-12      # ~ n * eps * sweeps
     assert np.abs(a @ z - z * w).max() < 1e-12 * scale
     assert 1 <= sweeps <= 15
 
