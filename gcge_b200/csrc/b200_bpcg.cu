@@ -35,7 +35,7 @@ extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 // r <- b - r ; acc0 = r.r ; acc1 = b.b (rel only)
 template <int CPT>
 __global__ void __launch_bounds__(RED_THREADS)
-bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *b, int ldb, double *r, int ldr,
+bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *__restrict__ b, int ldb, double *__restrict__ r, int ldr,
                   double tol, int rel, b200_bpcg_state st)
 {
 	extern __shared__ double sm[];
@@ -45,6 +45,7 @@ bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *b,
 	double acc[2][CPT];
 #pragma unroll
 	for (int i = 0; i < CPT; ++i) { acc[0][i] = 0.0; acc[1][i] = 0.0; }
+#pragma unroll 4
 	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
 #pragma unroll
 		for (int i = 0; i < CPT; ++i) {
@@ -81,13 +82,14 @@ bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *b,
 }
 
 // ------------------------------------------------------------------------- update_p
-__global__ void bpcg_update_p_kernel(long long n, int k, int rows_per_cta, const double *r, int ldr, double *p,
+__global__ void bpcg_update_p_kernel(long long n, int k, int rows_per_cta, const double *__restrict__ r, int ldr, double *__restrict__ p,
                                      int ldp, int first, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
 	const long long r0 = (long long)blockIdx.x * rows_per_cta;
 	long long nr = n - r0; if (nr > rows_per_cta) nr = rows_per_cta;
 	const int total = (int)nr * k;
+#pragma unroll 4
 	for (int i = threadIdx.x; i < total; i += blockDim.x) {
 		const int rr = i / k, c = i - rr * k;
 		if (!st.active[c]) continue;
@@ -101,7 +103,7 @@ __global__ void bpcg_update_p_kernel(long long n, int k, int rows_per_cta, const
 // ------------------------------------------------------------------------------ ptw
 template <int CPT>
 __global__ void __launch_bounds__(RED_THREADS)
-bpcg_ptw_kernel(long long n, int k, long long rows_per_chunk, const double *p, int ldp, double *w, int ldw,
+bpcg_ptw_kernel(long long n, int k, long long rows_per_chunk, const double *p, int ldp, double *__restrict__ w, int ldw,
                 double shift, const double *z, int ldz, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
@@ -112,6 +114,7 @@ bpcg_ptw_kernel(long long n, int k, long long rows_per_chunk, const double *p, i
 	double acc[1][CPT];
 #pragma unroll
 	for (int i = 0; i < CPT; ++i) acc[0][i] = 0.0;
+#pragma unroll 4
 	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
 #pragma unroll
 		for (int i = 0; i < CPT; ++i) {
@@ -137,8 +140,8 @@ bpcg_ptw_kernel(long long n, int k, long long rows_per_chunk, const double *p, i
 // ------------------------------------------------------------------------ update_xr
 template <int CPT>
 __global__ void __launch_bounds__(RED_THREADS)
-bpcg_update_xr_kernel(long long n, int k, long long rows_per_chunk, const double *p, int ldp, const double *w,
-                      int ldw, double *x, int ldx, double *r, int ldr, double rate, double tol,
+bpcg_update_xr_kernel(long long n, int k, long long rows_per_chunk, const double *__restrict__ p, int ldp, const double *__restrict__ w,
+                      int ldw, double *__restrict__ x, int ldx, double *__restrict__ r, int ldr, double rate, double tol,
                       b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
@@ -155,6 +158,7 @@ bpcg_update_xr_kernel(long long n, int k, long long rows_per_chunk, const double
 		act[i] = (c < k) && st.active[c];
 		alpha[i] = act[i] ? st.rho2[c] / st.ptw[c] : 0.0;       // reference src/ops_lin_sol.c:328
 	}
+#pragma unroll 4
 	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
 #pragma unroll
 		for (int i = 0; i < CPT; ++i) {

@@ -24,30 +24,86 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 	             : "d"(a), "d"(b));
 }
 
+// ------------------------------------------------------------------ cp.async helpers
+// 8-byte copies work for any column offset; the 16-byte form needs 16-byte aligned global
+// addresses (even column offset and even leading dimension).  src_size 0 zero-fills.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	const int sz = valid ? 8 : 0;
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc, bool valid)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	const int sz = valid ? 16 : 0;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
 // =========================================================================== gram
 constexpr int GR_BP = 64;     // tile of X columns (rows of C)
 constexpr int GR_BQ = 64;     // tile of Y columns (cols of C)
 constexpr int GR_BK = 32;     // multi-vector rows per stage
 constexpr int GR_S  = 68;     // smem row stride (doubles), == 4 mod 16
+constexpr int GR_STAGES = 3;
+constexpr int GR_STAGE_DBL = 2 * GR_BK * GR_S;          // Xs + Ys of one stage
 
-// Each CTA: rows [chunk*rows_per_chunk, ...) x one (p-tile, q-tile); 8 warps = 4 p-slices
-// (16 columns of X each) x 2 halves of the staged rows.  Partials go to
-// part[chunk][q][p] (column-major p x q per chunk); a second kernel sums the chunks in a
-// fixed order, so the result does not depend on scheduling.
-__global__ void __launch_bounds__(256)
+// Each CTA: rows [chunk*rows_per_chunk, ...) x one (p-tile, q-tile); blockIdx.x = p-tile
+// (fastest, so the CTAs that share a chunk's Y rows run together and meet in L2),
+// blockIdx.y = chunk, blockIdx.z = q-tile.  8 warps = 4 p-slices (16 columns of X each) x 2
+// halves of the staged rows.  Global -> shared through a 3-stage cp.async ring, so the
+// tensor pipe works on stage i while stages i+1, i+2 are in flight.  Partials go to
+// part[chunk][q][p]; a second kernel sums the chunks in a fixed order (deterministic).
+template <bool AL16>
+__global__ void __launch_bounds__(256, 2)
 gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
                     long long rows_per_chunk, double *part)
 {
-	__shared__ double Xs[GR_BK][GR_S];
-	__shared__ double Ys[GR_BK][GR_S];
+	extern __shared__ __align__(16) double gsm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
 	const int pw = warp & 3, kh = warp >> 2;
-	const int p0 = blockIdx.y * GR_BP, q0 = blockIdx.z * GR_BQ;
+	const int p0 = blockIdx.x * GR_BP, q0 = blockIdx.z * GR_BQ;
 	const int pt = min(GR_BP, p - p0), qt = min(GR_BQ, q - q0);
 	const int nq8 = (qt + 7) >> 3;                       // active 8-column groups of Y
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+	const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
 	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
+	const int ntiles = (int)((r_end - r_begin + GR_BK - 1) / GR_BK);
+
+	auto load_stage = [&](int stage, int tile) {
+		double *Xs = gsm + (size_t)stage * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
+		const long long r0 = r_begin + (long long)tile * GR_BK;
+		if (AL16) {
+			for (int i = tid; i < GR_BK * (GR_BP / 2); i += 256) {
+				const int rr = i / (GR_BP / 2), cc = (i - rr * (GR_BP / 2)) * 2;
+				const long long r = r0 + rr;
+				const bool ok = (r < r_end) && (cc < pt);          // pt is even on this path
+				cp_async16(Xs + rr * GR_S + cc, ok ? x + (size_t)r * ldx + p0 + cc : x, ok);
+			}
+			for (int i = tid; i < GR_BK * (GR_BQ / 2); i += 256) {
+				const int rr = i / (GR_BQ / 2), cc = (i - rr * (GR_BQ / 2)) * 2;
+				const long long r = r0 + rr;
+				const bool ok = (r < r_end) && (cc < qt);
+				cp_async16(Ys + rr * GR_S + cc, ok ? y + (size_t)r * ldy + q0 + cc : y, ok);
+			}
+		} else {
+			for (int i = tid; i < GR_BK * GR_BP; i += 256) {
+				const int rr = i / GR_BP, cc = i - rr * GR_BP;
+				const long long r = r0 + rr;
+				const bool ok = (r < r_end) && (cc < pt);
+				cp_async8(Xs + rr * GR_S + cc, ok ? x + (size_t)r * ldx + p0 + cc : x, ok);
+			}
+			for (int i = tid; i < GR_BK * GR_BQ; i += 256) {
+				const int rr = i / GR_BQ, cc = i - rr * GR_BQ;
+				const long long r = r0 + rr;
+				const bool ok = (r < r_end) && (cc < qt);
+				cp_async8(Ys + rr * GR_S + cc, ok ? y + (size_t)r * ldy + q0 + cc : y, ok);
+			}
+		}
+	};
 
 	double acc[2][8][2];
 #pragma unroll
@@ -55,63 +111,62 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 #pragma unroll
 		for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-	for (long long r0 = r_begin; r0 < r_end; r0 += GR_BK) {
-		// stage GR_BK rows of both operands (zero fill outside the block)
-		for (int i = tid; i < GR_BK * GR_BP; i += 256) {
-			const int rr = i / GR_BP, cc = i - rr * GR_BP;
-			const long long r = r0 + rr;
-			Xs[rr][cc] = (r < r_end && cc < pt) ? x[(size_t)r * ldx + p0 + cc] : 0.0;
-		}
-		for (int i = tid; i < GR_BK * GR_BQ; i += 256) {
-			const int rr = i / GR_BQ, cc = i - rr * GR_BQ;
-			const long long r = r0 + rr;
-			Ys[rr][cc] = (r < r_end && cc < qt) ? y[(size_t)r * ldy + q0 + cc] : 0.0;
-		}
+#pragma unroll
+	for (int s = 0; s < GR_STAGES - 1; ++s) {
+		if (s < ntiles) load_stage(s, s);
+		cp_async_commit();
+	}
+	for (int tile = 0; tile < ntiles; ++tile) {
+		cp_async_wait<GR_STAGES - 2>();
 		__syncthreads();
+		{   // refill the stage that was consumed in the previous iteration
+			const int nt = tile + GR_STAGES - 1;
+			if (nt < ntiles) load_stage(nt % GR_STAGES, nt);
+			cp_async_commit();
+		}
+		const double *Xs = gsm + (size_t)(tile % GR_STAGES) * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
 #pragma unroll
 		for (int ks = 0; ks < GR_BK / 2; ks += 4) {
 			const int kr = kh * (GR_BK / 2) + ks + t;
-			const double a0 = Xs[kr][pw * 16 + g];
-			const double a1 = Xs[kr][pw * 16 + 8 + g];
+			const double a0 = Xs[kr * GR_S + pw * 16 + g];
+			const double a1 = Xs[kr * GR_S + pw * 16 + 8 + g];
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				if (j < nq8) {
-					const double b = Ys[kr][j * 8 + g];
+					const double b = Ys[kr * GR_S + j * 8 + g];
 					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
 					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
 				}
 			}
 		}
-		__syncthreads();
 	}
-	// combine the two row halves through shared memory (reuse Xs as a 64 x 64 tile, stride 68)
-	// the 64 x 64 C tile of the upper row half goes through the two 32 x 68 stage buffers
-	// (Xs: C rows 0..31, Ys: C rows 32..63)
+	cp_async_wait<0>();
+	__syncthreads();
+	// combine the two row halves through shared memory: a 64 x 68 tile in stage 0
+	double *red = gsm;
 	if (kh == 1) {
 #pragma unroll
 		for (int i = 0; i < 2; ++i)
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				const int cr = pw * 16 + i * 8 + g;        // row of C tile (0..63)
-				double (*buf)[GR_S] = (cr < 32) ? Xs : Ys;
-				buf[cr & 31][j * 8 + 2 * t]     = acc[i][j][0];
-				buf[cr & 31][j * 8 + 2 * t + 1] = acc[i][j][1];
+				const int cr = pw * 16 + i * 8 + g;        // row of the C tile (0..63)
+				red[cr * GR_S + j * 8 + 2 * t]     = acc[i][j][0];
+				red[cr * GR_S + j * 8 + 2 * t + 1] = acc[i][j][1];
 			}
 	}
 	__syncthreads();
 	if (kh == 0) {
-		double *out = part + (size_t)blockIdx.x * p * q;
+		double *out = part + (size_t)blockIdx.y * p * q;
 #pragma unroll
 		for (int i = 0; i < 2; ++i)
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				const int cr = pw * 16 + i * 8 + g;
-				double (*buf)[GR_S] = (cr < 32) ? Xs : Ys;
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
 					const int cc = j * 8 + 2 * t + h;
 					if (cr < pt && cc < qt)
-						out[(size_t)(q0 + cc) * p + (p0 + cr)] = acc[i][j][h] + buf[cr & 31][cc];
+						out[(size_t)(q0 + cc) * p + (p0 + cr)] = acc[i][j][h] + red[cr * GR_S + cc];
 				}
 			}
 	}
@@ -144,6 +199,7 @@ dots_partial_kernel(long long n, int k, const double *x, int ldx, const double *
 	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
 	for (int c = threadIdx.x; c < k; c += cx) {
 		double s = 0.0;
+#pragma unroll 8
 		for (long long r = r_begin + threadIdx.y; r < r_end; r += ry)
 			s = fma(x[(size_t)r * ldx + c], y[(size_t)r * ldy + c], s);
 		sm[threadIdx.y * k + c] = s;
@@ -216,8 +272,20 @@ int b200k_gram(char mode, long long n, int p, int q, double alpha, const double 
 	chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
 	double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * p * q);
 	if (!part) return 1;
-	dim3 grid((unsigned)chunks, ptiles, qtiles);
-	gram_partial_kernel<<<grid, 256, 0, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+	dim3 grid(ptiles, (unsigned)chunks, qtiles);
+	const size_t smem = sizeof(double) * (size_t)GR_STAGES * GR_STAGE_DBL;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	// 16-byte copies need even column offsets (pointer alignment), even leading dimensions and
+	// even tile widths; anything else takes the 8-byte path
+	const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) &&
+	                  (p % 2 == 0) && (q % 2 == 0);
+	if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+	else      gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
 	B200_KERNEL_CHECK();
 	gram_reduce_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, (int)chunks, part, alpha, c_dev,
 	                                                                        c_rs, c_cs, mode == 'S' ? 1 : 0);
@@ -231,21 +299,58 @@ constexpr int LC_BN = 64;     // output columns per CTA
 constexpr int LC_BK = 16;     // slice of the contraction (columns of X / rows of C)
 constexpr int LC_SX = 20;     // Xs row stride, == 4 mod 16
 constexpr int LC_SC = 68;     // Cs row stride, == 4 mod 16
+constexpr int LC_STAGES = 3;
+constexpr int LC_STAGE_DBL = LC_BM * LC_SX + LC_BK * LC_SC;
 
-// C is device column-major (ldc).  8 warps, warp w owns rows [16w,16w+16) x 64 columns.
-template <bool HAS_BETA>
-__global__ void __launch_bounds__(256)
+// C: element (k,j) at c[k*c_rs + j*c_cs].  blockIdx.x = column tile (fastest: the CTAs that
+// re-read one X row tile run together), blockIdx.y = row tile.  8 warps, warp w owns rows
+// [16w,16w+16) x 64 columns; 3-stage cp.async ring over the contraction dimension.
+template <bool HAS_BETA, bool AL16>
+__global__ void __launch_bounds__(256, 2)
 lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double *__restrict__ c, int c_rs,
                int c_cs, const double *__restrict__ beta, int incb, double *y, int ldy)
 {
-	__shared__ double Xs[LC_BM][LC_SX];
-	__shared__ double Cs[LC_BK][LC_SC];
+	extern __shared__ __align__(16) double lsm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, t = lane & 3;
-	const long long r0 = (long long)blockIdx.x * LC_BM;
-	const int n0 = blockIdx.y * LC_BN;
+	const long long r0 = (long long)blockIdx.y * LC_BM;
+	const int n0 = blockIdx.x * LC_BN;
 	const int nt = min(LC_BN, q - n0);
 	const int nq8 = (nt + 7) >> 3;
+	const int ktiles = (p + LC_BK - 1) / LC_BK;
+
+	auto load_stage = [&](int stage, int kt) {
+		double *Xs = lsm + (size_t)stage * LC_STAGE_DBL, *Cs = Xs + LC_BM * LC_SX;
+		const int k0 = kt * LC_BK;
+		if (AL16) {
+			for (int i = tid; i < LC_BM * (LC_BK / 2); i += 256) {
+				const int rr = i / (LC_BK / 2), kk = (i - rr * (LC_BK / 2)) * 2;
+				const long long r = r0 + rr;
+				const bool ok = (r < n) && (k0 + kk < p);          // p is even on this path
+				cp_async16(Xs + rr * LC_SX + kk, ok ? x + (size_t)r * ldx + k0 + kk : x, ok);
+			}
+		} else {
+			for (int i = tid; i < LC_BM * LC_BK; i += 256) {
+				const int rr = i / LC_BK, kk = i - rr * LC_BK;
+				const long long r = r0 + rr;
+				const bool ok = (r < n) && (k0 + kk < p);
+				cp_async8(Xs + rr * LC_SX + kk, ok ? x + (size_t)r * ldx + k0 + kk : x, ok);
+			}
+		}
+		if (c_rs == 1) {             // column-major C: walk down columns
+			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
+				const int cc = i / LC_BK, kk = i - cc * LC_BK;
+				const bool ok = (k0 + kk < p) && (cc < nt);
+				cp_async8(Cs + kk * LC_SC + cc, ok ? c + (size_t)(n0 + cc) * c_cs + k0 + kk : c, ok);
+			}
+		} else {                     // row-major (or general strides): walk along rows
+			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
+				const int kk = i / LC_BN, cc = i - kk * LC_BN;
+				const bool ok = (k0 + kk < p) && (cc < nt);
+				cp_async8(Cs + kk * LC_SC + cc, ok ? c + (size_t)(k0 + kk) * c_rs + (size_t)(n0 + cc) * c_cs : c, ok);
+			}
+		}
+	};
 
 	double acc[2][8][2];
 #pragma unroll
@@ -253,39 +358,35 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 #pragma unroll
 		for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-	for (int k0 = 0; k0 < p; k0 += LC_BK) {
-		for (int i = tid; i < LC_BM * LC_BK; i += 256) {
-			const int rr = i / LC_BK, kk = i - rr * LC_BK;
-			const long long r = r0 + rr;
-			Xs[rr][kk] = (r < n && k0 + kk < p) ? x[(size_t)r * ldx + k0 + kk] : 0.0;
-		}
-		if (c_rs == 1) {             // column-major C: walk down columns
-			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
-				const int cc = i / LC_BK, kk = i - cc * LC_BK;
-				Cs[kk][cc] = (k0 + kk < p && cc < nt) ? c[(size_t)(n0 + cc) * c_cs + k0 + kk] : 0.0;
-			}
-		} else {                     // row-major (or general strides): walk along rows
-			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
-				const int kk = i / LC_BN, cc = i - kk * LC_BN;
-				Cs[kk][cc] = (k0 + kk < p && cc < nt) ? c[(size_t)(k0 + kk) * c_rs + (size_t)(n0 + cc) * c_cs] : 0.0;
-			}
-		}
+#pragma unroll
+	for (int s = 0; s < LC_STAGES - 1; ++s) {
+		if (s < ktiles) load_stage(s, s);
+		cp_async_commit();
+	}
+	for (int kt = 0; kt < ktiles; ++kt) {
+		cp_async_wait<LC_STAGES - 2>();
 		__syncthreads();
+		{
+			const int nk = kt + LC_STAGES - 1;
+			if (nk < ktiles) load_stage(nk % LC_STAGES, nk);
+			cp_async_commit();
+		}
+		const double *Xs = lsm + (size_t)(kt % LC_STAGES) * LC_STAGE_DBL, *Cs = Xs + LC_BM * LC_SX;
 #pragma unroll
 		for (int ks = 0; ks < LC_BK; ks += 4) {
-			const double a0 = Xs[warp * 16 + g][ks + t];
-			const double a1 = Xs[warp * 16 + 8 + g][ks + t];
+			const double a0 = Xs[(warp * 16 + g) * LC_SX + ks + t];
+			const double a1 = Xs[(warp * 16 + 8 + g) * LC_SX + ks + t];
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				if (j < nq8) {
-					const double b = Cs[ks + t][j * 8 + g];
+					const double b = Cs[(ks + t) * LC_SC + j * 8 + g];
 					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
 					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
 				}
 			}
 		}
-		__syncthreads();
 	}
+	cp_async_wait<0>();
 #pragma unroll
 	for (int i = 0; i < 2; ++i) {
 		const long long r = r0 + warp * 16 + i * 8 + g;
@@ -337,9 +438,24 @@ int b200k_lincomb(long long n, int p, int q, const double *x, int ldx, const dou
 		B200_KERNEL_CHECK();
 		return 0;
 	}
-	dim3 grid((unsigned)((n + LC_BM - 1) / LC_BM), b200_ceil_div(q, LC_BN));
-	if (beta_dev) lincomb_kernel<true><<<grid, 256, 0, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
-	else          lincomb_kernel<false><<<grid, 256, 0, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, nullptr, 0, y, ldy);
+	dim3 grid(b200_ceil_div(q, LC_BN), (unsigned)((n + LC_BM - 1) / LC_BM));
+	const size_t smem = sizeof(double) * (size_t)LC_STAGES * LC_STAGE_DBL;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(lincomb_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B200_CUDA(cudaFuncSetAttribute(lincomb_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B200_CUDA(cudaFuncSetAttribute(lincomb_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B200_CUDA(cudaFuncSetAttribute(lincomb_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	const bool al16 = ((uintptr_t)x % 16 == 0) && (ldx % 2 == 0) && (p % 2 == 0);
+	if (beta_dev) {
+		if (al16) lincomb_kernel<true, true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
+		else      lincomb_kernel<true, false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
+	} else {
+		if (al16) lincomb_kernel<false, true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, nullptr, 0, y, ldy);
+		else      lincomb_kernel<false, false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, nullptr, 0, y, ldy);
+	}
 	B200_KERNEL_CHECK();
 	return 0;
 }

@@ -5,7 +5,7 @@
 // ax <- ax - lam[c]*bx ; res[c] = ||ax[:,c]||_2   (reference src/ops_eig_sol_gcg.c:214-224)
 template <int CPT>
 __global__ void __launch_bounds__(RED_THREADS)
-residual_kernel(long long n, int k, long long rows_per_chunk, double *ax, int ldax, const double *bx, int ldbx,
+residual_kernel(long long n, int k, long long rows_per_chunk, double *__restrict__ ax, int ldax, const double *__restrict__ bx, int ldbx,
                 const double *__restrict__ lam, double *res, double *part, unsigned *ticket)
 {
 	extern __shared__ double sm[];
@@ -18,6 +18,7 @@ residual_kernel(long long n, int k, long long rows_per_chunk, double *ax, int ld
 		const int c = threadIdx.x + i * cx;
 		acc[0][i] = 0.0; l[i] = (c < k) ? lam[c] : 0.0;
 	}
+#pragma unroll 4
 	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
 #pragma unroll
 		for (int i = 0; i < CPT; ++i) {

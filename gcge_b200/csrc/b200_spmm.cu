@@ -12,6 +12,12 @@
 // so the result is bit-identical to the reference on every input.
 #include "b200_internal.h"
 
+// Matrix entries are fetched cooperatively: the G lanes of a row group load G consecutive
+// (value, column) pairs with one coalesced request each and hand them round with shuffles,
+// instead of every lane issuing the same broadcast load per entry -- the L1 wavefront count
+// per entry drops from 2 + ceil(8k/128) to ceil(8k/128) (+2/G), and L1TEX issue, not HBM, is
+// what bounds this kernel (profiles/).  Control flow is kept warp-uniform (loop bounds are
+// warp maxima) so the shuffles are always fully converged.
 template <int G, int CPL>
 __global__ void __launch_bounds__(256)
 spmm_csr_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
@@ -22,24 +28,49 @@ spmm_csr_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ c
 	const int gl = threadIdx.x % G;                          // lane inside the row group
 	const int groups_per_cta = 256 / G;
 	const long long row = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;
-	if (row >= nrows) return;
-	const int e0 = __ldg(rp + row), e1 = __ldg(rp + row + 1);
+	const bool live = row < nrows;
+	const int e0 = live ? __ldg(rp + row) : 0, e1 = live ? __ldg(rp + row + 1) : 0;
 	for (int cbase = 0; cbase < k; cbase += G * CPL) {
 		double acc[CPL];
 		bool on[CPL];
 #pragma unroll
-		for (int i = 0; i < CPL; ++i) { acc[i] = 0.0; on[i] = (cbase + gl + i * G) < k; }
-		for (int e = e0; e < e1; ++e) {
-			const double a = __ldg(va + e);
-			const double *xr = x + (size_t)__ldg(ci + e) * ldx + cbase + gl;
+		for (int i = 0; i < CPL; ++i) { acc[i] = 0.0; on[i] = live && (cbase + gl + i * G) < k; }
+		if (G >= 8) {
+			const int nchunk = (e1 - e0 + G - 1) / G;
+			const int nchunk_max = __reduce_max_sync(0xffffffffu, nchunk);
+			for (int ch = 0; ch < nchunk_max; ++ch) {
+				const int eb = e0 + ch * G;
+				int cnt = e1 - eb; cnt = cnt < 0 ? 0 : (cnt > G ? G : cnt);
+				const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
+				double a_l = 0.0; int c_l = 0;
+				if (gl < cnt) { a_l = __ldg(va + eb + gl); c_l = __ldg(ci + eb + gl); }
+#pragma unroll 4
+				for (int j = 0; j < cnt_max; ++j) {
+					const double a = __shfl_sync(0xffffffffu, a_l, j, G);
+					const int col = __shfl_sync(0xffffffffu, c_l, j, G);
+					if (j < cnt) {
+						const double *xr = x + (size_t)col * ldx + cbase + gl;
+#pragma unroll
+						for (int i = 0; i < CPL; ++i)
+							if (on[i]) acc[i] = __dadd_rn(acc[i], __dmul_rn(a, xr[i * G]));
+					}
+				}
+			}
+		} else {
+			for (int e = e0; e < e1; ++e) {
+				const double a = __ldg(va + e);
+				const double *xr = x + (size_t)__ldg(ci + e) * ldx + cbase + gl;
+#pragma unroll
+				for (int i = 0; i < CPL; ++i)
+					if (on[i]) acc[i] = __dadd_rn(acc[i], __dmul_rn(a, xr[i * G]));
+			}
+		}
+		if (live) {
+			double *yr = y + (size_t)row * ldy + cbase + gl;
 #pragma unroll
 			for (int i = 0; i < CPL; ++i)
-				if (on[i]) acc[i] = __dadd_rn(acc[i], __dmul_rn(a, xr[i * G]));
+				if (on[i]) yr[i * G] = acc[i];
 		}
-		double *yr = y + (size_t)row * ldy + cbase + gl;
-#pragma unroll
-		for (int i = 0; i < CPL; ++i)
-			if (on[i]) yr[i * G] = acc[i];
 	}
 }
 

@@ -45,6 +45,9 @@ long long b200_kernel_launches(void);  /* number of kernels this library launche
  * start records an event, stop records a second one, synchronises and returns milliseconds */
 int  b200_timer_start(void);
 int  b200_timer_stop(double *ms);
+/* measured FP64 tensor-core (DMMA m8n8k4) issue ceiling of this GPU, TFLOP/s: the roofline
+ * denominator of the Gram / LinearComb kernels */
+int  b200_measure_dmma_peak(double *tflops);
 /* overwrite a buffer larger than L2 so the next timed kernel starts cold */
 int  b200_flush_l2(void);
 
