@@ -90,6 +90,10 @@ def lib():
         L.b200_block_pcg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p, c_int_p,
                                      C.POINTER(_BpcgParams), C.c_void_p, C.c_void_p, C.c_void_p, c_int_p, c_dbl_p]
         L.b200_dense_syev.argtypes = [C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int, c_int_p]
+        L.b200_prof_get.argtypes = [C.c_int, C.POINTER(C.c_char_p), c_dbl_p, C.POINTER(C.c_longlong), c_dbl_p, c_dbl_p]
+        L.b200_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.b200_host_unregister.argtypes = [C.c_void_p]
+        L.b200_measure_dmma_peak.argtypes = [c_dbl_p]
         L.b200_gcg_default_params.argtypes = [C.c_int, C.POINTER(GCGParams)]
         L.b200_gcg_default_params.restype = None
         L.b200_gcg_solve.argtypes = [C.c_void_p, C.c_void_p, c_dbl_p, C.c_void_p, C.c_int, c_int_p,
@@ -135,6 +139,35 @@ def timer_stop() -> float:
 
 def flush_l2():
     _chk(lib().b200_flush_l2())
+
+
+def prof_enable(on: bool = True):
+    _chk(lib().b200_prof_enable(1 if on else 0))
+
+
+def prof_report() -> dict:
+    """{class: {ms, calls, bytes, flops}} since prof_enable(True) (device time from CUDA events
+    on the library stream, algorithmic bytes/flops of SURVEY.md 8d)."""
+    out = {}
+    for c in range(lib().b200_prof_classes()):
+        name = C.c_char_p(); ms = C.c_double(); calls = C.c_longlong(); by = C.c_double(); fl = C.c_double()
+        _chk(lib().b200_prof_get(c, C.byref(name), C.byref(ms), C.byref(calls), C.byref(by), C.byref(fl)))
+        out[name.value.decode()] = {"ms": ms.value, "calls": calls.value, "bytes": by.value, "flops": fl.value}
+    return out
+
+
+def host_register(a: np.ndarray):
+    _chk(lib().b200_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    _chk(lib().b200_host_unregister(a.ctypes.data))
+
+
+def measure_dmma_peak() -> float:
+    t = C.c_double(0)
+    _chk(lib().b200_measure_dmma_peak(C.byref(t)))
+    return t.value
 
 
 def libc_srand(seed: int = 0):

@@ -208,6 +208,7 @@ extern "C" int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const do
 {
 	const int k = st->k;
 	B200_CHECK(k >= 1 && k <= 128, "BlockPCG: %d columns (1..128 supported per block)", k);
+	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 5.0 * n * k);
 	const RedGeom g = red_geometry(n, k);
 	const size_t smem = sizeof(double) * (size_t)g.ry * k;
 	BPCG_DISPATCH_CPT(k, (bpcg_begin_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(
@@ -220,6 +221,7 @@ extern "C" int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const
                                    double *p, int ldp, int first)
 {
 	const int k = st->k;
+	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 2.0 * n * k);
 	int rows = 4096 / k; if (rows < 1) rows = 1;
 	bpcg_update_p_kernel<<<(unsigned)((n + rows - 1) / rows), 256, 0, g_b200.stream>>>(n, k, rows, r, ldr, p, ldp,
 	                                                                                 first, *st);
@@ -231,6 +233,7 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
                               double *w, int ldw, double shift, const double *z, int ldz)
 {
 	const int k = st->k;
+	B200Prof prof(B200_PROF_BPCG, (z ? 32.0 : 16.0) * n * k, (z ? 4.0 : 2.0) * n * k);
 	const RedGeom g = red_geometry(n, k);
 	const size_t smem = sizeof(double) * (size_t)g.ry * k;
 	BPCG_DISPATCH_CPT(k, (bpcg_ptw_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(
@@ -244,6 +247,7 @@ extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, cons
                                     double rate, double tol)
 {
 	const int k = st->k;
+	B200Prof prof(B200_PROF_BPCG, 48.0 * n * k, 6.0 * n * k);
 	const RedGeom g = red_geometry(n, k);
 	const size_t smem = sizeof(double) * (size_t)g.ry * k;
 	BPCG_DISPATCH_CPT(k, (bpcg_update_xr_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(

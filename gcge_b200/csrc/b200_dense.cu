@@ -236,6 +236,9 @@ int b200k_gram(char mode, long long n, int p, int q, double alpha, const double 
 {
 	if (p <= 0 || q <= 0) return 0;
 	cudaStream_t st = g_b200.stream;
+	B200Prof prof(mode == 'D' ? B200_PROF_DOTS : (n <= 1024 ? B200_PROF_SMALL : B200_PROF_GRAM),
+	              mode == 'D' ? 16.0 * n * p : 8.0 * n * ((double)p + q) + 8.0 * p * q,
+	              mode == 'D' ? 2.0 * n * p : 2.0 * n * p * q);
 	if (mode == 'D') {
 		const int k = p;
 		if (n <= 0) {
@@ -429,7 +432,11 @@ int b200k_lincomb(long long n, int p, int q, const double *x, int ldx, const dou
 {
 	if (n <= 0 || q <= 0) return 0;
 	cudaStream_t st = g_b200.stream;
-	if (x == nullptr || c_dev == nullptr || p <= 0) {
+	const bool scale_only = (x == nullptr || c_dev == nullptr || p <= 0);
+	B200Prof prof(scale_only ? B200_PROF_AXPBY : (n <= 1024 ? B200_PROF_SMALL : B200_PROF_LINCOMB),
+	              scale_only ? 16.0 * n * q : 8.0 * n * ((double)p + q + (beta_dev ? q : 0)) + 8.0 * p * q,
+	              scale_only ? 1.0 * n * q : 2.0 * n * p * q);
+	if (scale_only) {
 		// reference app/app_lapack.c:476-505: without x/coef only the dscal part runs, and
 		// with beta == NULL nothing runs at all
 		if (beta_dev == nullptr) return 0;
@@ -478,6 +485,7 @@ __global__ void colscale_vec_kernel(long long n, int q, int rows_per_cta, const 
 int b200k_colscale(long long n, int q, const double *s_dev, int invert, double *y, int ldy)
 {
 	if (n <= 0 || q <= 0) return 0;
+	B200Prof prof(B200_PROF_AXPBY, 16.0 * n * q, 1.0 * n * q);
 	int rows = 4096 / q; if (rows < 1) rows = 1;
 	colscale_vec_kernel<<<(unsigned)((n + rows - 1) / rows), 256, 0, g_b200.stream>>>(n, q, rows, s_dev, invert, y, ldy);
 	B200_KERNEL_CHECK();

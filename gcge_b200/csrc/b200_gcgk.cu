@@ -45,6 +45,7 @@ extern "C" int b200k_residual_norms(long long n, int k, double *ax, int ldax, co
 {
 	if (k <= 0) return 0;
 	B200_CHECK(k <= 128, "residual norms: %d columns (<=128 per call)", k);
+	B200Prof prof(B200_PROF_DOTS, 24.0 * n * k, 4.0 * n * k);
 	const RedGeom g = red_geometry(n, k);
 	char *base = (char *)b200_scratch(0, sizeof(double) * (size_t)(g.chunks + 1) * k + 64);
 	if (!base) return 1;

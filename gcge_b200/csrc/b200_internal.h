@@ -62,3 +62,15 @@ extern b200_ctx g_b200;
 
 static inline int b200_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+
+// ---- per-kernel-class device timing (b200_prof_*, include/gcge_b200.h) ---------------------
+// A scope object brackets the launches of one b200k_* call with two CUDA events on the library
+// stream and books the call's ALGORITHMIC bytes / flops to its class.  Free
+// when profiling is off.  Scopes do not nest: an inner scope is a no-op.
+enum { B200_PROF_SPMM = 0, B200_PROF_GRAM, B200_PROF_LINCOMB, B200_PROF_AXPBY, B200_PROF_DOTS,
+       B200_PROF_BPCG, B200_PROF_PANEL, B200_PROF_SYEV, B200_PROF_SMALL, B200_PROF_NCLS };
+struct B200Prof {
+	int slot;
+	B200Prof(int cls, double bytes, double flops);
+	~B200Prof();
+};

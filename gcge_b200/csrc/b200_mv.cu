@@ -209,6 +209,7 @@ int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx, doub
 	const bool has_x = (x != nullptr);
 	const bool has_y = (beta != 0.0);
 	if (!has_x && has_y && beta == 1.0) return 0;
+	B200Prof prof(B200_PROF_AXPBY, 8.0 * n * k * (1 + (has_x ? 1 : 0) + (has_y ? 1 : 0)), 2.0 * n * k);
 	int rows = 4096 / k; if (rows < 1) rows = 1;
 	const unsigned grid = (unsigned)((n + rows - 1) / rows);
 	const int threads = 256;

@@ -85,6 +85,7 @@ extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_
                                const double *scale_in, double *scale_out)
 {
 	B200_CHECK(k >= 1 && k <= 128, "orth panel: %d columns (1..128 supported)", k);
+	B200Prof prof(B200_PROF_PANEL, 16.0 * k * k, 2.0 * k * k * k / 3.0);
 	const size_t smem = sizeof(double) * ((size_t)2 * k * (k + 1) + 2 * k);
 	static bool attr_set = false;
 	if (!attr_set) {

@@ -197,3 +197,96 @@ extern "C" int b200_flush_l2(void)
 	B200_CUDA(cudaMemsetAsync(buf, 1, bytes, g_b200.stream));
 	return 0;
 }
+
+// ------------------------------------------------------------------ per-class profiling
+#include <vector>
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct ProfState {
+	bool on = false, open = false;
+	std::vector<ProfRec> pend;          // recorded, not yet resolved
+	std::vector<cudaEvent_t> pool;      // free events
+	double ms[B200_PROF_NCLS] = {}, bytes[B200_PROF_NCLS] = {}, flops[B200_PROF_NCLS] = {};
+	long long calls[B200_PROF_NCLS] = {};
+} g_prof;
+const char *g_prof_names[B200_PROF_NCLS] = {"spmm", "gram", "lincomb", "axpby", "dots", "bpcg_fused",
+                                            "orth_panel", "syev_jacobi", "small_dense"};
+cudaEvent_t prof_event()
+{
+	if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+void prof_resolve()
+{
+	if (g_prof.pend.empty()) return;
+	cudaEventSynchronize(g_prof.pend.back().b);
+	for (const ProfRec &r : g_prof.pend) {
+		float f = 0.f;
+		if (cudaEventElapsedTime(&f, r.a, r.b) == cudaSuccess) g_prof.ms[r.cls] += f;
+		g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b);
+	}
+	g_prof.pend.clear();
+}
+}  // namespace
+
+B200Prof::B200Prof(int cls, double bytes, double flops) : slot(-1)
+{
+	if (!g_prof.on || g_prof.open) return;
+	ProfRec r; r.cls = cls; r.a = prof_event(); r.b = prof_event();
+	if (!r.a || !r.b) return;
+	cudaEventRecord(r.a, g_b200.stream);
+	g_prof.pend.push_back(r);
+	g_prof.open = true;
+	g_prof.calls[cls] += 1; g_prof.bytes[cls] += bytes; g_prof.flops[cls] += flops;
+	slot = (int)g_prof.pend.size() - 1;
+}
+
+B200Prof::~B200Prof()
+{
+	if (slot < 0) return;
+	cudaEventRecord(g_prof.pend[slot].b, g_b200.stream);
+	g_prof.open = false;
+	if (g_prof.pend.size() >= 4096) prof_resolve();
+}
+
+extern "C" int b200_prof_enable(int on)
+{
+	B200_REQUIRE_INIT();
+	prof_resolve();
+	if (on) {
+		for (int i = 0; i < B200_PROF_NCLS; ++i) { g_prof.ms[i] = g_prof.bytes[i] = g_prof.flops[i] = 0.0; g_prof.calls[i] = 0; }
+	}
+	g_prof.on = on != 0;
+	return 0;
+}
+
+extern "C" int b200_prof_classes(void) { return B200_PROF_NCLS; }
+
+extern "C" int b200_prof_get(int cls, const char **name, double *ms, long long *calls, double *bytes, double *flops)
+{
+	B200_CHECK(cls >= 0 && cls < B200_PROF_NCLS, "b200_prof_get: class %d out of range", cls);
+	prof_resolve();
+	if (name) *name = g_prof_names[cls];
+	if (ms) *ms = g_prof.ms[cls];
+	if (calls) *calls = g_prof.calls[cls];
+	if (bytes) *bytes = g_prof.bytes[cls];
+	if (flops) *flops = g_prof.flops[cls];
+	return 0;
+}
+
+extern "C" int b200_host_register(void *host, unsigned long long bytes)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(host && bytes, "b200_host_register: bad arguments");
+	B200_CUDA(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault));
+	return 0;
+}
+
+extern "C" int b200_host_unregister(void *host)
+{
+	B200_CHECK(host, "b200_host_unregister: bad arguments");
+	B200_CUDA(cudaHostUnregister(host));
+	return 0;
+}

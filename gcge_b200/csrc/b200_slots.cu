@@ -69,8 +69,7 @@ extern "C" int b200_mv_qtap(char ntsA, char ntsdQAP, const b200_mv *Q, const b20
 		const int out_rows = tr ? A->ncols : A->nrows, in_rows = tr ? A->nrows : A->ncols;
 		B200_CHECK(P->nrows == in_rows && ws->nrows == out_rows && Q->nrows == out_rows,
 		           "b200_mv_qtap: shapes do not match the matrix");
-		int rc = tr ? b200k_spmm(A->ncols, A->t_rp, A->t_ci, A->t_va, P->d + start[1], P->ld, ws->d, ws->ld, nc)
-		            : b200k_spmm(A->nrows, A->rp, A->ci, A->va, P->d + start[1], P->ld, ws->d, ws->ld, nc);
+		int rc = b200k_spmm(A, tr ? 1 : 0, P->d + start[1], P->ld, ws->d, ws->ld, nc, nullptr);
 		if (rc) return rc;
 		pd = ws->d; pld = ws->ld; n = ws->nrows;
 	} else {

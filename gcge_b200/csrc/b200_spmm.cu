@@ -74,6 +74,101 @@ spmm_csr_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ c
 	}
 }
 
+// 128-bit variant (even k): lane l of a row group owns the column PAIR (2l, 2l+1), so one
+// LDG.128 per matrix entry covers 2G columns -- half the load and address instructions of the
+// scalar kernel for the same bytes.  The scalar kernel is instruction-issue bound (~380 warp
+// instructions per 15-entry row at k = 40, profiles/), so the inner loop is kept branch-free:
+// lanes past the last column pair redo the last pair (same addresses, no extra wavefront, no
+// store), gathers are unconditional (padding entries point at row 0 with a zero value that is
+// never accumulated) and only the two accumulate statements are predicated.  Needs 16-byte
+// aligned row segments (even column offsets / leading dimensions); the launcher falls back
+// to the scalar kernel otherwise.
+template <int G>
+__global__ void __launch_bounds__(256)
+spmm_csr_v2_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
+                   const double *__restrict__ va, const double *x, int ldx, double *y, int ldy, int k,
+                   const int *__restrict__ gate)
+{
+	if (gate != nullptr && *gate == 0) return;
+	const int gl = threadIdx.x % G;
+	const int groups_per_cta = 256 / G;
+	const long long row = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;
+	const bool live = row < nrows;
+	const int e0 = live ? __ldg(rp + row) : 0, e1 = live ? __ldg(rp + row + 1) : 0;
+	const size_t ldxb = (size_t)ldx;
+	for (int cbase = 0; cbase < k; cbase += 2 * G) {
+		int c = cbase + 2 * gl;
+		const bool store = live && (c + 1 < k);
+		if (c > k - 2) c = k - 2;
+		const double *xb = x + c;
+		double acc0 = 0.0, acc1 = 0.0;
+		// Loads are issued in explicit batches of U (all shuffles, then all gathers, then the
+		// in-order accumulation): a warp keeps U independent 128-bit gathers in flight instead
+		// of one, which is what this latency-bound loop needs (one request per ~12 cycles per SM
+		// before batching, independent of the request width -- profiles/).
+		constexpr int U = 8;
+		if (G >= 8) {
+			const int nchunk = (e1 - e0 + G - 1) / G;
+			const int nchunk_max = (G == 32) ? nchunk : __reduce_max_sync(0xffffffffu, nchunk);
+			for (int ch = 0; ch < nchunk_max; ++ch) {
+				const int eb = e0 + ch * G;
+				int cnt = e1 - eb; cnt = cnt < 0 ? 0 : (cnt > G ? G : cnt);
+				const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(0xffffffffu, cnt);
+				double a_l = 0.0; int c_l = 0;
+				if (gl < cnt) { a_l = __ldg(va + eb + gl); c_l = __ldg(ci + eb + gl); }
+				for (int j0 = 0; j0 < cnt_max; j0 += U) {
+					double a[U]; int col[U]; double2 v[U];
+#pragma unroll
+					for (int u = 0; u < U; ++u) {
+						a[u] = __shfl_sync(0xffffffffu, a_l, j0 + u, G);
+						col[u] = __shfl_sync(0xffffffffu, c_l, j0 + u, G);
+					}
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						v[u] = *reinterpret_cast<const double2 *>(xb + (size_t)col[u] * ldxb);
+#pragma unroll
+					for (int u = 0; u < U; ++u) {
+						const double t0 = __dadd_rn(acc0, __dmul_rn(a[u], v[u].x));
+						const double t1 = __dadd_rn(acc1, __dmul_rn(a[u], v[u].y));
+						if (j0 + u < cnt) { acc0 = t0; acc1 = t1; }
+					}
+				}
+			}
+		} else {
+			for (int eb = e0; eb < e1; eb += U) {
+				double a[U]; int col[U]; double2 v[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const bool ok = eb + u < e1;
+					a[u] = ok ? __ldg(va + eb + u) : 0.0;
+					col[u] = ok ? __ldg(ci + eb + u) : 0;
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u)
+					v[u] = *reinterpret_cast<const double2 *>(xb + (size_t)col[u] * ldxb);
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const double t0 = __dadd_rn(acc0, __dmul_rn(a[u], v[u].x));
+					const double t1 = __dadd_rn(acc1, __dmul_rn(a[u], v[u].y));
+					if (eb + u < e1) { acc0 = t0; acc1 = t1; }
+				}
+			}
+		}
+		if (store) *reinterpret_cast<double2 *>(y + (size_t)row * ldy + c) = make_double2(acc0, acc1);
+	}
+}
+
+template <int G>
+static int launch_spmm_v2(int nrows, const int *rp, const int *ci, const double *va,
+                          const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const int groups_per_cta = 256 / G;
+	const unsigned grid = (unsigned)(((long long)nrows + groups_per_cta - 1) / groups_per_cta);
+	spmm_csr_v2_kernel<G><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
 template <int G, int CPL>
 static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va,
                        const double *x, int ldx, double *y, int ldy, int k, const int *gate)
@@ -85,16 +180,24 @@ static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va
 	return 0;
 }
 
-int b200k_spmm(int nrows, const int *rp, const int *ci, const double *va,
-               const double *x, int ldx, double *y, int ldy, int k)
+int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
+               const int *gate)
 {
-	return b200k_spmm_gated(nrows, rp, ci, va, x, ldx, y, ldy, k, nullptr);
-}
-
-int b200k_spmm_gated(int nrows, const int *rp, const int *ci, const double *va,
-                     const double *x, int ldx, double *y, int ldy, int k, const int *gate)
-{
+	const int nrows = trans ? M->ncols : M->nrows;
+	const int *rp = trans ? M->t_rp : M->rp, *ci = trans ? M->t_ci : M->ci;
+	const double *va = trans ? M->t_va : M->va;
 	if (nrows <= 0 || k <= 0) return 0;
+	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
+	              2.0 * M->nnz * k);
+	const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0);
+	if (al16 && k >= 2 && k % 2 == 0) {
+		if (k <= 2)       return launch_spmm_v2<1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+		else if (k <= 4)  return launch_spmm_v2<2>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+		else if (k <= 8)  return launch_spmm_v2<4>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+		else if (k <= 16) return launch_spmm_v2<8>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+		else if (k <= 32) return launch_spmm_v2<16>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+		return launch_spmm_v2<32>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	}
 	if (k == 1)       return launch_spmm<1, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k == 2)  return launch_spmm<2, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k <= 4)  return launch_spmm<4, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
@@ -128,7 +231,5 @@ extern "C" int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv
 		const bool overlap = start[0] < end[1] && start[1] < end[0];
 		B200_CHECK(!overlap, "b200_mat_dot_multivec: x and y column ranges overlap on one multi-vector");
 	}
-	if (trans)
-		return b200k_spmm(A->ncols, A->t_rp, A->t_ci, A->t_va, x->d + start[0], x->ld, y->d + start[1], y->ld, k);
-	return b200k_spmm(A->nrows, A->rp, A->ci, A->va, x->d + start[0], x->ld, y->d + start[1], y->ld, k);
+	return b200k_spmm(A, trans, x->d + start[0], x->ld, y->d + start[1], y->ld, k, nullptr);
 }

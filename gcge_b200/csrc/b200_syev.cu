@@ -152,6 +152,7 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
                                  int *sweeps_host)
 {
 	B200_CHECK(n >= 1, "syev: n = %d", n);
+	B200Prof prof(B200_PROF_SYEV, 24.0 * n * n, 0.0);
 	cudaStream_t st = g_b200.stream;
 	int N = (n + 1) & ~1; if (N < 2) N = 2;
 	const size_t nn = (size_t)N * N, vn = (size_t)n * N;

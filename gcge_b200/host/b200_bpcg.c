@@ -26,10 +26,10 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	if (b200k_bpcg_state(k, &st)) return 1;
 	const double shift = prm->shift;
 	/* r = (A + shift B) x, then r = b - r and the initial masks */
-	if (b200k_spmm(A->nrows, A->rp, A->ci, A->va, x, ldx, r, ldr, k)) return 1;
+	if (b200k_spmm(A, 0, x, ldx, r, ldr, k, NULL)) return 1;
 	if (shift != 0.0) {
 		if (B) {
-			if (b200k_spmm(B->nrows, B->rp, B->ci, B->va, x, ldx, p, ldp, k)) return 1;
+			if (b200k_spmm(B, 0, x, ldx, p, ldp, k, NULL)) return 1;
 			if (b200k_axpby(n, k, shift, p, ldp, 1.0, r, ldr)) return 1;
 		} else {
 			if (b200k_axpby(n, k, shift, x, ldx, 1.0, r, ldr)) return 1;
@@ -38,12 +38,12 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	if (b200k_bpcg_begin(n, &st, b, ldb, r, ldr, prm->tol, prm->tol_type == 1)) return 1;
 	for (int it = 0; it < prm->max_iter; ++it) {
 		if (b200k_bpcg_update_p(n, &st, r, ldr, p, ldp, it == 0)) return 1;
-		if (b200k_spmm_gated(A->nrows, A->rp, A->ci, A->va, p, ldp, w, ldw, k, st.counters)) return 1;
+		if (b200k_spmm(A, 0, p, ldp, w, ldw, k, st.counters)) return 1;
 		if (shift != 0.0) {
 			if (B) {
 				/* the right-hand side is dead after the initial residual: use it as B p, like the
 				 * reference's MatDotMultiVecShift does (src/ops_eig_sol_gcg.c:63-96) */
-				if (b200k_spmm_gated(B->nrows, B->rp, B->ci, B->va, p, ldp, b, ldb, k, st.counters)) return 1;
+				if (b200k_spmm(B, 0, p, ldp, b, ldb, k, st.counters)) return 1;
 				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, b, ldb)) return 1;
 			} else {
 				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, p, ldp)) return 1;

@@ -46,11 +46,10 @@ int b200k_free(void *dev);
 
 /* y = A x for k columns; separate multiply and add in CSR column order (bit-exact with
  * the reference's scatter loop).  x, y may live in one multi-vector (disjoint columns). */
-int b200k_spmm(int nrows, const int *rp, const int *ci, const double *va,
-               const double *x, int ldx, double *y, int ldy, int k);
-/* same, but the kernel returns immediately when *gate_dev == 0 (device-side loop control) */
-int b200k_spmm_gated(int nrows, const int *rp, const int *ci, const double *va,
-                     const double *x, int ldx, double *y, int ldy, int k, const int *gate_dev);
+/* trans != 0 multiplies by the true transpose (the caller's CCS arrays read as CSR).
+ * gate_dev != NULL: the kernel returns at once when *gate_dev == 0 (device-side loop control) */
+int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
+               const int *gate_dev);
 /* y = alpha x + beta y over n x k; x may be NULL (scale); beta == 0 overwrites. */
 int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx,
                 double beta, double *y, int ldy);

@@ -57,7 +57,7 @@ static double tick(gcg_t *g) { return g->timing ? b200_wtime() : 0.0; }
 
 static int spmm_mv(const b200_mat *M, const double *x, int ldx, double *y, int ldy, long long n, int k)
 {
-	if (M) return b200k_spmm(M->nrows, M->rp, M->ci, M->va, x, ldx, y, ldy, k);
+	if (M) return b200k_spmm(M, 0, x, ldx, y, ldy, k, NULL);
 	return b200k_axpby(n, k, 1.0, x, ldx, 0.0, y, ldy);      /* NULL matrix == identity, reference app/app_ccs.c:134-137 */
 }
 

@@ -31,7 +31,7 @@ static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *
 {
 	const double *y = x1; int ldy = ldx;
 	if (B) {
-		if (b200k_spmm(B->nrows, B->rp, B->ci, B->va, x1, ldx, ws, ldws, kb)) return 1;
+		if (b200k_spmm(B, 0, x1, ldx, ws, ldws, kb, NULL)) return 1;
 		y = ws; ldy = ldws;
 	}
 	if (b200k_gram('S', n, kb, kb, 1.0, x1, ldx, y, ldy, g_dev, kb, 1)) return 1;
@@ -83,7 +83,7 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 			if (s1 > 0) {
 				const double *y = x1; int ldy = x->ld;
 				if (B) {
-					if (b200k_spmm(B->nrows, B->rp, B->ci, B->va, x1, x->ld, ws->d, ws->ld, kb)) return 1;
+					if (b200k_spmm(B, 0, x1, x->ld, ws->d, ws->ld, kb, NULL)) return 1;
 					y = ws->d; ldy = ws->ld;
 				}
 				/* C = -(X0^T B X1), row-major s1 x kb; X1 += X0 C */

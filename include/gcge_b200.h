@@ -50,6 +50,17 @@ int  b200_timer_stop(double *ms);
 int  b200_measure_dmma_peak(double *tflops);
 /* overwrite a buffer larger than L2 so the next timed kernel starts cold */
 int  b200_flush_l2(void);
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, every kernel call of
+ * the library is bracketed by two CUDA events on the library stream and booked, with its
+ * ALGORITHMIC bytes and flops, to one of b200_prof_classes() classes ("spmm",
+ * "gram", "lincomb", "axpby", "dots", "bpcg_fused", "orth_panel", "syev_jacobi", "small_dense").
+ * enable(1) resets the counters; get() synchronises and returns the totals since then. */
+/* page-lock / unlock a caller-owned host buffer so uploads from it run at full PCIe speed */
+int  b200_host_register(void *host, unsigned long long bytes);
+int  b200_host_unregister(void *host);
+int  b200_prof_enable(int on);
+int  b200_prof_classes(void);
+int  b200_prof_get(int cls, const char **name, double *ms, long long *calls, double *bytes, double *flops);
 
 /* ---- matrix: replaces the host CCSMAT the reference's drivers build directly
  *      (reference test/test_app_ccs.c:99-102, :142-184) ------------------------ */
