@@ -43,6 +43,8 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 
 	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
 	A->nrows = nrows; A->ncols = ncols; A->nnz = nnz; A->t_shared = shared; A->row0 = 0;
+	for (int r = 0; r < nrows; ++r) if (rp[r + 1] - rp[r] > A->max_row_nnz) A->max_row_nnz = rp[r + 1] - rp[r];
+	for (int j = 0; j < ncols; ++j) if (j_col[j + 1] - j_col[j] > A->t_max_row_nnz) A->t_max_row_nnz = j_col[j + 1] - j_col[j];
 	cudaStream_t st = g_b200.stream;
 	const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
 	B200_CUDA(cudaMalloc(&A->rp, sizeof(int) * ((size_t)nrows + 1)));

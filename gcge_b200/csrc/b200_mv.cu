@@ -157,31 +157,6 @@ extern "C" int b200_mv_download(const b200_mv *x, int start, int end, double *ho
 	return 0;
 }
 
-// glibc rand() stream, column-major order (reference app/app_lapack.c:322-333).  The values
-// are produced on the host, in the reference's order, from the process-wide generator the
-// reference's drivers seed with srand(0) (reference test/test_eig_sol_gcg.c:87), then staged.
-extern "C" int b200_mv_set_random(b200_mv *x, int start, int end)
-{
-	B200_REQUIRE_INIT();
-	B200_CHECK(x && start >= 0 && end <= x->ncols && start <= end, "b200_mv_set_random: bad arguments");
-	const long long n = x->nrows;
-	if (n == 0 || end == start) return 0;
-	int chunk = (int)(((size_t)64 << 20) / (sizeof(double) * (size_t)n));
-	if (chunk < 1) chunk = 1;
-	for (int c0 = start; c0 < end; c0 += chunk) {
-		const int k = (end - c0 < chunk) ? end - c0 : chunk;
-		double *h = (double *)b200_pinned(1, sizeof(double) * (size_t)n * k);
-		double *stage = (double *)b200_scratch(2, sizeof(double) * (size_t)n * k);
-		if (!h || !stage) return 1;
-		const size_t tot = (size_t)n * k;
-		for (size_t i = 0; i < tot; ++i) h[i] = ((double)rand()) / ((double)RAND_MAX + 1);
-		B200_CUDA(cudaMemcpyAsync(stage, h, sizeof(double) * tot, cudaMemcpyHostToDevice, g_b200.stream));
-		if (b200k_cm_to_rm(n, k, stage, n, x->d + c0, x->ld)) return 1;
-		B200_CUDA(cudaStreamSynchronize(g_b200.stream));
-	}
-	return 0;
-}
-
 // ------------------------------------------------------------------ axpby
 // One CTA handles ROWS_PER_CTA consecutive rows of the n x k block; threads walk the
 // block's elements in memory order (column fastest), so each row contributes one

@@ -74,108 +74,228 @@ spmm_csr_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ c
 	}
 }
 
-// 128-bit variant (even k): lane l of a row group owns the column PAIR (2l, 2l+1), so one
-// LDG.128 per matrix entry covers 2G columns -- half the load and address instructions of the
-// scalar kernel for the same bytes.  The scalar kernel is instruction-issue bound (~380 warp
-// instructions per 15-entry row at k = 40, profiles/), so the inner loop is kept branch-free:
-// lanes past the last column pair redo the last pair (same addresses, no extra wavefront, no
-// store), gathers are unconditional (padding entries point at row 0 with a zero value that is
-// never accumulated) and only the two accumulate statements are predicated.  Needs 16-byte
-// aligned row segments (even column offsets / leading dimensions); the launcher falls back
-// to the scalar kernel otherwise.
-template <int G>
+// Wide variant (k > 4).  G lanes (8, 16 or 32) own one row; lane l accumulates the column
+// pairs (2l, 2l+1) + 2G*pass, so every matrix entry costs one 128-bit gather per pass and the
+// gathered x row is one contiguous segment.  The scalar kernel above spends ~27 warp
+// instructions per matrix entry (64-bit shuffles, selects) and is issue-bound (profiles/);
+// here the row group stages its entries -- one coalesced load of G (value, column) pairs --
+// into shared memory as 16-byte records and the inner loop per entry is
+//     LDS.128 (broadcast)  IMAD.WIDE  LDG.128  2 x DMUL  2 x DADD        (per pass)
+// with U independent gathers in flight.  With G = 32 the loop bounds are warp-uniform and
+// nothing is predicated; narrower groups run to the warp's longest row with the accumulation
+// predicated off past a row's end (padding records point at row 0 and are never added).
+// VEC = false (odd offsets / leading dimensions, odd k) splits the gather into two 64-bit loads.
+template <int G, int NPASS, bool VEC, int U>
 __global__ void __launch_bounds__(256)
-spmm_csr_v2_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
-                   const double *__restrict__ va, const double *x, int ldx, double *y, int ldy, int k,
-                   const int *__restrict__ gate)
+spmm_csr_wide_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
+                     const double *__restrict__ va, const double *x, int ldx, double *y, int ldy, int k,
+                     const int *__restrict__ gate)
 {
 	if (gate != nullptr && *gate == 0) return;
-	const int gl = threadIdx.x % G;
-	const int groups_per_cta = 256 / G;
-	const long long row = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G;
+	constexpr int RPW = 32 / G;                       // rows per warp
+	__shared__ double2 ent_s[8][RPW][G];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int gl = lane % G, rg = lane / G;
+	const long long row = ((long long)blockIdx.x * 8 + warp) * RPW + rg;
 	const bool live = row < nrows;
 	const int e0 = live ? __ldg(rp + row) : 0, e1 = live ? __ldg(rp + row + 1) : 0;
-	const size_t ldxb = (size_t)ldx;
-	for (int cbase = 0; cbase < k; cbase += 2 * G) {
-		int c = cbase + 2 * gl;
-		const bool store = live && (c + 1 < k);
-		if (c > k - 2) c = k - 2;
-		const double *xb = x + c;
-		double acc0 = 0.0, acc1 = 0.0;
-		// Loads are issued in explicit batches of U (all shuffles, then all gathers, then the
-		// in-order accumulation): a warp keeps U independent 128-bit gathers in flight instead
-		// of one, which is what this latency-bound loop needs (one request per ~12 cycles per SM
-		// before batching, independent of the request width -- profiles/).
-		constexpr int U = 8;
-		if (G >= 8) {
-			const int nchunk = (e1 - e0 + G - 1) / G;
-			const int nchunk_max = (G == 32) ? nchunk : __reduce_max_sync(0xffffffffu, nchunk);
-			for (int ch = 0; ch < nchunk_max; ++ch) {
-				const int eb = e0 + ch * G;
-				int cnt = e1 - eb; cnt = cnt < 0 ? 0 : (cnt > G ? G : cnt);
-				const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(0xffffffffu, cnt);
-				double a_l = 0.0; int c_l = 0;
-				if (gl < cnt) { a_l = __ldg(va + eb + gl); c_l = __ldg(ci + eb + gl); }
-				for (int j0 = 0; j0 < cnt_max; j0 += U) {
-					double a[U]; int col[U]; double2 v[U];
+	double2 *ent = ent_s[warp][rg];
+	// column pair of this lane in each pass; lanes past the end redo the last pair (no store)
+	int c[NPASS]; bool st[NPASS];
+	double acc[NPASS][2];
 #pragma unroll
-					for (int u = 0; u < U; ++u) {
-						a[u] = __shfl_sync(0xffffffffu, a_l, j0 + u, G);
-						col[u] = __shfl_sync(0xffffffffu, c_l, j0 + u, G);
-					}
-#pragma unroll
-					for (int u = 0; u < U; ++u)
-						v[u] = *reinterpret_cast<const double2 *>(xb + (size_t)col[u] * ldxb);
-#pragma unroll
-					for (int u = 0; u < U; ++u) {
-						const double t0 = __dadd_rn(acc0, __dmul_rn(a[u], v[u].x));
-						const double t1 = __dadd_rn(acc1, __dmul_rn(a[u], v[u].y));
-						if (j0 + u < cnt) { acc0 = t0; acc1 = t1; }
-					}
-				}
-			}
-		} else {
-			for (int eb = e0; eb < e1; eb += U) {
-				double a[U]; int col[U]; double2 v[U];
+	for (int p = 0; p < NPASS; ++p) {
+		c[p] = 2 * gl + 2 * G * p;
+		st[p] = live && (c[p] < k);
+		if (c[p] > k - 2) c[p] = k - 2 < 0 ? 0 : k - 2;
+		acc[p][0] = 0.0; acc[p][1] = 0.0;
+	}
+	const bool odd_tail = (k & 1);                    // VEC == false only: last pair has one column
+	// gather address = x + column*ldx*8 bytes: one IMAD.WIDE per entry (32-bit column, 32-bit
+	// byte stride, 64-bit base) -- ldx*8 fits an int for any leading dimension below 2^28
+	const int ldx8 = ldx * 8;
+	const char *xbase = reinterpret_cast<const char *>(x);
+	const int nchunk = (e1 - e0 + G - 1) / G;
+	const int nchunk_max = (G == 32) ? nchunk : __reduce_max_sync(0xffffffffu, nchunk);
+	for (int ch = 0; ch < nchunk_max; ++ch) {
+		const int eb = e0 + ch * G;
+		int cnt = e1 - eb; cnt = cnt < 0 ? 0 : (cnt > G ? G : cnt);
+		const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(0xffffffffu, cnt);
+		{
+			double a_l = 0.0; int c_l = 0;
+			if (gl < cnt) { a_l = __ldg(va + eb + gl); c_l = __ldg(ci + eb + gl); }
+			if (gl < cnt_max) ent[gl] = make_double2(a_l, __longlong_as_double((long long)c_l));
+		}
+		__syncwarp();
+		if (cnt_max > 0) {
+			// Software pipeline over batches of U entries: the gathers of batch b+1 are issued
+			// before the arithmetic of batch b, across the loop back-edge, so ptxas cannot sink
+			// them next to their uses (it does inside one basic block, leaving one gather in
+			// flight per warp).  Slots past the end re-read the last entry and are not added.
+			double a[U]; double2 v[NPASS][U];
+			auto fetch = [&](int jb, double (&aa)[U], double2 (&vv)[NPASS][U]) {
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
-					const bool ok = eb + u < e1;
-					a[u] = ok ? __ldg(va + eb + u) : 0.0;
-					col[u] = ok ? __ldg(ci + eb + u) : 0;
-				}
+					int j = jb + u; j = j < cnt_max ? j : cnt_max - 1;
+					const double2 e = ent[j];
+					aa[u] = e.x;
+					const double *xr = reinterpret_cast<const double *>(xbase + (long long)__double2loint(e.y) * (long long)ldx8);
 #pragma unroll
-				for (int u = 0; u < U; ++u)
-					v[u] = *reinterpret_cast<const double2 *>(xb + (size_t)col[u] * ldxb);
+					for (int p = 0; p < NPASS; ++p) {
+						// x columns are never written by this launch (ranges are disjoint): non-coherent loads
+						if (VEC) vv[p][u] = __ldg(reinterpret_cast<const double2 *>(xr + c[p]));
+						else {
+							vv[p][u].x = __ldg(xr + c[p]);
+							vv[p][u].y = __ldg(xr + c[p] + ((odd_tail && c[p] == k - 1) ? 0 : 1));
+						}
+					}
+				}
+			};
+			fetch(0, a, v);
+			for (int j0 = 0; j0 < cnt_max; j0 += U) {
+				double a2[U]; double2 v2[NPASS][U];
+				if (j0 + U < cnt_max) fetch(j0 + U, a2, v2);
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
-					const double t0 = __dadd_rn(acc0, __dmul_rn(a[u], v[u].x));
-					const double t1 = __dadd_rn(acc1, __dmul_rn(a[u], v[u].y));
-					if (eb + u < e1) { acc0 = t0; acc1 = t1; }
+					if (j0 + u < cnt) {
+#pragma unroll
+						for (int p = 0; p < NPASS; ++p) {
+							acc[p][0] = __dadd_rn(acc[p][0], __dmul_rn(a[u], v[p][u].x));
+							acc[p][1] = __dadd_rn(acc[p][1], __dmul_rn(a[u], v[p][u].y));
+						}
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					a[u] = a2[u];
+#pragma unroll
+					for (int p = 0; p < NPASS; ++p) v[p][u] = v2[p][u];
 				}
 			}
 		}
-		if (store) *reinterpret_cast<double2 *>(y + (size_t)row * ldy + c) = make_double2(acc0, acc1);
+		__syncwarp();
+	}
+#pragma unroll
+	for (int p = 0; p < NPASS; ++p) {
+		if (!st[p]) continue;
+		double *yr = y + (size_t)row * ldy + c[p];
+		if (VEC) *reinterpret_cast<double2 *>(yr) = make_double2(acc[p][0], acc[p][1]);
+		else { yr[0] = acc[p][0]; if (c[p] + 1 < k) yr[1] = acc[p][1]; }
 	}
 }
 
-template <int G>
-static int launch_spmm_v2(int nrows, const int *rp, const int *ci, const double *va,
-                          const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+// Block variant: the main kernel for k <= 64 on matrices with short rows (FEM / stencil).
+// The wide kernel above makes every warp walk a chain of dependent global loads -- row
+// pointer -> entries -> gathers -- and at ~1 us per hop the SM spends most of a row's life
+// waiting (measured: time proportional to the number of warps, not to bytes; profiles/).
+// Here a CTA owns a contiguous block of R = 8*RPW*rw rows: all 256 threads first pull the
+// block's row pointers and then its (value, column) entries -- two fully coalesced sweeps,
+// paid once per block instead of once per row -- into shared memory as 16-byte records; then
+// each row group walks its rw rows entirely out of shared memory, with the whole row's gathers
+// (up to U) in flight at once.  Rows handled at the same time by the 8 warps are adjacent, so
+// gathered x rows shared between neighbouring matrix rows meet in L1.
+constexpr int SPMM_CAP = 2048;          // entries staged per CTA (32 KB of records)
+
+template <int G, bool VEC, int U>
+__global__ void __launch_bounds__(256)
+spmm_csr_block_kernel(int nrows, const int *__restrict__ rp, const int *__restrict__ ci,
+                      const double *__restrict__ va, const double *x, int ldx, double *y, int ldy, int k,
+                      const int *__restrict__ gate, int rw)
 {
-	const int groups_per_cta = 256 / G;
-	const unsigned grid = (unsigned)(((long long)nrows + groups_per_cta - 1) / groups_per_cta);
-	spmm_csr_v2_kernel<G><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	if (gate != nullptr && *gate == 0) return;
+	constexpr int RPW = 32 / G;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	double2 *ent = reinterpret_cast<double2 *>(smem_raw);            // [SPMM_CAP]
+	int *rp_s = reinterpret_cast<int *>(ent + SPMM_CAP);              // [R + 1]
+	const int R = 8 * RPW * rw;
+	const long long r0 = (long long)blockIdx.x * R;
+	for (int i = threadIdx.x; i <= R; i += 256) {
+		const long long r = r0 + i;
+		rp_s[i] = __ldg(rp + (r < nrows ? r : nrows));
+	}
+	__syncthreads();
+	const int eb = rp_s[0], ne = rp_s[R] - eb;
+	for (int i = threadIdx.x; i < ne; i += 256)
+		ent[i] = make_double2(__ldg(va + eb + i), __longlong_as_double((long long)__ldg(ci + eb + i)));
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int gl = lane % G, rg = lane / G;
+	int c = 2 * gl;
+	const bool in_cols = c < k;
+	if (c > k - 2) c = k - 2 < 0 ? 0 : k - 2;
+	const bool odd_tail = (k & 1);
+	const int ldx8 = ldx * 8;
+	const char *xbase = reinterpret_cast<const char *>(x + c);
+	const int second = (!VEC && odd_tail && c == k - 1) ? 0 : 1;
+	for (int j = 0; j < rw; ++j) {
+		const int lr = j * (8 * RPW) + warp * RPW + rg;
+		const long long row = r0 + lr;
+		const int e0 = rp_s[lr] - eb, e1 = rp_s[lr + 1] - eb;
+		const int cnt = e1 - e0;
+		const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(0xffffffffu, cnt);
+		double acc0 = 0.0, acc1 = 0.0;
+		for (int j0 = 0; j0 < cnt_max; j0 += U) {
+			double2 v[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				int e = j0 + u; e = e < cnt ? e : (cnt > 0 ? cnt - 1 : 0);
+				const int col = (cnt > 0) ? __double2loint(ent[e0 + e].y) : 0;
+				const double *xr = reinterpret_cast<const double *>(xbase + (long long)col * (long long)ldx8);
+				if (VEC) v[u] = __ldg(reinterpret_cast<const double2 *>(xr));
+				else { v[u].x = __ldg(xr); v[u].y = __ldg(xr + second); }
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (j0 + u < cnt) {
+					const double a = ent[e0 + j0 + u].x;
+					acc0 = __dadd_rn(acc0, __dmul_rn(a, v[u].x));
+					acc1 = __dadd_rn(acc1, __dmul_rn(a, v[u].y));
+				}
+			}
+		}
+		if (in_cols && row < nrows) {
+			double *yr = y + (size_t)row * ldy + c;
+			if (VEC) *reinterpret_cast<double2 *>(yr) = make_double2(acc0, acc1);
+			else { yr[0] = acc0; if (c + 1 < k) yr[1] = acc1; }
+		}
+	}
+}
+
+template <int G, int U>
+static int launch_spmm_block(int nrows, const int *rp, const int *ci, const double *va,
+                             const double *x, int ldx, double *y, int ldy, int k, const int *gate, int rw)
+{
+	const int R = 8 * (32 / G) * rw;
+	const unsigned grid = (unsigned)(((long long)nrows + R - 1) / R);
+	const size_t smem = sizeof(double2) * SPMM_CAP + sizeof(int) * ((size_t)R + 1);
+	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
+	if (vec) spmm_csr_block_kernel<G, true, U><<<grid, 256, smem, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+	else     spmm_csr_block_kernel<G, false, U><<<grid, 256, smem, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
 	B200_KERNEL_CHECK();
 	return 0;
 }
 
-template <int G, int CPL>
-static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va,
-                       const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+// Gathers in flight per row group: measured on B200 (P1-FEM n = 1 M, profiles/): a one-row warp
+// (G = 32) is fastest with U = 4 (0.475 ms at k = 40 vs 0.557 / 0.576 ms with 8 / 16), the
+// narrower groups with U = 8 (0.168 ms at k = 16 vs 0.186 / 0.227 ms with 4 / 16).
+template <int G>
+static int launch_spmm_block_u(int nrows, const int *rp, const int *ci, const double *va,
+                               const double *x, int ldx, double *y, int ldy, int k, const int *gate, int rw)
 {
-	const int groups_per_cta = 256 / G;
-	const unsigned grid = (unsigned)(((long long)nrows + groups_per_cta - 1) / groups_per_cta);
-	spmm_csr_kernel<G, CPL><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	if (G == 32) return launch_spmm_block<G, 4>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+	return launch_spmm_block<G, 8>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+}
+
+template <int G, int NPASS>
+static int launch_spmm_wide(int nrows, const int *rp, const int *ci, const double *va,
+                            const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const int rows_per_cta = 8 * (32 / G);
+	const unsigned grid = (unsigned)(((long long)nrows + rows_per_cta - 1) / rows_per_cta);
+	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
+	if (vec) spmm_csr_wide_kernel<G, NPASS, true, 4><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else     spmm_csr_wide_kernel<G, NPASS, false, 4><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	B200_KERNEL_CHECK();
 	return 0;
 }
@@ -189,23 +309,32 @@ int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y
 	if (nrows <= 0 || k <= 0) return 0;
 	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
 	              2.0 * M->nnz * k);
-	const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0);
-	if (al16 && k >= 2 && k % 2 == 0) {
-		if (k <= 2)       return launch_spmm_v2<1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-		else if (k <= 4)  return launch_spmm_v2<2>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-		else if (k <= 8)  return launch_spmm_v2<4>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-		else if (k <= 16) return launch_spmm_v2<8>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-		else if (k <= 32) return launch_spmm_v2<16>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-		return launch_spmm_v2<32>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	}
 	if (k == 1)       return launch_spmm<1, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k == 2)  return launch_spmm<2, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k <= 4)  return launch_spmm<4, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	else if (k <= 8)  return launch_spmm<8, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	else if (k <= 16) return launch_spmm<16, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	else if (k <= 32) return launch_spmm<32, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	else if (k <= 64) return launch_spmm<32, 2>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
-	return launch_spmm<32, 4>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	const int mrn = trans ? M->t_max_row_nnz : M->max_row_nnz;
+	if (k <= 64 && mrn > 0 && (long long)mrn * 8 <= SPMM_CAP) {
+		const int rpw = k <= 16 ? 4 : (k <= 32 ? 2 : 1);
+		int rw = 8;                                             // rows per row group
+		while (rw > 1 && (long long)8 * rpw * rw * mrn > SPMM_CAP) rw >>= 1;
+		if ((long long)8 * rpw * rw * mrn <= SPMM_CAP) {
+			if (k <= 16)      return launch_spmm_block_u<8>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+			else if (k <= 32) return launch_spmm_block_u<16>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+			return launch_spmm_block_u<32>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate, rw);
+		}
+	}
+	if (k <= 16) return launch_spmm_wide<8, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 32) return launch_spmm_wide<16, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	else if (k <= 64) return launch_spmm_wide<32, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	// wider blocks: 128 columns per launch pass
+	for (int c0 = 0; c0 < k; c0 += 128) {
+		const int kc = k - c0 < 128 ? k - c0 : 128;
+		int rc;
+		if (kc <= 64) rc = launch_spmm_wide<32, 1>(nrows, rp, ci, va, x + c0, ldx, y + c0, ldy, kc, gate);
+		else          rc = launch_spmm_wide<32, 2>(nrows, rp, ci, va, x + c0, ldx, y + c0, ldy, kc, gate);
+		if (rc) return rc;
+	}
+	return 0;
 }
 
 extern "C" int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv *x, b200_mv *y,

@@ -24,6 +24,7 @@ struct b200_mat_ {
 	int *t_rp; int *t_ci; double *t_va;
 	int t_shared;
 	int row0;
+	int max_row_nnz, t_max_row_nnz;   /* longest row of the CSR image / of the transpose image */
 };
 
 struct b200_mv_ {

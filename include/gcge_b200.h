@@ -85,8 +85,12 @@ int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view);
 int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld);
 int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld);
 /* x[row,col] = rand()/(RAND_MAX+1.0), column-major fill order, consuming the process's
- * glibc rand() stream exactly like reference app/app_lapack.c:322-333 */
+ * glibc rand() stream exactly like reference app/app_lapack.c:322-333.  The values are
+ * generated ON DEVICE by jump-ahead of glibc's lagged-Fibonacci recurrence from the live
+ * generator state; on return the process's generator has advanced by nrows*(end-start) calls. */
 int b200_mv_set_random(b200_mv *x, int start, int end);
+/* host-only self check of that jump-ahead against glibc's rand() itself (needs no device) */
+int b200_rand_selfcheck(unsigned long long steps);
 
 /* ---- slots --------------------------------------------------------------- */
 /* y[:,s1:e1] = A x[:,s0:e0]; A == NULL => copy.  Replaces MatDotMultiVec,

@@ -66,3 +66,15 @@ def test_product_does_not_touch_oracle():
             if re.search(r"from\s+oracle|import\s+oracle|oracle/_ref|libgcge_ref|libgcge_oracle|gcg_numpy", t):
                 bad.append(str(p))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("seed,steps", [(0, 0), (0, 1), (1, 30), (7, 31), (0, 1984), (123, 123457), (0, 3000000)])
+def test_rand_jump_ahead_matches_glibc(seed, steps):
+    """Host half of the device MultiVecSetRandomValue (reference app/app_lapack.c:322-333): the
+    31x31 matrix-power jump of glibc's TYPE_3 generator, the state read-out through
+    initstate()/setstate() and the write-back -- checked against glibc's own rand()."""
+    from gcge_b200 import api
+    L = api.lib()
+    L.b200_rand_selfcheck.argtypes = [C.c_ulonglong]
+    C.CDLL("libc.so.6").srand(C.c_uint(seed))
+    assert L.b200_rand_selfcheck(steps) == 0, L.b200_last_error()

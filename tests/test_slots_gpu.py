@@ -84,6 +84,29 @@ def test_set_random_is_glibc_stream(b200, refmod):
         assert np.array_equal(got, r)
 
 
+@pytest.mark.parametrize("n,k,seed", [(1, 3, 0), (31, 1, 5), (1984, 2, 0), (70001, 9, 0), (300007, 5, 42)])
+def test_set_random_device_jump_ahead(b200, n, k, seed):
+    """The device generator (jump-ahead of glibc's lagged-Fibonacci recurrence, one chunk of 1984
+    stream positions per thread, 128 chunks per CTA) must reproduce the rand() stream bit for bit
+    across chunk, CTA and column boundaries, and must leave the PROCESS generator advanced by
+    n*k calls, so a later rand() -- e.g. the next MultiVecSetRandomValue -- continues the stream."""
+    import ctypes as C
+    libc = C.CDLL("libc.so.6")
+    mv = b200.MultiVec(n, k + 2)
+    b200.libc_srand(seed)
+    mv.set_random(1, 1 + k)
+    after = [libc.rand() for _ in range(5)]
+    want = np.zeros((n, k + 2), order="F")
+    G.srand(seed); G.fill_random(want, 1, 1 + k)
+    got = mv.numpy()
+    assert np.array_equal(got, want)
+    assert np.all(got[:, 0] == 0) and np.all(got[:, k + 1] == 0)
+    b200.libc_srand(seed)
+    skip = np.zeros((n, k), order="F")
+    G.fill_random(skip, 0, k)                 # n*k real rand() calls on the host
+    assert after == [libc.rand() for _ in range(5)]
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 8, 10, 16, 31, 40, 70])
 def test_spmm_bitexact(b200, refmod, pencil, k):
     """MatDotMultiVec (reference app/app_ccs.c:50-139): identical bits, any block width."""
