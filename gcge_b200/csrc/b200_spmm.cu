@@ -300,6 +300,17 @@ static int launch_spmm_wide(int nrows, const int *rp, const int *ci, const doubl
 	return 0;
 }
 
+template <int G, int CPL>
+static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va,
+                       const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const int groups_per_cta = 256 / G;
+	const unsigned grid = (unsigned)(((long long)nrows + groups_per_cta - 1) / groups_per_cta);
+	spmm_csr_kernel<G, CPL><<<grid, 256, 0, g_b200.stream>>>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
 int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
                const int *gate)
 {
