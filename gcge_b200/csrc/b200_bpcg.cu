@@ -11,11 +11,13 @@
 //   SpMM     : matrix + read p, write w       nnz*12 + 2 * 8nk
 //   ptw      : read p,w                       2 * 8nk     (+ shift: read z, write w)
 //   update_xr: read p,w,x,r  write x,r        6 * 8nk
-#include "b200_reduce.cuh"
+#include "b200_stream.cuh"
+
+constexpr int BPCG_CTAS_PER_SM = 6;
 
 extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 {
-	const int chunks_max = g_b200.num_sms * 4 + 8;
+	const int chunks_max = g_b200.num_sms * BPCG_CTAS_PER_SM + 8;
 	const size_t dbl = (size_t)6 * k + (size_t)chunks_max * 2 * k;
 	const size_t bytes = sizeof(double) * dbl + sizeof(int) * ((size_t)k + 8) + 64;
 	char *base = (char *)b200_scratch(4, bytes);
@@ -33,40 +35,49 @@ extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 
 // ---------------------------------------------------------------------------- begin
 // r <- b - r ; acc0 = r.r ; acc1 = b.b (rel only)
-template <int CPT>
-__global__ void __launch_bounds__(RED_THREADS)
-bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *__restrict__ b, int ldb, double *__restrict__ r, int ldr,
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b, int ldb, double *__restrict__ r, int ldr,
                   double tol, int rel, b200_bpcg_state st)
 {
-	extern __shared__ double sm[];
-	const int cx = blockDim.x, ry = blockDim.y;
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
-	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	double acc[2][CPT];
+	const StreamThread t = stream_thread<VEC>(g);
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[2][VEC];
 #pragma unroll
-	for (int i = 0; i < CPT; ++i) { acc[0][i] = 0.0; acc[1][i] = 0.0; }
-#pragma unroll 4
-	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
+	for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.0; acc[1][i] = 0.0; }
+	if (t.active) {
+		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+			StV<VEC> bv[ST_UNROLL], rv[ST_UNROLL];
 #pragma unroll
-		for (int i = 0; i < CPT; ++i) {
-			const int c = threadIdx.x + i * cx;
-			if (c < k) {
-				const double bv = b[(size_t)row * ldb + c];
-				const double rv = bv - r[(size_t)row * ldr + c];
-				r[(size_t)row * ldr + c] = rv;
-				acc[0][i] = fma(rv, rv, acc[0][i]);
-				acc[1][i] = fma(bv, bv, acc[1][i]);
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) { bv[u] = st_ld<VEC>(b + (size_t)row * ldb + t.c); rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c); }
+			}
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i) {
+						const double x = bv[u].v[i] - rv[u].v[i];
+						rv[u].v[i] = x;
+						acc[0][i] = fma(x, x, acc[0][i]);
+						acc[1][i] = fma(bv[u].v[i], bv[u].v[i], acc[1][i]);
+					}
+					st_st<VEC>(r + (size_t)row * ldr + t.c, rv[u]);
+				}
 			}
 		}
 	}
-	if (!red_block_and_elect<CPT, 2>(acc, k, sm, st.partials, st.tickets)) return;
-	const int tid = threadIdx.y * cx + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if (!stream_reduce_and_elect<VEC, 2>(acc, k, g, t, st.partials, st.tickets)) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	__shared__ int n_active;
-	if (tid == 0) n_active = 0;
+	if (threadIdx.x == 0) n_active = 0;
 	__syncthreads();
-	for (int c = warp; c < k; c += RED_THREADS / 32) {
-		const double rr = red_total<2>(st.partials, gridDim.x, k, 0, c);
-		const double bb = red_total<2>(st.partials, gridDim.x, k, 1, c);
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+		const double rr = stream_total<2>(st.partials, gridDim.x, k, 0, c);
+		const double bb = stream_total<2>(st.partials, gridDim.x, k, 1, c);
 		if (lane == 0) {
 			const double nb = rel ? sqrt(bb) : 1.0;
 			const double res = sqrt(rr);
@@ -78,108 +89,161 @@ bpcg_begin_kernel(long long n, int k, long long rows_per_chunk, const double *__
 		}
 	}
 	__syncthreads();
-	if (tid == 0) { st.counters[0] = n_active; st.counters[1] = 0; }
+	if (threadIdx.x == 0) { st.counters[0] = n_active; st.counters[1] = 0; }
 }
 
 // ------------------------------------------------------------------------- update_p
-__global__ void bpcg_update_p_kernel(long long n, int k, int rows_per_cta, const double *__restrict__ r, int ldr, double *__restrict__ p,
-                                     int ldp, int first, b200_bpcg_state st)
+// p = r + (rho2/rho1) p on active columns; reference src/ops_lin_sol.c:271-284
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_update_p_kernel(long long n, int k, StreamGeom g, const double *__restrict__ r, int ldr, double *__restrict__ p,
+                     int ldp, int first, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
-	const long long r0 = (long long)blockIdx.x * rows_per_cta;
-	long long nr = n - r0; if (nr > rows_per_cta) nr = rows_per_cta;
-	const int total = (int)nr * k;
-#pragma unroll 4
-	for (int i = threadIdx.x; i < total; i += blockDim.x) {
-		const int rr = i / k, c = i - rr * k;
-		if (!st.active[c]) continue;
-		const double rv = r[(size_t)(r0 + rr) * ldr + c];
-		double *pp = p + (size_t)(r0 + rr) * ldp + c;
-		// reference src/ops_lin_sol.c:271-284: p = r + beta p, beta = rho2/rho1 (0 on iteration 0)
-		*pp = first ? rv : fma(st.rho2[c] / st.rho1[c], *pp, rv);
+	const StreamThread t = stream_thread<VEC>(g);
+	if (!t.active) return;
+	bool act[VEC]; double beta[VEC]; bool any = false;
+#pragma unroll
+	for (int i = 0; i < VEC; ++i) {
+		act[i] = st.active[t.c + i] != 0;
+		beta[i] = (act[i] && !first) ? st.rho2[t.c + i] / st.rho1[t.c + i] : 0.0;
+		any = any || act[i];
+	}
+	if (!any) return;
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+		StV<VEC> rv[ST_UNROLL], pv[ST_UNROLL];
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) {
+				rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c);
+				pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);     // also when first: an inactive neighbour column keeps its value
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) {
+#pragma unroll
+				for (int i = 0; i < VEC; ++i)
+					if (act[i]) pv[u].v[i] = first ? rv[u].v[i] : fma(beta[i], pv[u].v[i], rv[u].v[i]);
+				st_st<VEC>(p + (size_t)row * ldp + t.c, pv[u]);
+			}
+		}
 	}
 }
 
 // ------------------------------------------------------------------------------ ptw
-template <int CPT>
-__global__ void __launch_bounds__(RED_THREADS)
-bpcg_ptw_kernel(long long n, int k, long long rows_per_chunk, const double *p, int ldp, double *__restrict__ w, int ldw,
+// w += shift z (optional) ; ptw = diag(p^T w)
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, double *__restrict__ w, int ldw,
                 double shift, const double *z, int ldz, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
-	extern __shared__ double sm[];
-	const int cx = blockDim.x, ry = blockDim.y;
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
-	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	double acc[1][CPT];
+	const StreamThread t = stream_thread<VEC>(g);
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[1][VEC];
 #pragma unroll
-	for (int i = 0; i < CPT; ++i) acc[0][i] = 0.0;
-#pragma unroll 4
-	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
+	for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+	if (t.active) {
+		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+			StV<VEC> pv[ST_UNROLL], wv[ST_UNROLL], zv[ST_UNROLL];
 #pragma unroll
-		for (int i = 0; i < CPT; ++i) {
-			const int c = threadIdx.x + i * cx;
-			if (c < k) {
-				double wv = w[(size_t)row * ldw + c];
-				if (z) {       // w = (A + shift B) p, reference src/ops_eig_sol_gcg.c:63-96
-					wv = fma(shift, z[(size_t)row * ldz + c], wv);
-					w[(size_t)row * ldw + c] = wv;
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+					pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);
+					wv[u] = st_ld<VEC>(w + (size_t)row * ldw + t.c);
+					if (z) zv[u] = st_ld<VEC>(z + (size_t)row * ldz + t.c);
 				}
-				acc[0][i] = fma(p[(size_t)row * ldp + c], wv, acc[0][i]);
+			}
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+					if (z) {       // w = (A + shift B) p, reference src/ops_eig_sol_gcg.c:63-96
+#pragma unroll
+						for (int i = 0; i < VEC; ++i) wv[u].v[i] = fma(shift, zv[u].v[i], wv[u].v[i]);
+						st_st<VEC>(w + (size_t)row * ldw + t.c, wv[u]);
+					}
+#pragma unroll
+					for (int i = 0; i < VEC; ++i) acc[0][i] = fma(pv[u].v[i], wv[u].v[i], acc[0][i]);
+				}
 			}
 		}
 	}
-	if (!red_block_and_elect<CPT, 1>(acc, k, sm, st.partials, st.tickets)) return;
-	const int tid = threadIdx.y * cx + threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	for (int c = warp; c < k; c += RED_THREADS / 32) {
-		const double s = red_total<1>(st.partials, gridDim.x, k, 0, c);
+	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+		const double s = stream_total<1>(st.partials, gridDim.x, k, 0, c);
 		if (lane == 0 && st.active[c]) st.ptw[c] = s;
 	}
 }
 
 // ------------------------------------------------------------------------ update_xr
-template <int CPT>
-__global__ void __launch_bounds__(RED_THREADS)
-bpcg_update_xr_kernel(long long n, int k, long long rows_per_chunk, const double *__restrict__ p, int ldp, const double *__restrict__ w,
+// alpha = rho2/ptw ; x += alpha p ; r -= alpha w ; rho1 = rho2 ; rho2 = diag(r^T r) ; stop test
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict__ p, int ldp, const double *__restrict__ w,
                       int ldw, double *__restrict__ x, int ldx, double *__restrict__ r, int ldr, double rate, double tol,
                       b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
-	extern __shared__ double sm[];
-	const int cx = blockDim.x, ry = blockDim.y;
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
-	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	double acc[1][CPT], alpha[CPT];
-	bool act[CPT];
+	const StreamThread t = stream_thread<VEC>(g);
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[1][VEC], alpha[VEC];
+	bool act[VEC]; bool any = false;
 #pragma unroll
-	for (int i = 0; i < CPT; ++i) {
-		const int c = threadIdx.x + i * cx;
+	for (int i = 0; i < VEC; ++i) {
 		acc[0][i] = 0.0;
-		act[i] = (c < k) && st.active[c];
-		alpha[i] = act[i] ? st.rho2[c] / st.ptw[c] : 0.0;       // reference src/ops_lin_sol.c:328
+		act[i] = t.active && st.active[t.c + i];
+		alpha[i] = act[i] ? st.rho2[t.c + i] / st.ptw[t.c + i] : 0.0;       // reference src/ops_lin_sol.c:328
+		any = any || act[i];
 	}
-#pragma unroll 4
-	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
+	if (any) {
+		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+			StV<VEC> pv[ST_UNROLL], wv[ST_UNROLL], xv[ST_UNROLL], rv[ST_UNROLL];
 #pragma unroll
-		for (int i = 0; i < CPT; ++i) {
-			if (act[i]) {
-				const int c = threadIdx.x + i * cx;
-				const double pv = p[(size_t)row * ldp + c], wv = w[(size_t)row * ldw + c];
-				double *xp = x + (size_t)row * ldx + c, *rp = r + (size_t)row * ldr + c;
-				*xp = fma(alpha[i], pv, *xp);
-				const double rv = fma(-alpha[i], wv, *rp);
-				*rp = rv;
-				acc[0][i] = fma(rv, rv, acc[0][i]);
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+					pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);
+					wv[u] = st_ld<VEC>(w + (size_t)row * ldw + t.c);
+					xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c);
+					rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i) {
+						if (act[i]) {
+							xv[u].v[i] = fma(alpha[i], pv[u].v[i], xv[u].v[i]);
+							const double nr = fma(-alpha[i], wv[u].v[i], rv[u].v[i]);
+							rv[u].v[i] = nr;
+							acc[0][i] = fma(nr, nr, acc[0][i]);
+						}
+					}
+					st_st<VEC>(x + (size_t)row * ldx + t.c, xv[u]);
+					st_st<VEC>(r + (size_t)row * ldr + t.c, rv[u]);
+				}
 			}
 		}
 	}
-	if (!red_block_and_elect<CPT, 1>(acc, k, sm, st.partials, st.tickets)) return;
-	const int tid = threadIdx.y * cx + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	__shared__ int n_active;
-	if (tid == 0) n_active = 0;
+	if (threadIdx.x == 0) n_active = 0;
 	__syncthreads();
-	for (int c = warp; c < k; c += RED_THREADS / 32) {
-		const double rr = red_total<1>(st.partials, gridDim.x, k, 0, c);
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+		const double rr = stream_total<1>(st.partials, gridDim.x, k, 0, c);
 		if (lane == 0 && st.active[c]) {
 			st.rho1[c] = st.rho2[c];
 			st.rho2[c] = rr;
@@ -192,27 +256,18 @@ bpcg_update_xr_kernel(long long n, int k, long long rows_per_chunk, const double
 		}
 	}
 	__syncthreads();
-	if (tid == 0) { st.counters[0] = n_active; st.counters[1] += 1; }
+	if (threadIdx.x == 0) { st.counters[0] = n_active; st.counters[1] += 1; }
 }
 
 // ------------------------------------------------------------------------- launchers
-#define BPCG_DISPATCH_CPT(k, CALL)                         \
-	do {                                                   \
-		if ((k) <= 32) { constexpr int CPT = 1; CALL; }    \
-		else if ((k) <= 64) { constexpr int CPT = 2; CALL; } \
-		else { constexpr int CPT = 4; CALL; }              \
-	} while (0)
-
 extern "C" int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const double *b, int ldb,
                                 double *r, int ldr, double tol, int rel)
 {
 	const int k = st->k;
 	B200_CHECK(k >= 1 && k <= 128, "BlockPCG: %d columns (1..128 supported per block)", k);
 	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 5.0 * n * k);
-	const RedGeom g = red_geometry(n, k);
-	const size_t smem = sizeof(double) * (size_t)g.ry * k;
-	BPCG_DISPATCH_CPT(k, (bpcg_begin_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(
-		n, k, g.rows_per_chunk, b, ldb, r, ldr, tol, rel, *st)));
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(b, ldb) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, *st)));
 	B200_KERNEL_CHECK();
 	return 0;
 }
@@ -222,9 +277,8 @@ extern "C" int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const
 {
 	const int k = st->k;
 	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 2.0 * n * k);
-	int rows = 4096 / k; if (rows < 1) rows = 1;
-	bpcg_update_p_kernel<<<(unsigned)((n + rows - 1) / rows), 256, 0, g_b200.stream>>>(n, k, rows, r, ldr, p, ldp,
-	                                                                                 first, *st);
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(r, ldr) && stream_aligned16(p, ldp), BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_update_p_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, r, ldr, p, ldp, first, *st)));
 	B200_KERNEL_CHECK();
 	return 0;
 }
@@ -234,10 +288,9 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
 {
 	const int k = st->k;
 	B200Prof prof(B200_PROF_BPCG, (z ? 32.0 : 16.0) * n * k, (z ? 4.0 : 2.0) * n * k);
-	const RedGeom g = red_geometry(n, k);
-	const size_t smem = sizeof(double) * (size_t)g.ry * k;
-	BPCG_DISPATCH_CPT(k, (bpcg_ptw_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(
-		n, k, g.rows_per_chunk, p, ldp, w, ldw, shift, z, ldz, *st)));
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
+	                                     (!z || stream_aligned16(z, ldz)), BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_ptw_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, shift, z, ldz, *st)));
 	B200_KERNEL_CHECK();
 	return 0;
 }
@@ -248,10 +301,9 @@ extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, cons
 {
 	const int k = st->k;
 	B200Prof prof(B200_PROF_BPCG, 48.0 * n * k, 6.0 * n * k);
-	const RedGeom g = red_geometry(n, k);
-	const size_t smem = sizeof(double) * (size_t)g.ry * k;
-	BPCG_DISPATCH_CPT(k, (bpcg_update_xr_kernel<CPT><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(
-		n, k, g.rows_per_chunk, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, *st)));
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
+	                                     stream_aligned16(x, ldx) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, *st)));
 	B200_KERNEL_CHECK();
 	return 0;
 }

@@ -1,41 +1,48 @@
 // Small device helpers of the GCG driver: residual norms for CheckConvergence and the
 // element-wise assembly kernels of the projected (N x N) problem.
-#include "b200_reduce.cuh"
+#include "b200_stream.cuh"
 
 // ax <- ax - lam[c]*bx ; res[c] = ||ax[:,c]||_2   (reference src/ops_eig_sol_gcg.c:214-224)
-template <int CPT>
-__global__ void __launch_bounds__(RED_THREADS)
-residual_kernel(long long n, int k, long long rows_per_chunk, double *__restrict__ ax, int ldax, const double *__restrict__ bx, int ldbx,
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+residual_kernel(long long n, int k, StreamGeom g, double *__restrict__ ax, int ldax, const double *__restrict__ bx, int ldbx,
                 const double *__restrict__ lam, double *res, double *part, unsigned *ticket)
 {
-	extern __shared__ double sm[];
-	const int cx = blockDim.x, ry = blockDim.y;
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
-	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	double acc[1][CPT], l[CPT];
+	const StreamThread t = stream_thread<VEC>(g);
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[1][VEC], l[VEC];
 #pragma unroll
-	for (int i = 0; i < CPT; ++i) {
-		const int c = threadIdx.x + i * cx;
-		acc[0][i] = 0.0; l[i] = (c < k) ? lam[c] : 0.0;
-	}
-#pragma unroll 4
-	for (long long row = r_begin + threadIdx.y; row < r_end; row += ry) {
+	for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.0; l[i] = lam[t.c + i]; }
+	if (t.active) {
+		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+			StV<VEC> av[ST_UNROLL], bv[ST_UNROLL];
 #pragma unroll
-		for (int i = 0; i < CPT; ++i) {
-			const int c = threadIdx.x + i * cx;
-			if (c < k) {
-				// lambda*Bx is rounded first, then subtracted: the reference scales Bx (dscal) and
-				// then forms Ax - (lambda Bx) (daxpy), src/ops_eig_sol_gcg.c:214-220
-				const double v = ax[(size_t)row * ldax + c] - __dmul_rn(l[i], bx[(size_t)row * ldbx + c]);
-				ax[(size_t)row * ldax + c] = v;
-				acc[0][i] = fma(v, v, acc[0][i]);
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) { av[u] = st_ld<VEC>(ax + (size_t)row * ldax + t.c); bv[u] = st_ld<VEC>(bx + (size_t)row * ldbx + t.c); }
+			}
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i) {
+						// lambda*Bx is rounded first, then subtracted: the reference scales Bx (dscal) and
+						// then forms Ax - (lambda Bx) (daxpy), src/ops_eig_sol_gcg.c:214-220
+						const double v = av[u].v[i] - __dmul_rn(l[i], bv[u].v[i]);
+						av[u].v[i] = v;
+						acc[0][i] = fma(v, v, acc[0][i]);
+					}
+					st_st<VEC>(ax + (size_t)row * ldax + t.c, av[u]);
+				}
 			}
 		}
 	}
-	if (!red_block_and_elect<CPT, 1>(acc, k, sm, part, ticket)) return;
-	const int tid = threadIdx.y * cx + threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	for (int c = warp; c < k; c += RED_THREADS / 32) {
-		const double s = red_total<1>(part, gridDim.x, k, 0, c);
+	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, part, ticket)) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+		const double s = stream_total<1>(part, gridDim.x, k, 0, c);
 		if (lane == 0) res[c] = sqrt(s);
 	}
 }
@@ -46,16 +53,13 @@ extern "C" int b200k_residual_norms(long long n, int k, double *ax, int ldax, co
 	if (k <= 0) return 0;
 	B200_CHECK(k <= 128, "residual norms: %d columns (<=128 per call)", k);
 	B200Prof prof(B200_PROF_DOTS, 24.0 * n * k, 4.0 * n * k);
-	const RedGeom g = red_geometry(n, k);
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(ax, ldax) && stream_aligned16(bx, ldbx));
 	char *base = (char *)b200_scratch(0, sizeof(double) * (size_t)(g.chunks + 1) * k + 64);
 	if (!base) return 1;
 	double *part = (double *)base;
 	unsigned *ticket = (unsigned *)(part + (size_t)(g.chunks + 1) * k);
 	B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), g_b200.stream));
-	const size_t smem = sizeof(double) * (size_t)g.ry * k;
-	if (k <= 32)      residual_kernel<1><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
-	else if (k <= 64) residual_kernel<2><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
-	else              residual_kernel<4><<<g.chunks, dim3(g.cx, g.ry), smem, g_b200.stream>>>(n, k, g.rows_per_chunk, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket);
+	ST_DISPATCH_VEC(g, (residual_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket)));
 	B200_KERNEL_CHECK();
 	return 0;
 }
