@@ -170,6 +170,52 @@ def measure_dmma_peak() -> float:
     return t.value
 
 
+def partition_plan(ccs, rank: int, nranks: int) -> dict:
+    """Host-only (no device): the row-block partition plan rank `rank` of `nranks` builds for a CCS
+    matrix -- the same code path b200_mat_create_from_ccs runs on every rank (b200_plan_*)."""
+    L = lib()
+    j_col = np.ascontiguousarray(ccs.j_col, dtype=np.int32); i_row = np.ascontiguousarray(ccs.i_row, dtype=np.int32)
+    data = np.ascontiguousarray(ccs.data, dtype=np.float64)
+    h = C.c_void_p()
+    L.b200_plan_create.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.b200_plan_sizes.argtypes = [C.c_void_p] + [c_int_p] * 7
+    L.b200_plan_copy.argtypes = [C.c_void_p, c_int_p, c_int_p, c_dbl_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]
+    L.b200_plan_destroy.argtypes = [C.c_void_p]
+    _chk(L.b200_plan_create(ccs.nrows, ccs.ncols, _ip(j_col), _ip(i_row), _dp(data), rank, nranks, C.byref(h)))
+    v = [C.c_int(0) for _ in range(7)]
+    _chk(L.b200_plan_sizes(h, *[C.byref(x) for x in v]))
+    row0, nloc, nnz, nhalo, nnbr, nsend, sym = [x.value for x in v]
+    out = {"row0": row0, "nloc": nloc, "nnz": nnz, "nhalo": nhalo, "symmetric": bool(sym),
+           "rp": np.zeros(nloc + 1, np.int32), "ci": np.zeros(max(nnz, 1), np.int32), "va": np.zeros(max(nnz, 1)),
+           "halo_cols": np.zeros(max(nhalo, 1), np.int32), "nbr": np.zeros(max(nnbr, 1), np.int32),
+           "recv_off": np.zeros(nnbr + 1, np.int32), "send_off": np.zeros(nnbr + 1, np.int32),
+           "send_rows": np.zeros(max(nsend, 1), np.int32)}
+    _chk(L.b200_plan_copy(h, _ip(out["rp"]), _ip(out["ci"]), _dp(out["va"]), _ip(out["halo_cols"]), _ip(out["nbr"]),
+                          _ip(out["recv_off"]), _ip(out["send_off"]), _ip(out["send_rows"])))
+    L.b200_plan_destroy(h)
+    out["ci"] = out["ci"][:nnz]; out["va"] = out["va"][:nnz]; out["halo_cols"] = out["halo_cols"][:nhalo]
+    out["nbr"] = out["nbr"][:nnbr]; out["send_rows"] = out["send_rows"][:nsend]
+    return out
+
+
+def comm_init_from_torch():
+    """Bootstrap the library's NCCL communicator from an initialised torch.distributed group:
+    rank 0 creates the unique id, broadcast_object_list ships it, every rank joins."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _chk(lib().b200_comm_unique_id(buf))
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=0)
+    _chk(lib().b200_comm_init(rank, world, C.create_string_buffer(box[0], 128)))
+    return rank, world
+
+
+def comm_finalize():
+    lib().b200_comm_finalize()
+
+
 def libc_srand(seed: int = 0):
     """srand() of the process's glibc -- the generator b200_mv_set_random consumes, exactly as
     the reference's drivers do (reference test/test_eig_sol_gcg.c:87)."""

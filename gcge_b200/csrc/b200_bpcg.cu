@@ -18,7 +18,7 @@ constexpr int BPCG_CTAS_PER_SM = 6;
 extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 {
 	const int chunks_max = g_b200.num_sms * BPCG_CTAS_PER_SM + 8;
-	const size_t dbl = (size_t)6 * k + (size_t)chunks_max * 2 * k;
+	const size_t dbl = (size_t)8 * k + (size_t)chunks_max * 2 * k;
 	const size_t bytes = sizeof(double) * dbl + sizeof(int) * ((size_t)k + 8) + 64;
 	char *base = (char *)b200_scratch(4, bytes);
 	if (!base) return 1;
@@ -26,11 +26,76 @@ extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 	st->k = k;
 	st->norm_b = d; st->rho1 = d + k; st->rho2 = d + 2 * k; st->ptw = d + 3 * k;
 	st->init_res = d + 4 * k; st->last_res = d + 5 * k;
-	st->partials = d + 6 * k;
+	st->totals = d + 6 * k;                       /* 2k: per-column sums of the current reduction */
+	st->partials = d + 8 * k;
 	int *ip = (int *)(d + dbl);
 	st->active = ip; st->counters = ip + k; st->tickets = (unsigned *)(ip + k + 4);
 	B200_CUDA(cudaMemsetAsync(st->counters, 0, sizeof(int) * 8, g_b200.stream));
 	return 0;
+}
+
+// The tiny per-column scalar step that follows each reduction.  Single GPU: run by the last
+// CTA of the streaming kernel itself.  Several ranks: the streaming kernel only leaves the
+// per-column sums in st.totals, the host enqueues one ncclAllReduce on them (reference:
+// MPI_Allreduce at src/ops_lin_sol.c:317,365) and then this runs as a one-CTA kernel -- every
+// rank computes the same alpha / beta / masks from the same bits.
+//   phase 0: after r = b - A x     phase 1: after p^T w     phase 2: after r -= alpha w
+__device__ __forceinline__ void bpcg_scalar_phase(int phase, int k, const b200_bpcg_state &st, double tol, int rel,
+                                                  double rate)
+{
+	__shared__ int n_active;
+	if (threadIdx.x == 0) n_active = 0;
+	__syncthreads();
+	for (int c = threadIdx.x; c < k; c += blockDim.x) {
+		if (phase == 0) {
+			const double rr = st.totals[c], bb = st.totals[k + c];
+			const double nb = rel ? sqrt(bb) : 1.0;
+			const double res = sqrt(rr);
+			st.norm_b[c] = nb; st.rho2[c] = rr; st.rho1[c] = rr;
+			st.init_res[c] = res; st.last_res[c] = res;
+			const int act = (res > tol * nb) ? 1 : 0;      // reference src/ops_lin_sol.c:239-247
+			st.active[c] = act;
+			if (act) atomicAdd(&n_active, 1);
+		} else if (phase == 1) {
+			if (st.active[c]) st.ptw[c] = st.totals[c];
+		} else if (st.active[c]) {
+			const double rr = st.totals[c];
+			st.rho1[c] = st.rho2[c];
+			st.rho2[c] = rr;
+			const double res = sqrt(rr);
+			st.last_res[c] = res;
+			// reference src/ops_lin_sol.c:383-394: stay active while res > rate*res0 AND res > tol*||b||
+			const int still = (res > rate * st.init_res[c]) && (res > tol * st.norm_b[c]);
+			st.active[c] = still;
+			if (still) atomicAdd(&n_active, 1);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (phase == 0) { st.counters[0] = n_active; st.counters[1] = 0; }
+		else if (phase == 2) { st.counters[0] = n_active; st.counters[1] += 1; }
+	}
+}
+
+// last CTA: per-column totals of NACC accumulators into st.totals[a*k + c]
+template <int NACC>
+__device__ __forceinline__ void bpcg_store_totals(int k, const b200_bpcg_state &st)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+#pragma unroll
+		for (int a = 0; a < NACC; ++a) {
+			const double s = stream_total<NACC>(st.partials, gridDim.x, k, a, c);
+			if (lane == 0) st.totals[a * k + c] = s;
+		}
+	}
+	__syncthreads();
+}
+
+__global__ void bpcg_finish_kernel(int phase, int k, b200_bpcg_state st, double tol, int rel, double rate)
+{
+	if (phase != 0 && st.counters[0] == 0) return;
+	bpcg_scalar_phase(phase, k, st, tol, rel, rate);
 }
 
 // ---------------------------------------------------------------------------- begin
@@ -38,7 +103,7 @@ extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b, int ldb, double *__restrict__ r, int ldr,
-                  double tol, int rel, b200_bpcg_state st)
+                  double tol, int rel, int defer, b200_bpcg_state st)
 {
 	const StreamThread t = stream_thread<VEC>(g);
 	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
@@ -71,25 +136,8 @@ bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b
 		}
 	}
 	if (!stream_reduce_and_elect<VEC, 2>(acc, k, g, t, st.partials, st.tickets)) return;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	__shared__ int n_active;
-	if (threadIdx.x == 0) n_active = 0;
-	__syncthreads();
-	for (int c = warp; c < k; c += ST_THREADS / 32) {
-		const double rr = stream_total<2>(st.partials, gridDim.x, k, 0, c);
-		const double bb = stream_total<2>(st.partials, gridDim.x, k, 1, c);
-		if (lane == 0) {
-			const double nb = rel ? sqrt(bb) : 1.0;
-			const double res = sqrt(rr);
-			st.norm_b[c] = nb; st.rho2[c] = rr; st.rho1[c] = rr;
-			st.init_res[c] = res; st.last_res[c] = res;
-			const int act = (res > tol * nb) ? 1 : 0;      // reference src/ops_lin_sol.c:239-247
-			st.active[c] = act;
-			if (act) atomicAdd(&n_active, 1);
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) { st.counters[0] = n_active; st.counters[1] = 0; }
+	bpcg_store_totals<2>(k, st);
+	if (!defer) bpcg_scalar_phase(0, k, st, tol, rel, 0.0);
 }
 
 // ------------------------------------------------------------------------- update_p
@@ -140,7 +188,7 @@ bpcg_update_p_kernel(long long n, int k, StreamGeom g, const double *__restrict_
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, double *__restrict__ w, int ldw,
-                double shift, const double *z, int ldz, b200_bpcg_state st)
+                double shift, const double *z, int ldz, int defer, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
 	const StreamThread t = stream_thread<VEC>(g);
@@ -177,11 +225,8 @@ bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, doub
 		}
 	}
 	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	for (int c = warp; c < k; c += ST_THREADS / 32) {
-		const double s = stream_total<1>(st.partials, gridDim.x, k, 0, c);
-		if (lane == 0 && st.active[c]) st.ptw[c] = s;
-	}
+	bpcg_store_totals<1>(k, st);
+	if (!defer) bpcg_scalar_phase(1, k, st, 0.0, 0, 0.0);
 }
 
 // ------------------------------------------------------------------------ update_xr
@@ -190,7 +235,7 @@ template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict__ p, int ldp, const double *__restrict__ w,
                       int ldw, double *__restrict__ x, int ldx, double *__restrict__ r, int ldr, double rate, double tol,
-                      b200_bpcg_state st)
+                      int defer, b200_bpcg_state st)
 {
 	if (st.counters[0] == 0) return;
 	const StreamThread t = stream_thread<VEC>(g);
@@ -238,37 +283,31 @@ bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict
 		}
 	}
 	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	__shared__ int n_active;
-	if (threadIdx.x == 0) n_active = 0;
-	__syncthreads();
-	for (int c = warp; c < k; c += ST_THREADS / 32) {
-		const double rr = stream_total<1>(st.partials, gridDim.x, k, 0, c);
-		if (lane == 0 && st.active[c]) {
-			st.rho1[c] = st.rho2[c];
-			st.rho2[c] = rr;
-			const double res = sqrt(rr);
-			st.last_res[c] = res;
-			// reference src/ops_lin_sol.c:383-394: stay active while res > rate*res0 AND res > tol*||b||
-			const int still = (res > rate * st.init_res[c]) && (res > tol * st.norm_b[c]);
-			st.active[c] = still;
-			if (still) atomicAdd(&n_active, 1);
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) { st.counters[0] = n_active; st.counters[1] += 1; }
+	bpcg_store_totals<1>(k, st);
+	if (!defer) bpcg_scalar_phase(2, k, st, tol, 0, rate);
 }
 
 // ------------------------------------------------------------------------- launchers
+// several ranks: sum the per-column totals over the ranks, then the scalar step
+static int bpcg_finish(int phase, int nacc, const b200_bpcg_state *st, double tol, int rel, double rate)
+{
+	if (b200k_allreduce_sum(st->totals, (size_t)nacc * st->k)) return 1;
+	bpcg_finish_kernel<<<1, 128, 0, g_b200.stream>>>(phase, st->k, *st, tol, rel, rate);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
 extern "C" int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const double *b, int ldb,
                                 double *r, int ldr, double tol, int rel)
 {
 	const int k = st->k;
+	const int defer = b200_multi() ? 1 : 0;
 	B200_CHECK(k >= 1 && k <= 128, "BlockPCG: %d columns (1..128 supported per block)", k);
 	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 5.0 * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(b, ldb) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, defer, *st)));
 	B200_KERNEL_CHECK();
+	if (defer) return bpcg_finish(0, 2, st, tol, rel, 0.0);
 	return 0;
 }
 
@@ -287,11 +326,13 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
                               double *w, int ldw, double shift, const double *z, int ldz)
 {
 	const int k = st->k;
+	const int defer = b200_multi() ? 1 : 0;
 	B200Prof prof(B200_PROF_BPCG, (z ? 32.0 : 16.0) * n * k, (z ? 4.0 : 2.0) * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
 	                                     (!z || stream_aligned16(z, ldz)), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_ptw_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, shift, z, ldz, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_ptw_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, shift, z, ldz, defer, *st)));
 	B200_KERNEL_CHECK();
+	if (defer) return bpcg_finish(1, 1, st, 0.0, 0, 0.0);
 	return 0;
 }
 
@@ -300,10 +341,12 @@ extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, cons
                                     double rate, double tol)
 {
 	const int k = st->k;
+	const int defer = b200_multi() ? 1 : 0;
 	B200Prof prof(B200_PROF_BPCG, 48.0 * n * k, 6.0 * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
 	                                     stream_aligned16(x, ldx) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, defer, *st)));
 	B200_KERNEL_CHECK();
+	if (defer) return bpcg_finish(2, 1, st, tol, 0, rate);
 	return 0;
 }

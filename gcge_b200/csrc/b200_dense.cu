@@ -230,69 +230,107 @@ __global__ void fill2d_kernel(int p, int q, double v, double *c, int c_rs, int c
 	c[(size_t)(idx % p) * c_rs + (size_t)(idx / p) * c_cs] = v;
 }
 
+// scatter a contiguous column-major p x q block (already summed over ranks) into the caller's
+// strided destination; mode 'S' mirrors the lower triangle, 'D' writes p values with stride c_rs
+__global__ void gram_scatter_kernel(int p, int q, const double *__restrict__ tmp, double *__restrict__ c, int c_rs,
+                                    int c_cs, int symmetric)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= p * q) return;
+	const int i = idx % p, j = idx / p;
+	if (symmetric && i < j) return;
+	const double s = tmp[idx];
+	c[(size_t)i * c_rs + (size_t)j * c_cs] = s;
+	if (symmetric && i > j) c[(size_t)j * c_rs + (size_t)i * c_cs] = s;
+}
+
+int b200k_multi(void) { return g_b200.nranks > 1 ? g_b200.nranks : 1; }
+
 // 'D': c_dev[i*c_rs] = alpha * x_i . y_i  (c_cs ignored)
 int b200k_gram(char mode, long long n, int p, int q, double alpha, const double *x, int ldx,
-               const double *y, int ldy, double *c_dev, int c_rs, int c_cs)
+               const double *y, int ldy, double *c_dev, int c_rs, int c_cs, int dist)
 {
 	if (p <= 0 || q <= 0) return 0;
 	cudaStream_t st = g_b200.stream;
-	B200Prof prof(mode == 'D' ? B200_PROF_DOTS : (n <= 1024 ? B200_PROF_SMALL : B200_PROF_GRAM),
+	B200Prof prof(mode == 'D' ? B200_PROF_DOTS : (n <= 1024 && !dist ? B200_PROF_SMALL : B200_PROF_GRAM),
 	              mode == 'D' ? 16.0 * n * p : 8.0 * n * ((double)p + q) + 8.0 * p * q,
 	              mode == 'D' ? 2.0 * n * p : 2.0 * n * p * q);
+	// Several ranks: every rank reduces its slab into a contiguous block, one NCCL allreduce sums
+	// the blocks (reference: MPI_Allreduce after the local inner product, src/ops_multi_vec.c:214),
+	// then the block is scattered into the caller's layout.  All ranks get identical bits.
+	const bool multi = dist && b200_multi();
+	double *dst = c_dev; int d_rs = c_rs, d_cs = c_cs;
+	const int cnt = (mode == 'D') ? p : p * q;
+	if (multi) {
+		dst = (double *)b200_scratch(8, sizeof(double) * (size_t)cnt + 256);
+		if (!dst) return 1;
+		d_rs = 1; d_cs = p;
+	}
 	if (mode == 'D') {
 		const int k = p;
 		if (n <= 0) {
-			fill2d_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, 1, 0.0, c_dev, c_rs, 0);
+			fill2d_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, 1, 0.0, dst, d_rs, 0);
 			B200_KERNEL_CHECK();
-			return 0;
+		} else {
+			int cx = 1; while (cx < k && cx < 32) cx <<= 1;
+			const int ry = 256 / cx;
+			long long chunks = g_b200.num_sms * 4;
+			long long rows_per_chunk = (n + chunks - 1) / chunks;
+			if (rows_per_chunk < ry) rows_per_chunk = ry;
+			chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
+			double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * k);
+			if (!part) return 1;
+			dots_partial_kernel<<<(unsigned)chunks, dim3(cx, ry), sizeof(double) * (size_t)ry * k, st>>>(
+				n, k, x, ldx, y, ldy, rows_per_chunk, part);
+			B200_KERNEL_CHECK();
+			dots_reduce_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, (int)chunks, part, alpha, dst, d_rs);
+			B200_KERNEL_CHECK();
 		}
-		int cx = 1; while (cx < k && cx < 32) cx <<= 1;
-		const int ry = 256 / cx;
-		long long chunks = g_b200.num_sms * 4;
-		long long rows_per_chunk = (n + chunks - 1) / chunks;
-		if (rows_per_chunk < ry) rows_per_chunk = ry;
-		chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
-		double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * k);
-		if (!part) return 1;
-		dots_partial_kernel<<<(unsigned)chunks, dim3(cx, ry), sizeof(double) * (size_t)ry * k, st>>>(
-			n, k, x, ldx, y, ldy, rows_per_chunk, part);
-		B200_KERNEL_CHECK();
-		dots_reduce_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, (int)chunks, part, alpha, c_dev, c_rs);
-		B200_KERNEL_CHECK();
+		if (multi) {
+			if (b200k_allreduce_sum(dst, (size_t)k)) return 1;
+			gram_scatter_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, 1, dst, c_dev, c_rs, 0, 0);
+			B200_KERNEL_CHECK();
+		}
 		return 0;
 	}
 	if (n <= 0) {
-		fill2d_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, 0.0, c_dev, c_rs, c_cs);
+		fill2d_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, 0.0, dst, d_rs, d_cs);
 		B200_KERNEL_CHECK();
-		return 0;
+	} else {
+		const int ptiles = b200_ceil_div(p, GR_BP), qtiles = b200_ceil_div(q, GR_BQ);
+		long long chunks = (long long)(g_b200.num_sms * 4) / ((long long)ptiles * qtiles);
+		if (chunks < 1) chunks = 1;
+		long long rows_per_chunk = (n + chunks - 1) / chunks;
+		rows_per_chunk = ((rows_per_chunk + GR_BK - 1) / GR_BK) * GR_BK;
+		if (rows_per_chunk < 4 * GR_BK) rows_per_chunk = 4 * GR_BK;
+		chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
+		double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * p * q);
+		if (!part) return 1;
+		dim3 grid(ptiles, (unsigned)chunks, qtiles);
+		const size_t smem = sizeof(double) * (size_t)GR_STAGES * GR_STAGE_DBL;
+		static bool attr_set = false;
+		if (!attr_set) {
+			B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			attr_set = true;
+		}
+		// 16-byte copies need even column offsets (pointer alignment), even leading dimensions and
+		// even tile widths; anything else takes the 8-byte path
+		const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) &&
+		                  (p % 2 == 0) && (q % 2 == 0);
+		if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		else      gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		B200_KERNEL_CHECK();
+		gram_reduce_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, (int)chunks, part, alpha, dst,
+		                                                                        d_rs, d_cs, (!multi && mode == 'S') ? 1 : 0);
+		B200_KERNEL_CHECK();
 	}
-	const int ptiles = b200_ceil_div(p, GR_BP), qtiles = b200_ceil_div(q, GR_BQ);
-	long long chunks = (long long)(g_b200.num_sms * 4) / ((long long)ptiles * qtiles);
-	if (chunks < 1) chunks = 1;
-	long long rows_per_chunk = (n + chunks - 1) / chunks;
-	rows_per_chunk = ((rows_per_chunk + GR_BK - 1) / GR_BK) * GR_BK;
-	if (rows_per_chunk < 4 * GR_BK) rows_per_chunk = 4 * GR_BK;
-	chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
-	double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * p * q);
-	if (!part) return 1;
-	dim3 grid(ptiles, (unsigned)chunks, qtiles);
-	const size_t smem = sizeof(double) * (size_t)GR_STAGES * GR_STAGE_DBL;
-	static bool attr_set = false;
-	if (!attr_set) {
-		B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		B200_CUDA(cudaFuncSetAttribute(gram_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
+	if (multi) {
+		if (b200k_allreduce_sum(dst, (size_t)p * q)) return 1;
+		gram_scatter_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, dst, c_dev, c_rs, c_cs,
+		                                                                         mode == 'S' ? 1 : 0);
+		B200_KERNEL_CHECK();
 	}
-	// 16-byte copies need even column offsets (pointer alignment), even leading dimensions and
-	// even tile widths; anything else takes the 8-byte path
-	const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) &&
-	                  (p % 2 == 0) && (q % 2 == 0);
-	if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
-	else      gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
-	B200_KERNEL_CHECK();
-	gram_reduce_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, (int)chunks, part, alpha, c_dev,
-	                                                                        c_rs, c_cs, mode == 'S' ? 1 : 0);
-	B200_KERNEL_CHECK();
 	return 0;
 }
 

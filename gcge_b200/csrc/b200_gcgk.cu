@@ -6,7 +6,7 @@
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 residual_kernel(long long n, int k, StreamGeom g, double *__restrict__ ax, int ldax, const double *__restrict__ bx, int ldbx,
-                const double *__restrict__ lam, double *res, double *part, unsigned *ticket)
+                const double *__restrict__ lam, double *res, double *part, unsigned *ticket, int defer)
 {
 	const StreamThread t = stream_thread<VEC>(g);
 	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
@@ -43,8 +43,14 @@ residual_kernel(long long n, int k, StreamGeom g, double *__restrict__ ax, int l
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int c = warp; c < k; c += ST_THREADS / 32) {
 		const double s = stream_total<1>(part, gridDim.x, k, 0, c);
-		if (lane == 0) res[c] = sqrt(s);
+		if (lane == 0) res[c] = defer ? s : sqrt(s);      // several ranks: sum first, root after the allreduce
 	}
+}
+
+__global__ void sqrt_inplace_kernel(int k, double *v)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < k) v[i] = sqrt(v[i]);
 }
 
 extern "C" int b200k_residual_norms(long long n, int k, double *ax, int ldax, const double *bx, int ldbx,
@@ -59,8 +65,13 @@ extern "C" int b200k_residual_norms(long long n, int k, double *ax, int ldax, co
 	double *part = (double *)base;
 	unsigned *ticket = (unsigned *)(part + (size_t)(g.chunks + 1) * k);
 	B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), g_b200.stream));
-	ST_DISPATCH_VEC(g, (residual_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket)));
+	ST_DISPATCH_VEC(g, (residual_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, ax, ldax, bx, ldbx, lam_dev, res_dev, part, ticket, b200_multi() ? 1 : 0)));
 	B200_KERNEL_CHECK();
+	if (b200_multi()) {
+		if (b200k_allreduce_sum(res_dev, (size_t)k)) return 1;
+		sqrt_inplace_kernel<<<1, 128, 0, g_b200.stream>>>(k, res_dev);
+		B200_KERNEL_CHECK();
+	}
 	return 0;
 }
 

@@ -18,16 +18,29 @@ struct b200_ctx {
 	cudaStream_t stream;
 	// growable device scratch: [0] reduction partials, [1] coefficient staging,
 	// [2] host<->device column-major staging, [3] small results
-	void *scratch[6];
-	size_t scratch_bytes[6];
+	// [4] BlockPCG state, [5] Jacobi work, [6] halo send buffer, [7] halo receive buffer,
+	// [8] contiguous Gram block for the allreduce
+	void *scratch[10];
+	size_t scratch_bytes[10];
 	// pinned host staging for small results / coefficients
 	void *pinned[2];
 	size_t pinned_bytes[2];
 	long long launches;
 	char err[512];
+	// multi-GPU layout (b200_comm.cu): rank of this process, number of ranks (0/1 = single GPU)
+	int rank, nranks;
+	// halo rows a multi-vector with n global rows must be able to hold behind its local rows:
+	// the largest halo of any matrix with that many columns created so far
+	long long halo_n[8];
+	int halo_cap[8];
 };
 
+int b200k_allreduce_sum(double *buf_dev, size_t count);
+int b200k_neighbor_exchange(int nnbr, const int *nbr, const double *send_dev, const size_t *send_off,
+                            const size_t *send_cnt, double *recv_dev, const size_t *recv_off, const size_t *recv_cnt);
+
 extern b200_ctx g_b200;
+static inline bool b200_multi() { return g_b200.nranks > 1; }
 
 #define B200_CUDA(call)                                                            \
 	do {                                                                           \

@@ -7,55 +7,207 @@
 // reference's floating-point sum bit for bit.
 #include "b200_internal.h"
 #include <vector>
+#include <algorithm>
+
+extern "C" void b200_partition_range(long long n, int rank, int nranks, long long *lo, long long *hi);
+
+static int owner_of(long long row, long long n, int nranks)
+{
+	// largest g with floor(g n / G) <= row
+	int g = (int)(((__int128)(row + 1) * nranks - 1) / n);
+	if (g >= nranks) g = nranks - 1;
+	long long lo, hi;
+	b200_partition_range(n, g, nranks, &lo, &hi);
+	while (row < lo) { --g; b200_partition_range(n, g, nranks, &lo, &hi); }
+	while (row >= hi) { ++g; b200_partition_range(n, g, nranks, &lo, &hi); }
+	return g;
+}
+
+// Host-only: the local CSR slab of rank `rank`, its halo list and the send lists.  No device
+// call in here, so tests can run it on a CPU-only box for any (rank, nranks).
+extern "C" int b200_partition_build(int nrows, int ncols, const int *j_col, const int *i_row, const double *data,
+                                    int rank, int nranks, b200_mat *A, int **rp_h, int **ci_h, double **va_h)
+{
+	B200_CHECK(A && j_col && nrows >= 0 && ncols >= 0 && rp_h && ci_h && va_h, "partition: bad arguments");
+	if (nranks < 1) nranks = 1;
+	B200_CHECK(nranks == 1 || nrows == ncols, "partition: a %d x %d matrix cannot be row-partitioned together with "
+	           "its multi-vectors (square matrices only across ranks)", nrows, ncols);
+	const int nnz = j_col[ncols];
+	B200_CHECK(nnz >= 0 && (nnz == 0 || (i_row && data)), "b200_mat_create_from_ccs: bad CCS arrays");
+	for (int j = 0; j < ncols; ++j)
+		B200_CHECK(j_col[j] <= j_col[j + 1], "b200_mat_create_from_ccs: j_col not monotone at %d", j);
+	long long lo = 0, hi = nrows;
+	if (nranks > 1) b200_partition_range(nrows, rank, nranks, &lo, &hi);
+	const int nloc = (int)(hi - lo);
+	// local CSR by counting sort over the slab's rows, columns visited ascending
+	int *rp = (int *)calloc((size_t)nloc + 1, sizeof(int));
+	B200_CHECK(rp, "partition: out of host memory");
+	for (int e = 0; e < nnz; ++e) {
+		const int r = i_row[e];
+		if (r < 0 || r >= nrows) { free(rp); return b200_fail("b200_mat_create_from_ccs: row index %d out of range at %d", r, e); }
+		if (r >= lo && r < hi) ++rp[r - lo + 1];
+	}
+	for (int r = 0; r < nloc; ++r) rp[r + 1] += rp[r];
+	const int nnz_loc = rp[nloc];
+	int *ci = (int *)malloc(sizeof(int) * (size_t)(nnz_loc > 0 ? nnz_loc : 1));
+	double *va = (double *)malloc(sizeof(double) * (size_t)(nnz_loc > 0 ? nnz_loc : 1));
+	if (!ci || !va) { free(rp); free(ci); free(va); return b200_fail("partition: out of host memory"); }
+	{
+		std::vector<int> next(rp, rp + nloc);
+		for (int j = 0; j < ncols; ++j)
+			for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
+				const int r = i_row[e];
+				if (r >= lo && r < hi) { const int pos = next[r - lo]++; ci[pos] = j; va[pos] = data[e]; }
+			}
+	}
+	A->nrows = nloc; A->ncols = (nranks == 1) ? ncols : nloc; A->nnz = nnz_loc;
+	A->nrows_global = nrows; A->ncols_global = ncols; A->nnz_global = nnz; A->row0 = (int)lo; A->t_col0 = lo;
+	for (int r = 0; r < nloc; ++r) if (rp[r + 1] - rp[r] > A->max_row_nnz) A->max_row_nnz = rp[r + 1] - rp[r];
+	// symmetric: the slab's CSR rows (global columns) are the caller's CCS columns [lo, hi) bit for bit
+	int sym = (nrows == ncols);
+	if (sym) {
+		const int base = j_col[lo];
+		for (int r = 0; r <= nloc && sym; ++r) sym = (rp[r] == j_col[lo + r] - base);
+		if (sym && nnz_loc) sym = (0 == memcmp(ci, i_row + base, sizeof(int) * (size_t)nnz_loc));
+		if (sym && nnz_loc) sym = (0 == memcmp(va, data + base, sizeof(double) * (size_t)nnz_loc));
+	}
+	A->symmetric = sym;
+	if (nranks > 1) {
+		// halo list: off-slab columns, ascending, unique
+		std::vector<unsigned char> mark((size_t)ncols, 0);
+		for (int e = 0; e < nnz_loc; ++e) if (ci[e] < lo || ci[e] >= hi) mark[ci[e]] = 1;
+		std::vector<int> halo;
+		for (int c = 0; c < ncols; ++c) if (mark[c]) halo.push_back(c);
+		A->nhalo = (int)halo.size();
+		for (int e = 0; e < nnz_loc; ++e) {
+			const int c = ci[e];
+			if (c >= lo && c < hi) ci[e] = c - (int)lo;
+			else ci[e] = nloc + (int)(std::lower_bound(halo.begin(), halo.end(), c) - halo.begin());
+		}
+		// what the other ranks need from me: my columns j with an entry in a row they own
+		std::vector<std::vector<int>> send((size_t)nranks);
+		for (long long j = lo; j < hi; ++j)
+			for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
+				const int r = i_row[e];
+				if (r >= lo && r < hi) continue;
+				const int q = owner_of(r, nrows, nranks);
+				if (send[q].empty() || send[q].back() != (int)(j - lo)) send[q].push_back((int)(j - lo));
+			}
+		std::vector<int> recv_cnt((size_t)nranks, 0);
+		for (int c : halo) ++recv_cnt[owner_of(c, nrows, nranks)];
+		std::vector<int> nbr;
+		for (int q = 0; q < nranks; ++q) if (q != rank && (recv_cnt[q] || !send[q].empty())) nbr.push_back(q);
+		A->nnbr = (int)nbr.size();
+		A->nbr = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->recv_off = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->send_off = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->halo_cols = (int *)malloc(sizeof(int) * (halo.size() + 1));
+		memcpy(A->halo_cols, halo.data(), sizeof(int) * halo.size());
+		int so = 0, ro = 0;
+		for (size_t i = 0; i < nbr.size(); ++i) {
+			A->nbr[i] = nbr[i]; A->recv_off[i] = ro; A->send_off[i] = so;
+			ro += recv_cnt[nbr[i]]; so += (int)send[nbr[i]].size();
+		}
+		A->recv_off[nbr.size()] = ro; A->send_off[nbr.size()] = so;
+		A->send_rows = (int *)malloc(sizeof(int) * (size_t)(so > 0 ? so : 1));
+		for (size_t i = 0; i < nbr.size(); ++i)
+			memcpy(A->send_rows + A->send_off[i], send[nbr[i]].data(), sizeof(int) * send[nbr[i]].size());
+	}
+	*rp_h = rp; *ci_h = ci; *va_h = va;
+	return 0;
+}
+
+// ---- host-only view of the partition plan (tests; needs no device) ---------------------------
+struct b200_plan_ { b200_mat m; int *rp, *ci; double *va; };
+
+extern "C" int b200_plan_create(int nrows, int ncols, const int *j_col, const int *i_row, const double *data,
+                                int rank, int nranks, b200_plan **out)
+{
+	B200_CHECK(out, "b200_plan_create: bad arguments");
+	b200_plan *p = (b200_plan *)calloc(1, sizeof(b200_plan));
+	if (b200_partition_build(nrows, ncols, j_col, i_row, data, rank, nranks, &p->m, &p->rp, &p->ci, &p->va)) { free(p); return 1; }
+	*out = p;
+	return 0;
+}
+
+extern "C" int b200_plan_sizes(const b200_plan *p, int *row0, int *nrows_local, int *nnz_local, int *nhalo, int *nnbr,
+                               int *nsend, int *symmetric)
+{
+	B200_CHECK(p, "b200_plan_sizes: NULL plan");
+	if (row0) *row0 = p->m.row0;
+	if (nrows_local) *nrows_local = p->m.nrows;
+	if (nnz_local) *nnz_local = p->m.nnz;
+	if (nhalo) *nhalo = p->m.nhalo;
+	if (nnbr) *nnbr = p->m.nnbr;
+	if (nsend) *nsend = p->m.nnbr ? p->m.send_off[p->m.nnbr] : 0;
+	if (symmetric) *symmetric = p->m.symmetric;
+	return 0;
+}
+
+extern "C" int b200_plan_copy(const b200_plan *p, int *rp, int *ci, double *va, int *halo_cols, int *nbr,
+                              int *recv_off, int *send_off, int *send_rows)
+{
+	B200_CHECK(p, "b200_plan_copy: NULL plan");
+	const b200_mat *m = &p->m;
+	if (rp) memcpy(rp, p->rp, sizeof(int) * ((size_t)m->nrows + 1));
+	if (ci) memcpy(ci, p->ci, sizeof(int) * (size_t)m->nnz);
+	if (va) memcpy(va, p->va, sizeof(double) * (size_t)m->nnz);
+	if (halo_cols && m->nhalo) memcpy(halo_cols, m->halo_cols, sizeof(int) * (size_t)m->nhalo);
+	if (m->nnbr) {
+		if (nbr) memcpy(nbr, m->nbr, sizeof(int) * (size_t)m->nnbr);
+		if (recv_off) memcpy(recv_off, m->recv_off, sizeof(int) * ((size_t)m->nnbr + 1));
+		if (send_off) memcpy(send_off, m->send_off, sizeof(int) * ((size_t)m->nnbr + 1));
+		if (send_rows) memcpy(send_rows, m->send_rows, sizeof(int) * (size_t)m->send_off[m->nnbr]);
+	}
+	return 0;
+}
+
+extern "C" int b200_plan_destroy(b200_plan *p)
+{
+	if (!p) return 0;
+	free(p->rp); free(p->ci); free(p->va);
+	free(p->m.nbr); free(p->m.halo_cols); free(p->m.recv_off); free(p->m.send_off); free(p->m.send_rows);
+	free(p);
+	return 0;
+}
+
+static void note_halo_capacity(long long n_global, int nhalo)
+{
+	for (int i = 0; i < 8; ++i) {
+		if (g_b200.halo_n[i] == n_global || g_b200.halo_n[i] == 0) {
+			g_b200.halo_n[i] = n_global;
+			if (nhalo > g_b200.halo_cap[i]) g_b200.halo_cap[i] = nhalo;
+			return;
+		}
+	}
+}
 
 extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, const int *i_row,
                                         const double *data, b200_mat **out)
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(out && j_col && nrows >= 0 && ncols >= 0, "b200_mat_create_from_ccs: bad arguments");
-	const int nnz = j_col[ncols];
-	B200_CHECK(nnz >= 0 && (nnz == 0 || (i_row && data)), "b200_mat_create_from_ccs: bad CCS arrays");
-	for (int j = 0; j < ncols; ++j)
-		B200_CHECK(j_col[j] <= j_col[j + 1], "b200_mat_create_from_ccs: j_col not monotone at %d", j);
-
-	// host transpose (counting sort by row, columns visited ascending)
-	std::vector<int> rp((size_t)nrows + 1, 0), ci((size_t)nnz);
-	std::vector<double> va((size_t)nnz);
-	for (int e = 0; e < nnz; ++e) {
-		B200_CHECK(i_row[e] >= 0 && i_row[e] < nrows, "b200_mat_create_from_ccs: row index %d out of range at %d",
-		           i_row[e], e);
-		++rp[(size_t)i_row[e] + 1];
-	}
-	for (int r = 0; r < nrows; ++r) rp[r + 1] += rp[r];
-	{
-		std::vector<int> next(rp.begin(), rp.end() - 1);
-		for (int j = 0; j < ncols; ++j)
-			for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
-				const int pos = next[i_row[e]]++;
-				ci[pos] = j; va[pos] = data[e];
-			}
-	}
-	// identical images (symmetric matrix, sorted columns) => share storage
-	int shared = (nrows == ncols);
-	if (shared) shared = (0 == memcmp(rp.data(), j_col, sizeof(int) * ((size_t)nrows + 1)));
-	if (shared && nnz) shared = (0 == memcmp(ci.data(), i_row, sizeof(int) * (size_t)nnz));
-	if (shared && nnz) shared = (0 == memcmp(va.data(), data, sizeof(double) * (size_t)nnz));
-
+	const int nranks = g_b200.nranks > 1 ? g_b200.nranks : 1;
 	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
-	A->nrows = nrows; A->ncols = ncols; A->nnz = nnz; A->t_shared = shared; A->row0 = 0;
-	for (int r = 0; r < nrows; ++r) if (rp[r + 1] - rp[r] > A->max_row_nnz) A->max_row_nnz = rp[r + 1] - rp[r];
+	int *rp = nullptr, *ci = nullptr; double *va = nullptr;
+	if (b200_partition_build(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A, &rp, &ci, &va)) { free(A); return 1; }
+	const int nnz = A->nnz, nloc = A->nrows;
 	for (int j = 0; j < ncols; ++j) if (j_col[j + 1] - j_col[j] > A->t_max_row_nnz) A->t_max_row_nnz = j_col[j + 1] - j_col[j];
+	// single GPU, symmetric matrix: the CCS arrays ARE the CSR image => share storage
+	const int shared = (nranks == 1) && A->symmetric;
+	A->t_shared = shared;
 	cudaStream_t st = g_b200.stream;
 	const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
-	B200_CUDA(cudaMalloc(&A->rp, sizeof(int) * ((size_t)nrows + 1)));
+	B200_CUDA(cudaMalloc(&A->rp, sizeof(int) * ((size_t)nloc + 1)));
 	B200_CUDA(cudaMalloc(&A->ci, sizeof(int) * nz));
 	B200_CUDA(cudaMalloc(&A->va, sizeof(double) * nz));
-	B200_CUDA(cudaMemcpyAsync(A->rp, rp.data(), sizeof(int) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, st));
-	B200_CUDA(cudaMemcpyAsync(A->ci, ci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-	B200_CUDA(cudaMemcpyAsync(A->va, va.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->rp, rp, sizeof(int) * ((size_t)nloc + 1), cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->ci, ci, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->va, va, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
 	if (shared) {
 		A->t_rp = A->rp; A->t_ci = A->ci; A->t_va = A->va;
-	} else {
+	} else if (nranks == 1) {
+		// the caller's CCS arrays verbatim: CSR of A^T, and the bit-exact round trip
 		B200_CUDA(cudaMalloc(&A->t_rp, sizeof(int) * ((size_t)ncols + 1)));
 		B200_CUDA(cudaMalloc(&A->t_ci, sizeof(int) * nz));
 		B200_CUDA(cudaMalloc(&A->t_va, sizeof(double) * nz));
@@ -63,7 +215,14 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 		B200_CUDA(cudaMemcpyAsync(A->t_ci, i_row, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
 		B200_CUDA(cudaMemcpyAsync(A->t_va, data, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
 	}
+	if (nranks > 1) {
+		const int ns = A->send_off[A->nnbr];
+		B200_CUDA(cudaMalloc(&A->send_rows_dev, sizeof(int) * (size_t)(ns > 0 ? ns : 1)));
+		B200_CUDA(cudaMemcpyAsync(A->send_rows_dev, A->send_rows, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
+		note_halo_capacity(A->ncols_global, A->nhalo);
+	}
 	B200_CUDA(cudaStreamSynchronize(st));
+	free(rp); free(ci); free(va);
 	*out = A;
 	return 0;
 }
@@ -72,8 +231,10 @@ extern "C" int b200_mat_destroy(b200_mat *A)
 {
 	if (!A) return 0;
 	if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
-	if (!A->t_shared) { cudaFree(A->t_rp); cudaFree(A->t_ci); cudaFree(A->t_va); }
+	if (!A->t_shared && A->t_rp) { cudaFree(A->t_rp); cudaFree(A->t_ci); cudaFree(A->t_va); }
 	cudaFree(A->rp); cudaFree(A->ci); cudaFree(A->va);
+	if (A->send_rows_dev) cudaFree(A->send_rows_dev);
+	free(A->nbr); free(A->halo_cols); free(A->recv_off); free(A->send_off); free(A->send_rows);
 	free(A);
 	return 0;
 }
@@ -81,9 +242,38 @@ extern "C" int b200_mat_destroy(b200_mat *A)
 extern "C" int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nnz)
 {
 	B200_CHECK(A, "b200_mat_shape: NULL matrix");
-	if (nrows) *nrows = A->nrows;
-	if (ncols) *ncols = A->ncols;
-	if (nnz) *nnz = A->nnz;
+	if (nrows) *nrows = A->nrows_global;
+	if (ncols) *ncols = A->ncols_global;
+	if (nnz) *nnz = A->nnz_global;
+	return 0;
+}
+
+extern "C" int b200_mat_local_range(const b200_mat *A, int *row0, int *nrows_local, int *nnz_local, int *nhalo)
+{
+	B200_CHECK(A, "b200_mat_local_range: NULL matrix");
+	if (row0) *row0 = A->row0;
+	if (nrows_local) *nrows_local = A->nrows;
+	if (nnz_local) *nnz_local = A->nnz;
+	if (nhalo) *nhalo = A->nhalo;
+	return 0;
+}
+
+// This rank's CSR row slab from the device, with GLOBAL column indices.  Concatenating the slabs
+// of all ranks in rank order gives the CSR image of the whole matrix (== CCS of A^T): the
+// bit-exact round trip of the partition.
+extern "C" int b200_mat_local_csr(const b200_mat *A, int *rp, int *ci, double *va)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(A && rp, "b200_mat_local_csr: bad arguments");
+	cudaStream_t st = g_b200.stream;
+	B200_CUDA(cudaMemcpyAsync(rp, A->rp, sizeof(int) * ((size_t)A->nrows + 1), cudaMemcpyDeviceToHost, st));
+	if (A->nnz) {
+		B200_CUDA(cudaMemcpyAsync(ci, A->ci, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaMemcpyAsync(va, A->va, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, st));
+	}
+	B200_CUDA(cudaStreamSynchronize(st));
+	if (A->nhalo || A->row0)
+		for (int e = 0; e < A->nnz; ++e) ci[e] = ci[e] < A->nrows ? ci[e] + A->row0 : A->halo_cols[ci[e] - A->nrows];
 	return 0;
 }
 
@@ -91,6 +281,8 @@ extern "C" int b200_mat_to_ccs(const b200_mat *A, int *j_col, int *i_row, double
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(A && j_col, "b200_mat_to_ccs: bad arguments");
+	B200_CHECK(A->t_rp, "b200_mat_to_ccs: the matrix is row-partitioned over %d ranks; gather the slabs with "
+	           "b200_mat_local_csr", g_b200.nranks);
 	cudaStream_t st = g_b200.stream;
 	B200_CUDA(cudaMemcpyAsync(j_col, A->t_rp, sizeof(int) * ((size_t)A->ncols + 1), cudaMemcpyDeviceToHost, st));
 	if (A->nnz) {
@@ -124,8 +316,8 @@ extern "C" int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200
 	                                                                      : g_b200.num_sms * 8;
 	mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->va, beta, Y->va);
 	B200_KERNEL_CHECK();
-	if (!Y->t_shared) {
-		B200_CHECK(!X->t_shared || X->t_va, "b200_mat_axpby: internal");
+	if (!Y->t_shared && Y->t_va) {
+		B200_CHECK(X->t_va, "b200_mat_axpby: internal");
 		mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->t_va, beta, Y->t_va);
 		B200_KERNEL_CHECK();
 	}

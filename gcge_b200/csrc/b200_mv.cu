@@ -9,13 +9,27 @@ static int mv_ld_for(int ncols)
 	return (ncols + 3) & ~3;
 }
 
+extern "C" void b200_partition_range(long long n, int rank, int nranks, long long *lo, long long *hi);
+
+// nrows is the GLOBAL row count.  On several ranks only this rank's row block is allocated,
+// followed by room for the SpMM halo rows of the widest-halo matrix with that many columns
+// created so far (matrices are created before their multi-vectors: MultiVecCreateByMat).
 extern "C" int b200_mv_create(int nrows, int ncols, b200_mv **out)
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(out && nrows >= 0 && ncols >= 0, "b200_mv_create: bad arguments");
 	b200_mv *x = (b200_mv *)calloc(1, sizeof(b200_mv));
+	long long lo = 0, hi = nrows;
+	int halo = 0;
+	if (b200_multi()) {
+		b200_partition_range(nrows, g_b200.rank, g_b200.nranks, &lo, &hi);
+		for (int i = 0; i < 8; ++i) if (g_b200.halo_n[i] == nrows) halo = g_b200.halo_cap[i];
+		x->dist = 1;
+	}
+	x->nrows_global = nrows; x->row0 = lo; x->halo_cap = halo;
+	nrows = (int)(hi - lo);
 	x->nrows = nrows; x->ncols = ncols; x->ld = mv_ld_for(ncols); x->owner = 1;
-	size_t bytes = sizeof(double) * (size_t)(nrows > 0 ? nrows : 1) * (size_t)x->ld;
+	size_t bytes = sizeof(double) * (size_t)(nrows + halo > 0 ? nrows + halo : 1) * (size_t)x->ld;
 	cudaError_t e = cudaMalloc(&x->d, bytes);
 	if (e != cudaSuccess) {
 		free(x);
@@ -41,7 +55,8 @@ extern "C" int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view
 {
 	B200_CHECK(x && view && start >= 0 && start <= end && end <= x->ncols, "b200_mv_view: bad arguments");
 	b200_mv *v = (b200_mv *)calloc(1, sizeof(b200_mv));
-	v->nrows = x->nrows; v->ncols = end - start; v->ld = x->ld; v->d = x->d + start; v->owner = 0;
+	*v = *x;
+	v->ncols = end - start; v->d = x->d + start; v->owner = 0;
 	*view = v;
 	return 0;
 }
@@ -49,8 +64,16 @@ extern "C" int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view
 extern "C" int b200_mv_shape(const b200_mv *x, int *nrows, int *ncols)
 {
 	B200_CHECK(x, "b200_mv_shape: NULL multi-vector");
-	if (nrows) *nrows = x->nrows;
+	if (nrows) *nrows = x->nrows_global;
 	if (ncols) *ncols = x->ncols;
+	return 0;
+}
+
+extern "C" int b200_mv_local_range(const b200_mv *x, int *row0, int *nrows_local)
+{
+	B200_CHECK(x, "b200_mv_local_range: NULL multi-vector");
+	if (row0) *row0 = (int)x->row0;
+	if (nrows_local) *nrows_local = x->nrows;
 	return 0;
 }
 
@@ -115,8 +138,10 @@ static const size_t kStageBytes = (size_t)256 << 20;
 extern "C" int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld)
 {
 	B200_REQUIRE_INIT();
-	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows_global,
 	           "b200_mv_upload: bad arguments");
+	// host is the GLOBAL column-major block; this rank takes its rows [row0, row0 + nrows)
+	host += x->row0;
 	const long long n = x->nrows;
 	if (n == 0 || end == start) return 0;
 	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));
@@ -138,8 +163,10 @@ extern "C" int b200_mv_upload(b200_mv *x, int start, int end, const double *host
 extern "C" int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld)
 {
 	B200_REQUIRE_INIT();
-	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows_global,
 	           "b200_mv_download: bad arguments");
+	// host is the GLOBAL column-major block; this rank fills its rows [row0, row0 + nrows) only
+	host += x->row0;
 	const long long n = x->nrows;
 	if (n == 0 || end == start) return 0;
 	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));

@@ -132,9 +132,11 @@ __device__ __forceinline__ void dev_mat_vec(const uint32_t *__restrict__ m, uint
 
 // pw: NPOW matrices, P_j = M^(CHUNK 2^j), row-major 31 x 31.  x: row-major destination block
 // (first element of the first column to fill); stream position t -> row t % n, column t / n.
+// Several ranks: n is the GLOBAL row count and x holds the rows [row_lo, row_hi) only; every
+// rank walks the same stream and keeps its own rows (chunks that miss the slab exit early).
 __global__ void __launch_bounds__(RTHREADS)
 rand_fill_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ pw, unsigned long long total,
-                 long long n, double *__restrict__ x, int ld)
+                 long long n, long long row_lo, long long row_hi, double *__restrict__ x, int ld)
 {
 	__shared__ uint32_t base[2][DEG];
 	const unsigned long long c0 = (unsigned long long)blockIdx.x * RTHREADS;
@@ -156,6 +158,13 @@ rand_fill_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ p
 	const unsigned long long c = c0 + threadIdx.x;
 	const unsigned long long t0 = c * (unsigned long long)CHUNK;
 	if (t0 >= total) return;
+	{
+		const unsigned long long len = (total - t0 < (unsigned long long)CHUNK) ? total - t0 : (unsigned long long)CHUNK;
+		const unsigned long long r_first = t0 % (unsigned long long)n;
+		if (r_first + len <= (unsigned long long)n &&
+		    (r_first >= (unsigned long long)row_hi || r_first + len <= (unsigned long long)row_lo))
+			return;                                    // no row of this chunk is ours
+	}
 	uint32_t s[DEG];
 #pragma unroll
 	for (int i = 0; i < DEG; ++i) s[i] = base[cur][i];
@@ -164,16 +173,16 @@ rand_fill_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ p
 	long long col = (long long)(t0 / (unsigned long long)n);
 	long long row = (long long)(t0 - (unsigned long long)col * (unsigned long long)n);
 	unsigned long long left = total - t0;
-	double *xp = x + (size_t)row * ld + col;
 	for (int r = 0; r < ROUNDS && left > 0; ++r) {
 #pragma unroll
 		for (int i = 0; i < DEG; ++i) {
 			s[i] += s[(i + DEG - SEP) % DEG];
 			if (left > 0) {
-				*xp = (double)(s[i] >> 1) * (1.0 / 2147483648.0);
+				if (row >= row_lo && row < row_hi)
+					x[(size_t)(row - row_lo) * ld + col] = (double)(s[i] >> 1) * (1.0 / 2147483648.0);
 				--left;
-				++row; xp += ld;
-				if (row == n) { row = 0; ++col; xp = x + col; }
+				++row;
+				if (row == n) { row = 0; ++col; }
 			}
 		}
 	}
@@ -244,7 +253,7 @@ extern "C" int b200_mv_set_random(b200_mv *x, int start, int end)
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(x && start >= 0 && end <= x->ncols && start <= end, "b200_mv_set_random: bad arguments");
-	const long long n = x->nrows;
+	const long long n = x->nrows_global;
 	if (n == 0 || end == start) return 0;
 	const unsigned long long total = (unsigned long long)n * (unsigned long long)(end - start);
 	if (ensure_powers()) return 1;
@@ -262,7 +271,8 @@ extern "C" int b200_mv_set_random(b200_mv *x, int start, int end)
 	if (e == cudaSuccess) {
 		const unsigned long long chunks = (total + CHUNK - 1) / CHUNK;
 		const unsigned long long ctas = (chunks + RTHREADS - 1) / RTHREADS;
-		rand_fill_kernel<<<(unsigned)ctas, RTHREADS, 0, g_b200.stream>>>(s_dev, g_pw_dev, total, n, x->d + start, x->ld);
+		rand_fill_kernel<<<(unsigned)ctas, RTHREADS, 0, g_b200.stream>>>(s_dev, g_pw_dev, total, n, x->row0, x->row0 + x->nrows,
+		                                                                 x->d + start, x->ld);
 		B200_LAUNCHED();
 		e = cudaGetLastError();
 	}

@@ -53,7 +53,7 @@ extern "C" void b200_finalize(void)
 {
 	if (!g_b200.initialised) return;
 	cudaStreamSynchronize(g_b200.stream);
-	for (int i = 0; i < 6; ++i) {
+	for (int i = 0; i < 10; ++i) {
 		if (g_b200.scratch[i]) cudaFree(g_b200.scratch[i]);
 		g_b200.scratch[i] = nullptr; g_b200.scratch_bytes[i] = 0;
 	}

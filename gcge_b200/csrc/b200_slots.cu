@@ -17,14 +17,14 @@ static int fetch_to_host(const double *dev, int rows, int cols, double *host, in
 }
 
 static int inner_prod_impl(char nsd, const double *x, int ldx, const double *y, int ldy, long long n,
-                           int p, int q, double *host, int ld)
+                           int p, int q, double *host, int ld, int dist)
 {
 	if (p <= 0 || q <= 0) return 0;
 	if (nsd == 'D') {
 		B200_CHECK(p == q, "inner_prod 'D': %d x %d is not square", p, q);
 		double *dev = (double *)b200_scratch(3, sizeof(double) * (size_t)p);
 		if (!dev) return 1;
-		if (b200k_gram('D', n, p, q, 1.0, x, ldx, y, ldy, dev, 1, 0)) return 1;
+		if (b200k_gram('D', n, p, q, 1.0, x, ldx, y, ldy, dev, 1, 0, dist)) return 1;
 		double *pin = (double *)b200_pinned(0, sizeof(double) * (size_t)p);
 		if (!pin) return 1;
 		B200_CUDA(cudaMemcpyAsync(pin, dev, sizeof(double) * (size_t)p, cudaMemcpyDeviceToHost, g_b200.stream));
@@ -36,7 +36,7 @@ static int inner_prod_impl(char nsd, const double *x, int ldx, const double *y, 
 	B200_CHECK(ld >= p, "inner_prod: ld %d < %d rows", ld, p);
 	double *dev = (double *)b200_scratch(3, sizeof(double) * (size_t)p * q);
 	if (!dev) return 1;
-	if (b200k_gram(nsd == 'S' ? 'S' : 'N', n, p, q, 1.0, x, ldx, y, ldy, dev, 1, p)) return 1;
+	if (b200k_gram(nsd == 'S' ? 'S' : 'N', n, p, q, 1.0, x, ldx, y, ldy, dev, 1, p, dist)) return 1;
 	return fetch_to_host(dev, p, q, host, ld);
 }
 
@@ -49,8 +49,10 @@ extern "C" int b200_mv_inner_prod(char nsd, const b200_mv *x, const b200_mv *y,
 	B200_CHECK(x->nrows == y->nrows, "b200_mv_inner_prod: row counts differ");
 	B200_CHECK(start[0] >= 0 && end[0] <= x->ncols && start[1] >= 0 && end[1] <= y->ncols,
 	           "b200_mv_inner_prod: column range out of bounds");
+	// several ranks: the result is the GLOBAL inner product on every rank -- the reference, built
+	// without MPI, expects that from MultiVecLocalInnerProd and MultiVecInnerProd alike
 	return inner_prod_impl(nsd, x->d + start[0], x->ld, y->d + start[1], y->ld, x->nrows,
-	                       end[0] - start[0], end[1] - start[1], inner_prod, ld);
+	                       end[0] - start[0], end[1] - start[1], inner_prod, ld, x->dist);
 }
 
 extern "C" int b200_mv_qtap(char ntsA, char ntsdQAP, const b200_mv *Q, const b200_mat *A, const b200_mv *P,
@@ -69,6 +71,7 @@ extern "C" int b200_mv_qtap(char ntsA, char ntsdQAP, const b200_mv *Q, const b20
 		const int out_rows = tr ? A->ncols : A->nrows, in_rows = tr ? A->nrows : A->ncols;
 		B200_CHECK(P->nrows == in_rows && ws->nrows == out_rows && Q->nrows == out_rows,
 		           "b200_mv_qtap: shapes do not match the matrix");
+		if (b200k_spmm_check_halo(A, P)) return 1;
 		int rc = b200k_spmm(A, tr ? 1 : 0, P->d + start[1], P->ld, ws->d, ws->ld, nc, nullptr);
 		if (rc) return rc;
 		pd = ws->d; pld = ws->ld; n = ws->nrows;
@@ -77,8 +80,8 @@ extern "C" int b200_mv_qtap(char ntsA, char ntsdQAP, const b200_mv *Q, const b20
 		pd = P->d + start[1]; pld = P->ld; n = P->nrows;
 	}
 	if (ntsdQAP == 'T')   // store the transpose: (A P)^T Q, nc x nr (reference src/ops_multi_vec.c:394-398)
-		return inner_prod_impl('N', pd, pld, Q->d + start[0], Q->ld, n, nc, nr, qAp, ldQAP);
-	return inner_prod_impl(ntsdQAP, Q->d + start[0], Q->ld, pd, pld, n, nr, nc, qAp, ldQAP);
+		return inner_prod_impl('N', pd, pld, Q->d + start[0], Q->ld, n, nc, nr, qAp, ldQAP, Q->dist);
+	return inner_prod_impl(ntsdQAP, Q->d + start[0], Q->ld, pd, pld, n, nr, nc, qAp, ldQAP, Q->dist);
 }
 
 extern "C" int b200_mv_linear_comb(const b200_mv *x, b200_mv *y, const int *start, const int *end,

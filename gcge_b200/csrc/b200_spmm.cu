@@ -311,13 +311,67 @@ static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va
 	return 0;
 }
 
+// sendbuf[i, 0:k] = x[rows[i], 0:k]
+__global__ void halo_pack_kernel(int nsend, int k, const int *__restrict__ rows, const double *__restrict__ x, int ldx,
+                                 double *__restrict__ buf)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (long long)nsend * k) return;
+	const int i = (int)(idx / k), c = (int)(idx - (long long)i * k);
+	buf[idx] = x[(size_t)rows[i] * ldx + c];
+}
+
+extern "C" int b200k_spmm_check_halo(const b200_mat *M, const b200_mv *x)
+{
+	if (!b200_multi() || !M) return 0;
+	if (x->halo_cap < M->nhalo)
+		return b200_fail("SpMM across ranks: the multi-vector has room for %d halo rows but the matrix needs %d "
+		                 "(create matrices before their multi-vectors)", x->halo_cap, M->nhalo);
+	return 0;
+}
+
+// Halo rows of the k-column block x (rows [nrows, nrows + nhalo) of the multi-vector) from the
+// slab neighbours: pack the rows each neighbour needs, one grouped ncclSend/ncclRecv over
+// NVLink, unpack behind the local rows (reference analogue: the scatter of off-process
+// entries in app/app_phg.c:292-357, done there per column; here once for the whole block).
+static int halo_exchange(const b200_mat *M, double *x, int ldx, int k)
+{
+	if (M->nnbr == 0) return 0;
+	const int nsend = M->send_off[M->nnbr], nrecv = M->recv_off[M->nnbr];
+	double *sbuf = (double *)b200_scratch(6, sizeof(double) * (size_t)(nsend > 0 ? nsend : 1) * k);
+	double *rbuf = (double *)b200_scratch(7, sizeof(double) * (size_t)(nrecv > 0 ? nrecv : 1) * k);
+	if (!sbuf || !rbuf) return 1;
+	if (nsend > 0) {
+		const long long tot = (long long)nsend * k;
+		halo_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, g_b200.stream>>>(nsend, k, M->send_rows_dev, x, ldx, sbuf);
+		B200_KERNEL_CHECK();
+	}
+	size_t so[64], sc[64], ro[64], rc[64];
+	B200_CHECK(M->nnbr <= 64, "halo exchange: %d neighbours (at most 64)", M->nnbr);
+	for (int i = 0; i < M->nnbr; ++i) {
+		so[i] = (size_t)M->send_off[i] * k; sc[i] = (size_t)(M->send_off[i + 1] - M->send_off[i]) * k;
+		ro[i] = (size_t)M->recv_off[i] * k; rc[i] = (size_t)(M->recv_off[i + 1] - M->recv_off[i]) * k;
+	}
+	if (b200k_neighbor_exchange(M->nnbr, M->nbr, sbuf, so, sc, rbuf, ro, rc)) return 1;
+	if (nrecv > 0) return b200k_axpby(nrecv, k, 1.0, rbuf, k, 0.0, x + (size_t)M->nrows * ldx, ldx);
+	return 0;
+}
+
 int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
                const int *gate)
 {
+	if (trans && !M->t_rp) {
+		// row-partitioned matrix: only the forward image is kept; A^T x == A x when A is symmetric
+		// (the reference assumes that for every matrix, app/app_ccs.c:140-150)
+		B200_CHECK(M->symmetric, "transposed SpMM of a non-symmetric matrix is not available across ranks");
+		trans = 0;
+	}
 	const int nrows = trans ? M->ncols : M->nrows;
 	const int *rp = trans ? M->t_rp : M->rp, *ci = trans ? M->t_ci : M->ci;
 	const double *va = trans ? M->t_va : M->va;
-	if (nrows <= 0 || k <= 0) return 0;
+	if (k <= 0) return 0;
+	if (b200_multi() && halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
+	if (nrows <= 0) return 0;
 	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
 	              2.0 * M->nnz * k);
 	if (k == 1)       return launch_spmm<1, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
@@ -371,5 +425,6 @@ extern "C" int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv
 		const bool overlap = start[0] < end[1] && start[1] < end[0];
 		B200_CHECK(!overlap, "b200_mat_dot_multivec: x and y column ranges overlap on one multi-vector");
 	}
+	if (b200k_spmm_check_halo(A, x)) return 1;
 	return b200k_spmm(A, trans, x->d + start[0], x->ld, y->d + start[1], y->ld, k, nullptr);
 }

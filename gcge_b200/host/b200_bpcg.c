@@ -78,6 +78,8 @@ int b200_block_pcg(const b200_mat *A, const b200_mat *B, const b200_mv *b, b200_
 	const long long n = x->nrows;
 	if (A->nrows != n || A->ncols != n || b->nrows != n || ws_r->nrows != n || ws_p->nrows != n || ws_w->nrows != n)
 		return b200_fail("b200_block_pcg: shape mismatch");
+	if (b200k_spmm_check_halo(A, x) || b200k_spmm_check_halo(A, ws_p)) return 1;
+	if (B && prm->shift != 0.0 && (b200k_spmm_check_halo(B, x) || b200k_spmm_check_halo(B, ws_p))) return 1;
 	if (niter) *niter = 0;
 	if (residual) *residual = 0.0;
 	int wk = ws_r->ncols;

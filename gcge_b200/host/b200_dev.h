@@ -14,6 +14,12 @@
 extern "C" {
 #endif
 
+/* Multi-GPU (b200_comm.cu): every rank owns the row block [row0, row0 + nrows) of a matrix
+ * with nrows_global rows.  nrows / ncols / nnz below are LOCAL; column indices of the local
+ * CSR are remapped: a column owned by this rank becomes (column - row0), any other column
+ * becomes nrows + (its position in the sorted halo list).  SpMM therefore reads x rows
+ * [0, nrows) (local) and [nrows, nrows + nhalo) (halo), which every multi-vector keeps right
+ * behind its local rows.  Single GPU: row0 = 0, nhalo = 0, local == global. */
 struct b200_mat_ {
 	int nrows, ncols, nnz;
 	/* CSR of A: row r holds entries rp[r]..rp[r+1] in ascending column order -- the order
@@ -25,12 +31,34 @@ struct b200_mat_ {
 	int t_shared;
 	int row0;
 	int max_row_nnz, t_max_row_nnz;   /* longest row of the CSR image / of the transpose image */
+	int nrows_global, ncols_global, nnz_global;
+	int symmetric;                    /* CSR image == CCS image (A == A^T bit for bit) */
+	/* halo exchange plan (nranks > 1) */
+	int nhalo;                        /* halo rows of x this matrix needs */
+	int nnbr;                         /* ranks exchanged with, ascending */
+	int *nbr;                         /* [nnbr] */
+	int *halo_cols;                   /* host, [nhalo] global column of each halo slot, ascending */
+	int *recv_off;                    /* host, [nnbr+1] halo slots received from nbr[i]: [recv_off[i], recv_off[i+1]) */
+	int *send_off;                    /* host, [nnbr+1] */
+	int *send_rows;                   /* host, [send_off[nnbr]] LOCAL row sent to nbr[i], ascending per neighbour */
+	int *send_rows_dev;               /* device copy */
+	long long t_col0;                 /* first CCS column kept in the t_ arrays (== row0) */
 };
 
+/* host-side partition plan, usable without a device (tests): fills a zeroed b200_mat with
+ * the LOCAL CSR (host arrays rp_h/ci_h/va_h malloc'ed, to be freed by the caller), the halo
+ * and send lists.  rank/nranks explicit. */
+int b200_partition_build(int nrows, int ncols, const int *j_col, const int *i_row, const double *data,
+                         int rank, int nranks, struct b200_mat_ *A, int **rp_h, int **ci_h, double **va_h);
+
 struct b200_mv_ {
-	int nrows, ncols, ld;
+	int nrows, ncols, ld;       /* nrows: LOCAL rows */
 	double *d;
 	int owner;          /* 0: view into another multi-vector's storage */
+	int nrows_global;
+	int halo_cap;       /* rows allocated behind the local ones for SpMM halos */
+	int dist;           /* rows are a slab of a distributed object (Gram blocks need an allreduce) */
+	long long row0;
 };
 
 int  b200_fail(const char *fmt, ...);
@@ -51,13 +79,20 @@ int b200k_free(void *dev);
  * gate_dev != NULL: the kernel returns at once when *gate_dev == 0 (device-side loop control) */
 int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
                const int *gate_dev);
+/* Several ranks: the x block must belong to a multi-vector with room for M's halo rows behind its
+ * local rows (b200_mv.halo_cap >= M->nhalo); b200k_spmm fills them from the slab neighbours
+ * before multiplying.  Callers check with this helper. */
+int b200k_spmm_check_halo(const b200_mat *M, const b200_mv *x);
 /* y = alpha x + beta y over n x k; x may be NULL (scale); beta == 0 overwrites. */
 int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx,
                 double beta, double *y, int ldy);
 /* C(p x q, device, element (i,j) at c[i*c_rs + j*c_cs]) = alpha X^T Y over n rows;
  * mode 'N', 'S' (lower triangle mirrored) or 'D' (dots: c[i*(c_rs+c_cs)]... see .cu). */
+/* dist != 0: the n rows are this rank's slab of a distributed block; the result is summed over
+ * all ranks (NCCL allreduce on the library stream) and identical on every rank. */
 int b200k_gram(char mode, long long n, int p, int q, double alpha, const double *x, int ldx,
-               const double *y, int ldy, double *c_dev, int c_rs, int c_cs);
+               const double *y, int ldy, double *c_dev, int c_rs, int c_cs, int dist);
+int b200k_multi(void);          /* number of ranks (1 = single GPU) */
 /* Y(n x q) = X(n x p) C + Y diag(beta); C device, element (k,j) at c[k*c_rs + j*c_cs];
  * beta_dev NULL => 0 (overwrite) else beta_dev[incb*col]; x or c NULL => scaling only. */
 int b200k_lincomb(long long n, int p, int q, const double *x, int ldx,
@@ -87,6 +122,7 @@ typedef struct b200_bpcg_state_ {
 	double *norm_b, *rho1, *rho2, *ptw, *init_res, *last_res;   /* k doubles each (device) */
 	int *active;        /* k ints (device): 1 while the column is unconverged */
 	int *counters;      /* [0] number of active columns, [1] iterations done (device) */
+	double *totals;     /* 2k doubles: per-column sums of the current reduction (allreduced across ranks) */
 	double *partials;   /* reduction scratch */
 	unsigned *tickets;  /* last-block election counters */
 } b200_bpcg_state;

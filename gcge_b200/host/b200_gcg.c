@@ -71,7 +71,7 @@ static int rayleigh_ritz(gcg_t *g, int nevConv)
 		/* P^T (old projected matrix) P, reference :936-949 */
 		const int Nold = g->sizeV - g->sizeC, c0 = g->sizeX - g->sizeC;
 		TRY(b200k_lincomb(Nold, Nold, g->sizeP, g->matA_d, ldE, g->evec_d + c0, ldE, 1, NULL, 0, g->t1_d, g->bsp));
-		TRY(b200k_gram('N', Nold, g->sizeP, g->sizeP, 1.0, g->evec_d + c0, ldE, g->t1_d, g->bsp, g->ptap_d, bs, 1));
+		TRY(b200k_gram('N', Nold, g->sizeP, g->sizeP, 1.0, g->evec_d + c0, ldE, g->t1_d, g->bsp, g->ptap_d, bs, 1, 0));
 	}
 	g->sizeV  = g->sizeX + g->sizeP + g->sizeW;
 	g->startN = g->startN + (nevConv - g->sizeC);
@@ -86,7 +86,7 @@ static int rayleigh_ritz(gcg_t *g, int nevConv)
 		const int c0 = g->sizeX + g->sizeP - g->sizeC;
 		TRY(spmm_mv(g->A, g->V->d + g->startW, g->V->ld, g->ws[0]->d, g->ws[0]->ld, g->n, g->sizeW));
 		TRY(b200k_gram('N', g->n, N, g->sizeW, 1.0, g->V->d + g->startN, g->V->ld, g->ws[0]->d, g->ws[0]->ld,
-		               g->matA_d + c0, ldE, 1));
+		               g->matA_d + c0, ldE, 1, 1));
 	}
 	if (g->sizeX == g->sizeV) {
 		/* first call: full X^T A X by block_size-wide panels, reference :989-1011 */
@@ -95,7 +95,7 @@ static int rayleigh_ritz(gcg_t *g, int nevConv)
 			const int w = bs < length ? bs : length;
 			TRY(spmm_mv(g->A, g->V->d + c, g->V->ld, g->ws[0]->d, g->ws[0]->ld, g->n, w));
 			TRY(b200k_gram('N', g->n, g->sizeX - g->sizeC, w, 1.0, g->V->d + g->sizeC, g->V->ld,
-			               g->ws[0]->d, g->ws[0]->ld, g->matA_d + (c - g->sizeC), ldE, 1));
+			               g->ws[0]->d, g->ws[0]->ld, g->matA_d + (c - g->sizeC), ldE, 1, 1));
 			c += w; length -= w;
 		}
 	} else {
@@ -210,8 +210,10 @@ static int compute_p(gcg_t *g, const int *offset)
 	/* orthonormalise them against the X coefficient columns and themselves (B = I) in
 	 * coefficient space, reference :371-414 */
 	b200_mv E, W;
-	E.nrows = N; E.ncols = c0 + np; E.ld = ldE; E.d = g->evec_d; E.owner = 0;
-	W.nrows = N; W.ncols = g->bsp; W.ld = g->bsp; W.d = g->wsE_d; W.owner = 0;
+	/* replicated coefficient-space objects: not distributed, no allreduce in their Gram blocks */
+	memset(&E, 0, sizeof(E)); memset(&W, 0, sizeof(W));
+	E.nrows = N; E.nrows_global = N; E.ncols = c0 + np; E.ld = ldE; E.d = g->evec_d; E.owner = 0;
+	W.nrows = N; W.nrows_global = N; W.ncols = g->bsp; W.ld = g->bsp; W.d = g->wsE_d; W.owner = 0;
 	b200_orth_params op;
 	op.block_size = p->compP_orth_block_size; op.max_reorth = p->compP_orth_max_reorth;
 	op.orth_zero_tol = p->compP_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
@@ -411,9 +413,12 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
 			if (!g.ws[i] || g.ws[i]->ncols < bs || g.ws[i]->nrows != A->nrows) return b200_fail("b200_gcg_solve: mv_ws[%d] needs %d columns", i + 1, bs);
 	} else {
 		g.own_ws = 1;
-		if (b200_mv_create(A->nrows, sizeVmax, &g.V)) return 1;
-		for (int i = 0; i < 3; ++i) if (b200_mv_create(A->nrows, bs, &g.ws[i])) goto done;
+		if (b200_mv_create(A->nrows_global, sizeVmax, &g.V)) return 1;
+		for (int i = 0; i < 3; ++i) if (b200_mv_create(A->nrows_global, bs, &g.ws[i])) goto done;
 	}
+	if (b200k_spmm_check_halo(A, g.V) || b200k_spmm_check_halo(A, evec) || b200k_spmm_check_halo(A, g.ws[1]) ||
+	    (B && (b200k_spmm_check_halo(B, g.V) || b200k_spmm_check_halo(B, evec) || b200k_spmm_check_halo(B, g.ws[1]))))
+		goto done;
 	g.Nmax = prm->nevInit + 2 * bs; if (g.Nmax < sizeVmax) g.Nmax = sizeVmax;
 	g.ldE = (g.Nmax + 3) & ~3;
 	g.bsp = (bs + 3) & ~3;

@@ -27,14 +27,14 @@
 
 static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *B, double *ws, int ldws,
                       double zero_tol, double *g_dev, double *t_dev, int *nlive_dev, int *n_live,
-                      const double *scale_in, double *scale_out)
+                      const double *scale_in, double *scale_out, int dist)
 {
 	const double *y = x1; int ldy = ldx;
 	if (B) {
 		if (b200k_spmm(B, 0, x1, ldx, ws, ldws, kb, NULL)) return 1;
 		y = ws; ldy = ldws;
 	}
-	if (b200k_gram('S', n, kb, kb, 1.0, x1, ldx, y, ldy, g_dev, kb, 1)) return 1;
+	if (b200k_gram('S', n, kb, kb, 1.0, x1, ldx, y, ldy, g_dev, kb, 1, dist)) return 1;
 	if (b200k_chol_drop(kb, g_dev, zero_tol, t_dev, nlive_dev, scale_in, scale_out)) return 1;
 	/* X1 <- X1 T through the workspace (T: element (i,j) at t[i*kb+j]) */
 	if (b200k_lincomb(n, kb, kb, x1, ldx, t_dev, kb, 1, NULL, 0, ws, ldws)) return 1;
@@ -51,6 +51,7 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 	if (start_x < 0 || *end_x > x->ncols) return b200_fail("b200_mv_orth: range [%d,%d) outside %d columns", start_x, *end_x, x->ncols);
 	if (ws->nrows != x->nrows) return b200_fail("b200_mv_orth: workspace row count differs");
 	if (B && (B->nrows != x->nrows || B->ncols != x->nrows)) return b200_fail("b200_mv_orth: B is not n x n");
+	if (B && b200k_spmm_check_halo(B, x)) return 1;
 	const long long n = x->nrows;
 	int end = *end_x;
 	int init_start = start_x;
@@ -87,12 +88,12 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 					y = ws->d; ldy = ws->ld;
 				}
 				/* C = -(X0^T B X1), row-major s1 x kb; X1 += X0 C */
-				if (b200k_gram('N', n, s1, kb, -1.0, x->d, x->ld, y, ldy, c_dev, kb, 1)) return 1;
+				if (b200k_gram('N', n, s1, kb, -1.0, x->d, x->ld, y, ldy, c_dev, kb, 1, x->dist)) return 1;
 				if (b200k_lincomb(n, s1, kb, x->d, x->ld, c_dev, kb, 1, one_dev, 0, x1, x->ld)) return 1;
 			}
 			int n_live = kb;
 			if (orth_panel(n, x1, x->ld, kb, B, ws->d, ws->ld, prm->orth_zero_tol, g_dev, t_dev, nlive_dev, &n_live,
-			               round == 0 ? NULL : sc0_dev, round == 0 ? sc0_dev : sc1_dev))
+			               round == 0 ? NULL : sc0_dev, round == 0 ? sc0_dev : sc1_dev, x->dist))
 				return 1;
 			e1 = s1 + n_live;
 		}

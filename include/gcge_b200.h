@@ -62,6 +62,38 @@ int  b200_prof_enable(int on);
 int  b200_prof_classes(void);
 int  b200_prof_get(int cls, const char **name, double *ms, long long *calls, double *bytes, double *flops);
 
+/* ---- several GPUs: one process per GPU, 1-D contiguous row blocks -----------
+ * The scheme of the reference's MPI back ends (every rank owns a row slab of A, B and of
+ * every multi-vector; reference app/app_slepc.c:610-634, app/app_phg.c:292-357,
+ * src/ops_multi_vec.c:214): rank g owns rows [floor(g n/G), floor((g+1) n/G)).  After
+ * b200_comm_init every call below keeps its GLOBAL meaning -- matrices are created from the
+ * global CCS arrays, multi-vectors are created / uploaded / downloaded with global shapes, Gram
+ * blocks and dots come back globally reduced and identical on every rank -- while each process
+ * stores and computes its slab only.  SpMM halo rows travel by ncclSend/ncclRecv over NVLink,
+ * reductions by ncclAllReduce; the small projected problem is replicated.  All ranks must make
+ * the same calls in the same order (they do: the host control flow is replicated, exactly like
+ * the reference under MPI).  Bootstrap: rank 0 obtains the 128-byte id, the host program ships
+ * it to the other ranks (bench.py: torch.distributed), every rank calls b200_comm_init. */
+int  b200_comm_unique_id(char *id128);
+int  b200_comm_init(int rank, int nranks, const char *id128);
+int  b200_comm_finalize(void);
+int  b200_comm_rank(void);
+int  b200_comm_size(void);
+void b200_partition_range(long long n, int rank, int nranks, long long *lo, long long *hi);
+/* host-only: lay out as rank `rank` of `nranks` without a communicator (partition tests) */
+int  b200_comm_set_layout(int rank, int nranks);
+/* host-only view of one rank's partition plan: local CSR slab with remapped columns (local
+ * column = global - row0; halo column = nrows_local + slot), the sorted halo list, the neighbour
+ * ranks and, per neighbour, the halo slots received from it and the local rows sent to it */
+typedef struct b200_plan_ b200_plan;
+int  b200_plan_create(int nrows, int ncols, const int *j_col, const int *i_row, const double *data,
+                      int rank, int nranks, b200_plan **out);
+int  b200_plan_sizes(const b200_plan *p, int *row0, int *nrows_local, int *nnz_local, int *nhalo, int *nnbr,
+                     int *nsend, int *symmetric);
+int  b200_plan_copy(const b200_plan *p, int *rp, int *ci, double *va, int *halo_cols, int *nbr,
+                    int *recv_off, int *send_off, int *send_rows);
+int  b200_plan_destroy(b200_plan *p);
+
 /* ---- matrix: replaces the host CCSMAT the reference's drivers build directly
  *      (reference test/test_app_ccs.c:99-102, :142-184) ------------------------ */
 int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, const int *i_row,
@@ -70,6 +102,11 @@ int b200_mat_destroy(b200_mat *A);
 int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nnz);
 /* gather the device matrix back to CCS arrays; bit-exact round trip */
 int b200_mat_to_ccs(const b200_mat *A, int *j_col, int *i_row, double *data);
+/* several ranks: this rank's row block and its CSR slab read back from the device with GLOBAL
+ * column indices; the slabs of all ranks, concatenated in rank order, are the CSR image of the
+ * whole matrix (== the CCS arrays of its transpose) bit for bit */
+int b200_mat_local_range(const b200_mat *A, int *row0, int *nrows_local, int *nnz_local, int *nhalo);
+int b200_mat_local_csr(const b200_mat *A, int *rp, int *ci, double *va);
 /* Y = alpha X + beta Y on identical sparsity patterns; slot MatAxpby, reference src/ops.h:52 */
 int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200_mat *Y);
 
@@ -77,11 +114,13 @@ int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200_mat *Y);
  *      app/app_lapack.c:230-286 (create/destroy) ------------------------------ */
 int b200_mv_create(int nrows, int ncols, b200_mv **out);   /* zero-filled */
 int b200_mv_destroy(b200_mv *x);
-int b200_mv_shape(const b200_mv *x, int *nrows, int *ncols);
+int b200_mv_shape(const b200_mv *x, int *nrows, int *ncols);   /* global shape */
+int b200_mv_local_range(const b200_mv *x, int *row0, int *nrows_local);
 /* non-owning view of columns [start,end); destroy with b200_mv_destroy.  Replaces
  * GetVecFromMultiVec / RestoreVecForMultiVec, reference app/app_lapack.c:262-286 */
 int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view);
-/* host column-major (ld >= nrows) <-> device columns [start,end) */
+/* host column-major (ld >= nrows, GLOBAL shape) <-> device columns [start,end); on several ranks
+ * each process moves its own rows [row0, row0 + nrows_local) of the host block only */
 int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld);
 int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld);
 /* x[row,col] = rand()/(RAND_MAX+1.0), column-major fill order, consuming the process's

@@ -1,0 +1,129 @@
+"""Multi-GPU parity worker (one process per GPU, launched by torchrun from
+tests/test_dist_gpu.py or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/dist_worker_gpu.py
+Every rank builds the SAME global inputs, the library keeps its row block; results are compared
+with the oracle (plain-C SpMM, numpy, the reference's golden eigenvalues)."""
+import ctypes as C
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from gcge_b200 import api, problems as P          # noqa: E402
+from oracle import gcg_numpy as G                  # noqa: E402
+from test_partition import oracle_spmm             # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+api.init(local)
+rank, world = api.comm_init_from_torch()
+L = api.lib()
+
+
+def gather_rows(mv, k0, k1, n):
+    """global (n x k) block from every rank's slab"""
+    full = np.zeros((n, k1 - k0), order="F")
+    api._chk(L.b200_mv_download(mv.h, k0, k1, full.ctypes.data_as(api.c_dbl_p), n))   # fills own rows only
+    t = torch.from_numpy(np.ascontiguousarray(full)).cuda()
+    dist.all_reduce(t)                                                                 # other rows are zero
+    return t.cpu().numpy()
+
+
+def check(cond, msg):
+    if not cond:
+        raise AssertionError(f"rank {rank}: {msg}")
+
+
+# ---- partition round trip from the device --------------------------------------------------
+pen = P.p1_fem_kuhn(9)
+n = pen.A.ncols
+A, B = api.Mat(pen.A), api.Mat(pen.B)
+row0, nloc, nnzl, nhalo = (C.c_int(), C.c_int(), C.c_int(), C.c_int())
+L.b200_mat_local_range.argtypes = [C.c_void_p] + [api.c_int_p] * 4
+api._chk(L.b200_mat_local_range(A.h, C.byref(row0), C.byref(nloc), C.byref(nnzl), C.byref(nhalo)))
+rp = np.zeros(nloc.value + 1, np.int32); ci = np.zeros(max(nnzl.value, 1), np.int32); va = np.zeros(max(nnzl.value, 1))
+L.b200_mat_local_csr.argtypes = [C.c_void_p, api.c_int_p, api.c_int_p, api.c_dbl_p]
+api._chk(L.b200_mat_local_csr(A.h, api._ip(rp), api._ip(ci), api._dp(va)))
+csr = pen.A.to_scipy().tocsr(); csr.sort_indices()
+lo, hi = row0.value, row0.value + nloc.value
+check(lo == (n * rank) // world and hi == (n * (rank + 1)) // world, "row range")
+check(np.array_equal(rp, csr.indptr[lo:hi + 1] - csr.indptr[lo]), "local row pointers")
+check(np.array_equal(ci[:nnzl.value], csr.indices[csr.indptr[lo]:csr.indptr[hi]]), "local columns (global ids)")
+check(np.array_equal(va[:nnzl.value], csr.data[csr.indptr[lo]:csr.indptr[hi]]), "local values")
+
+# ---- SpMM with halo exchange: bit-exact against the oracle -----------------------------------
+for k in (1, 6, 10, 40, 70):
+    x = np.asfortranarray(np.random.default_rng(k).standard_normal((n, k + 2)))
+    X = api.MultiVec.from_numpy(x); Y = api.MultiVec(n, k)
+    api.mat_dot_multivec(A, X, Y, (1, 0), (1 + k, k))
+    got = gather_rows(Y, 0, k, n)
+    want = oracle_spmm(pen.A, np.asfortranarray(x[:, 1:1 + k]))
+    check(np.array_equal(got, want), f"SpMM k={k} differs from the oracle")
+
+# ---- Gram / dots: globally reduced, identical on every rank -----------------------------------
+x = np.asfortranarray(np.random.default_rng(1).standard_normal((n, 24)))
+y = np.asfortranarray(np.random.default_rng(2).standard_normal((n, 10)))
+X = api.MultiVec.from_numpy(x); Y = api.MultiVec.from_numpy(y)
+g = np.zeros((24, 10), order="F")
+api.multivec_inner_prod("N", X, Y, (0, 0), (24, 10), g, 24)
+check(np.abs(g - x.T @ y).max() < 1e-11 * np.abs(x.T @ y).max(), "Gram block")
+t = torch.from_numpy(np.ascontiguousarray(g)).cuda(); t2 = t.clone(); dist.broadcast(t2, 0)
+check(bool(torch.equal(t, t2)), "Gram block is not bit-identical across ranks")
+d = np.zeros(10)
+api.multivec_inner_prod("D", X, Y, (3, 0), (13, 10), d, 1)
+check(np.abs(d - np.einsum("ij,ij->j", x[:, 3:13], y)).max() < 1e-11 * n, "column dots")
+q = np.zeros((10, 10), order="F"); ws = api.MultiVec(n, 10)
+api.multivec_qtap("S", "N", Y, B, Y, (0, 0), (10, 10), q, 10, ws)
+Bd = pen.B.to_scipy()
+check(np.abs(q - y.T @ (Bd @ y)).max() < 1e-11 * np.abs(q).max(), "QtAP")
+
+# ---- RNG: every rank keeps its rows of the one global glibc stream --------------------------------
+R = api.MultiVec(n, 5)
+api.libc_srand(0); R.set_random(1, 4)
+want = np.zeros((n, 5), order="F"); G.srand(0); G.fill_random(want, 1, 4)
+check(np.array_equal(gather_rows(R, 0, 5, n), want), "set_random differs from the glibc stream")
+
+# ---- fused providers ------------------------------------------------------------------------------
+xs = np.asfortranarray(np.random.default_rng(5).random((n, 12)))
+V = api.MultiVec.from_numpy(xs)
+end = api.orth(V, 0, 12, B=B, block_size=8)
+v = gather_rows(V, 0, 12, n)
+check(end == 12 and np.abs(v.T @ (Bd @ v) - np.eye(12)).max() < 1e-12, "B-orthonormalisation")
+Ad = pen.A.to_scipy()
+sol = np.asfortranarray(np.random.default_rng(6).random((n, 4))); rhs = np.asfortranarray(Ad @ sol)
+Xs = api.MultiVec(n, 4)
+api.block_pcg(A, api.MultiVec.from_numpy(rhs), Xs, (0, 0), (4, 4), max_iter=600, rate=1e-30, tol=1e-10)
+check(np.abs(Ad @ gather_rows(Xs, 0, 4, n) - rhs).max() < 1e-8, "BlockPCG residual")
+
+# ---- whole solve against the reference's golden output ------------------------------------------------
+gold = json.loads((ROOT / "tests" / "golden" / "gcg_reference.json").read_text())["cases"]
+for idx in (4, 2):
+    case = gold[idx]
+    pc = getattr(P, case["generator"])(**case["args"])
+    Am = api.Mat(pc.A); Bm = None if pc.B is None else api.Mat(pc.B)
+    o = api.gcg_solve(Am, Bm, nev=case["nev"])
+    k = min(o["nev_conv"], case["nev_conv"])
+    err = np.max(np.abs(o["eval"][:k] - np.array(case["eval"][:k])) / np.abs(np.array(case["eval"][:k])))
+    check(o["nev_conv"] >= case["nev"], "not converged")
+    check(err < 1e-10, f"eigenvalues differ from the reference: {err:.2e}")
+    check(abs(o["num_iter"] - case["num_iter"]) <= 2, f"iterations {o['num_iter']} vs reference {case['num_iter']}")
+    vec = gather_rows(o["evec_mv"], 0, k, pc.A.ncols)
+    Ax = pc.A.to_scipy() @ vec; Bx = vec if pc.B is None else pc.B.to_scipy() @ vec
+    res = np.linalg.norm(Ax - Bx * o["eval"][:k], axis=0)
+    check(np.all(res <= 1e-1) and np.all(res <= np.abs(o["eval"][:k]) * 1e-8 * 1.0000001), "residual test")
+    ev = torch.from_numpy(o["eval"].copy()).cuda(); ev0 = ev.clone(); dist.broadcast(ev0, 0)
+    check(bool(torch.equal(ev, ev0)), "eigenvalues are not bit-identical across ranks")
+
+dist.barrier()
+if rank == 0:
+    print(f"dist gpu ok: world={world} launches={api.kernel_launches()}")
+api.comm_finalize()
+dist.destroy_process_group()
