@@ -19,8 +19,9 @@ cpu_baseline / --impl reference
          and tolerances on a smaller lattice, solved to convergence), scaled linearly in n and
          in the outer-iteration count to the full workload -- see `sample` in the JSON line.
 
-Multi-GPU (torchrun, one rank per GPU): the row-block partition is not built yet; each rank
-solves the whole pencil on its own GPU ("replicas", weak scaling = N solves in the same time).
+Multi-GPU (torchrun, one rank per GPU): the SAME pencil is split into 1-D row blocks over the N
+GPUs (strong scaling): halo rows of SpMM by ncclSend/ncclRecv, Gram blocks / dots / CG scalars by
+ncclAllReduce, projected problem replicated.  value = seconds per solve, max over ranks.
 """
 from __future__ import annotations
 
@@ -158,7 +159,7 @@ def run_reference(a) -> int:
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": "gcg_solve_seconds", "value": value, "unit": "s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, 1),
             "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "reference", "sample": last},
             "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -172,7 +173,7 @@ def workload_config(a, n_gpus: int) -> dict:
                         f"{a.m ** 3}, nev = {a.nev} (nevMax {2 * a.nev}, block_size {a.nev // 5 if a.nev >= 30 else a.nev}), "
                         f"B-orthogonal GCG with BlockPCG, tol = (1e-1, 1e-8), srand(0)",
             "generator": "gcge_b200.problems.p1_fem_kuhn", "m": a.m, "nev": a.nev,
-            "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (row-block partition not built yet)",
+            "parallelism": "single GPU" if n_gpus == 1 else f"1-D row blocks over {n_gpus} GPUs (NCCL halo exchange + allreduce, replicated Rayleigh-Ritz)",
             "l2": "inputs >> L2 (matrices 2.9 GB, multi-vectors 64 GB at m=200); no flush needed"}
 
 
@@ -187,6 +188,8 @@ def run_b200(a) -> int:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gcge_b200 import api, problems as P
     api.init(local)
+    if world > 1:
+        api.comm_init_from_torch()
 
     t0 = time.time()
     pen = P.p1_fem_kuhn(a.m)
@@ -238,7 +241,8 @@ def run_b200(a) -> int:
     # ---- e2e: host CCS arrays -> upload -> solve -> eigenpairs back on the host ------------
     A.close(); B.close()
     nev_out = a.nev
-    host_vec = np.zeros((n, nev_out), order="F")
+    _, nloc = evec.local_range()
+    host_vec = np.zeros((nloc, nev_out), order="F")          # this rank's rows of the eigenvectors
     api.host_register(host_vec)
     e2e_s = []
     for i in range(a.e2e_steps):
@@ -246,7 +250,7 @@ def run_b200(a) -> int:
         w0 = time.time()
         A2, B2 = api.Mat(pen.A), api.Mat(pen.B)
         o2 = solve(A2, B2)
-        api.lib().b200_mv_download(evec.h, 0, nev_out, host_vec.ctypes.data_as(api.c_dbl_p), n)
+        evec.numpy_local(0, nev_out, out=host_vec)
         ev_host = o2["eval"][:nev_out].copy()
         barrier()
         e2e_s.append(time.time() - w0)
@@ -257,9 +261,10 @@ def run_b200(a) -> int:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = float(t.item())
     h2d = sum(h.nbytes for h in host_arrays)
-    d2h = host_vec.nbytes + 8 * prm.nevMax
+    d2h = 8 * n * nev_out + 8 * prm.nevMax            # all ranks together
 
     if rank != 0:
+        api.comm_finalize()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -325,7 +330,7 @@ def run_b200(a) -> int:
 
     line = {"metric": "gcg_solve_seconds", "value": sec, "unit": "s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, world),
             "result": {"num_iter": int(out["num_iter"]), "nev_conv": int(out["nev_conv"]),
                        "eval_first": float(out["eval"][0]), "eval_nev": float(out["eval"][a.nev - 1]),
@@ -340,6 +345,7 @@ def run_b200(a) -> int:
             "clocks": clocks,
             "setup_s": {"generate_pencil": round(t_gen, 2)}}
     print(json.dumps(line))
+    api.comm_finalize()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -79,6 +79,9 @@ def lib():
         L.b200_mat_dot_multivec.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p]
         L.b200_mv_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int]
         L.b200_mv_download.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int]
+        L.b200_mv_upload_local.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int]
+        L.b200_mv_download_local.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int]
+        L.b200_mv_local_range.argtypes = [C.c_void_p, c_int_p, c_int_p]
         L.b200_mv_set_random.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b200_mv_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.b200_mv_destroy.argtypes = [C.c_void_p]
@@ -178,14 +181,15 @@ def partition_plan(ccs, rank: int, nranks: int) -> dict:
     data = np.ascontiguousarray(ccs.data, dtype=np.float64)
     h = C.c_void_p()
     L.b200_plan_create.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    L.b200_plan_sizes.argtypes = [C.c_void_p] + [c_int_p] * 7
+    L.b200_plan_sizes.argtypes = [C.c_void_p] + [c_int_p] * 9
     L.b200_plan_copy.argtypes = [C.c_void_p, c_int_p, c_int_p, c_dbl_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]
     L.b200_plan_destroy.argtypes = [C.c_void_p]
     _chk(L.b200_plan_create(ccs.nrows, ccs.ncols, _ip(j_col), _ip(i_row), _dp(data), rank, nranks, C.byref(h)))
-    v = [C.c_int(0) for _ in range(7)]
+    v = [C.c_int(0) for _ in range(9)]
     _chk(L.b200_plan_sizes(h, *[C.byref(x) for x in v]))
-    row0, nloc, nnz, nhalo, nnbr, nsend, sym = [x.value for x in v]
+    row0, nloc, nnz, nhalo, nnbr, nsend, sym, contig, hbelow = [x.value for x in v]
     out = {"row0": row0, "nloc": nloc, "nnz": nnz, "nhalo": nhalo, "symmetric": bool(sym),
+           "halo_contiguous": bool(contig), "halo_below": hbelow,
            "rp": np.zeros(nloc + 1, np.int32), "ci": np.zeros(max(nnz, 1), np.int32), "va": np.zeros(max(nnz, 1)),
            "halo_cols": np.zeros(max(nhalo, 1), np.int32), "nbr": np.zeros(max(nnbr, 1), np.int32),
            "recv_off": np.zeros(nnbr + 1, np.int32), "send_off": np.zeros(nnbr + 1, np.int32),
@@ -292,6 +296,21 @@ class MultiVec:
         out = np.zeros((self.nrows, end - start), order="F")
         if out.size:
             _chk(lib().b200_mv_download(self.h, start, end, _dp(out), max(self.nrows, 1)))
+        return out
+
+    def local_range(self):
+        """(row0, nrows_local): this rank's row block (the whole vector on one GPU)."""
+        r0, nl = C.c_int(0), C.c_int(0)
+        _chk(lib().b200_mv_local_range(self.h, C.byref(r0), C.byref(nl)))
+        return r0.value, nl.value
+
+    def numpy_local(self, start: int = 0, end: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        end = self.ncols if end is None else end
+        _, nl = self.local_range()
+        if out is None:
+            out = np.zeros((nl, end - start), order="F")
+        if out.size:
+            _chk(lib().b200_mv_download_local(self.h, start, end, _dp(out), max(nl, 1)))
         return out
 
     def set_random(self, start: int, end: int):

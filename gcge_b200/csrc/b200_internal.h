@@ -73,6 +73,9 @@ static inline bool b200_multi() { return g_b200.nranks > 1; }
 			                 cudaGetErrorString(e_));                              \
 	} while (0)
 
+// rows the diagonal image of a matrix is padded to a multiple of (largest SpMM row block)
+constexpr int B200_DIA_PAD = 256;
+
 static inline int b200_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 

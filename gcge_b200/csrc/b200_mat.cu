@@ -73,26 +73,63 @@ extern "C" int b200_partition_build(int nrows, int ncols, const int *j_col, cons
 	}
 	A->symmetric = sym;
 	if (nranks > 1) {
-		// halo list: off-slab columns, ascending, unique
-		std::vector<unsigned char> mark((size_t)ncols, 0);
-		for (int e = 0; e < nnz_loc; ++e) if (ci[e] < lo || ci[e] >= hi) mark[ci[e]] = 1;
+		// Column extent of every rank's slab: [cmin_q, cmax_q] over the entries of its rows.  One
+		// pass over the whole CCS (every rank holds it here), identical on all ranks.
+		std::vector<long long> cmin((size_t)nranks), cmax((size_t)nranks), rlo((size_t)nranks), rhi((size_t)nranks);
+		for (int q = 0; q < nranks; ++q) { b200_partition_range(nrows, q, nranks, &rlo[q], &rhi[q]); cmin[q] = rlo[q]; cmax[q] = rhi[q] - 1; }
+		{
+			int q = 0;
+			for (int j = 0; j < ncols; ++j)
+				for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
+					const int r = i_row[e];
+					if (r < rlo[q] || r >= rhi[q]) q = owner_of(r, nrows, nranks);
+					if (j < cmin[q]) cmin[q] = j;
+					if (j > cmax[q]) cmax[q] = j;
+				}
+		}
+		// Banded matrices (stencils, FEM on lattices): take the halo as the two CONTIGUOUS column
+		// ranges [cmin, lo) and [hi, cmax] -- at most a few unreferenced rows travel, and the x block
+		// a slab multiplies with is then piecewise contiguous, which the diagonal-storage SpMM needs.
+		// The rule is global (every rank must pick the same mode): contiguous iff no rank's two
+		// ranges together exceed its own slab.
+		bool contiguous = true;
+		for (int q = 0; q < nranks; ++q)
+			if ((rlo[q] - cmin[q]) + (cmax[q] + 1 - rhi[q]) > (rhi[q] - rlo[q])) contiguous = false;
+		A->halo_contiguous = contiguous ? 1 : 0;
+		A->halo_below = contiguous ? (int)(lo - cmin[rank]) : 0;
 		std::vector<int> halo;
-		for (int c = 0; c < ncols; ++c) if (mark[c]) halo.push_back(c);
+		std::vector<std::vector<int>> send((size_t)nranks);
+		if (contiguous) {
+			for (long long c = cmin[rank]; c < lo; ++c) halo.push_back((int)c);
+			for (long long c = hi; c <= cmax[rank]; ++c) halo.push_back((int)c);
+			for (int q = 0; q < nranks; ++q) {
+				if (q == rank) continue;
+				// my rows inside q's two ranges, ascending
+				long long a0 = std::max(cmin[q], lo), a1 = std::min(rlo[q], hi);
+				for (long long c = a0; c < a1; ++c) send[q].push_back((int)(c - lo));
+				a0 = std::max(rhi[q], lo); a1 = std::min(cmax[q] + 1, hi);
+				for (long long c = a0; c < a1; ++c) send[q].push_back((int)(c - lo));
+			}
+		} else {
+			// exact list: off-slab columns, ascending, unique
+			std::vector<unsigned char> mark((size_t)ncols, 0);
+			for (int e = 0; e < nnz_loc; ++e) if (ci[e] < lo || ci[e] >= hi) mark[ci[e]] = 1;
+			for (int c = 0; c < ncols; ++c) if (mark[c]) halo.push_back(c);
+			// what the other ranks need from me: my columns j with an entry in a row they own
+			for (long long j = lo; j < hi; ++j)
+				for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
+					const int r = i_row[e];
+					if (r >= lo && r < hi) continue;
+					const int q = owner_of(r, nrows, nranks);
+					if (send[q].empty() || send[q].back() != (int)(j - lo)) send[q].push_back((int)(j - lo));
+				}
+		}
 		A->nhalo = (int)halo.size();
 		for (int e = 0; e < nnz_loc; ++e) {
 			const int c = ci[e];
-			if (c >= lo && c < hi) ci[e] = c - (int)lo;
+			if (contiguous || (c >= lo && c < hi)) ci[e] = c - (int)lo;      // may be negative / >= nloc: halo rows
 			else ci[e] = nloc + (int)(std::lower_bound(halo.begin(), halo.end(), c) - halo.begin());
 		}
-		// what the other ranks need from me: my columns j with an entry in a row they own
-		std::vector<std::vector<int>> send((size_t)nranks);
-		for (long long j = lo; j < hi; ++j)
-			for (int e = j_col[j]; e < j_col[j + 1]; ++e) {
-				const int r = i_row[e];
-				if (r >= lo && r < hi) continue;
-				const int q = owner_of(r, nrows, nranks);
-				if (send[q].empty() || send[q].back() != (int)(j - lo)) send[q].push_back((int)(j - lo));
-			}
 		std::vector<int> recv_cnt((size_t)nranks, 0);
 		for (int c : halo) ++recv_cnt[owner_of(c, nrows, nranks)];
 		std::vector<int> nbr;
@@ -131,7 +168,7 @@ extern "C" int b200_plan_create(int nrows, int ncols, const int *j_col, const in
 }
 
 extern "C" int b200_plan_sizes(const b200_plan *p, int *row0, int *nrows_local, int *nnz_local, int *nhalo, int *nnbr,
-                               int *nsend, int *symmetric)
+                               int *nsend, int *symmetric, int *halo_contiguous, int *halo_below)
 {
 	B200_CHECK(p, "b200_plan_sizes: NULL plan");
 	if (row0) *row0 = p->m.row0;
@@ -140,6 +177,8 @@ extern "C" int b200_plan_sizes(const b200_plan *p, int *row0, int *nrows_local, 
 	if (nhalo) *nhalo = p->m.nhalo;
 	if (nnbr) *nnbr = p->m.nnbr;
 	if (nsend) *nsend = p->m.nnbr ? p->m.send_off[p->m.nnbr] : 0;
+	if (halo_contiguous) *halo_contiguous = p->m.halo_contiguous;
+	if (halo_below) *halo_below = p->m.halo_below;
 	if (symmetric) *symmetric = p->m.symmetric;
 	return 0;
 }
@@ -168,6 +207,75 @@ extern "C" int b200_plan_destroy(b200_plan *p)
 	free(p->rp); free(p->ci); free(p->va);
 	free(p->m.nbr); free(p->m.halo_cols); free(p->m.recv_off); free(p->m.send_off); free(p->m.send_rows);
 	free(p);
+	return 0;
+}
+
+// ---- diagonal image -----------------------------------------------------------------------------
+// A lattice operator in natural ordering has its entries on a handful of diagonals
+// (col - row in a fixed set: 7 / 15 / 27 offsets for the 7-point, P1-Kuhn and 27-point
+// operators).  Storing it by diagonals drops the column indices (8 nd + 4 bytes per row instead
+// of 12 per entry) and, more importantly, lets the SpMM kernel slide along consecutive rows:
+// rows r and r+1 share the x rows of adjacent offsets, so a thread that walks a block of rows
+// loads every x row once instead of once per matrix row that touches it (b200_spmm.cu).
+// rp/ci/va: the local CSR slab with REMAPPED columns (see b200_partition_build).
+static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va, int nranks)
+{
+	const int nloc = A->nrows;
+	A->dia_nd = 0;
+	if (nloc <= 0 || A->nnz <= 0 || getenv("B200_NO_DIA")) return 0;
+	if (nranks > 1 && !A->halo_contiguous) return 0;
+	const long long lo = A->row0;
+	auto gcol = [&](int c) -> long long {
+		return (A->halo_contiguous || c < nloc) ? lo + c : (long long)A->halo_cols[c - nloc];
+	};
+	// distinct offsets (give up beyond 32)
+	std::vector<long long> offs;
+	for (int r = 0; r < nloc; ++r)
+		for (int e = rp[r]; e < rp[r + 1]; ++e) {
+			const long long d = gcol(ci[e]) - (lo + r);
+			auto it = std::lower_bound(offs.begin(), offs.end(), d);
+			if (it == offs.end() || *it != d) {
+				if (offs.size() >= 32) return 0;
+				offs.insert(it, d);
+			}
+		}
+	const int nd = (int)offs.size();
+	if ((double)A->nnz < 0.5 * (double)nd * nloc) return 0;      // too sparse on its diagonals
+	for (long long d : offs) if (d > 0x3fffffff || d < -0x3fffffff) return 0;
+	// runs of consecutive offsets, at most 3 wide; every run starts on an even slot of the image
+	// (one padding slot after a run of odd width) so its values are one aligned 128-bit load
+	int ng = 0, ndp = 0;
+	std::vector<int> slot_of((size_t)nd);
+	for (int s0 = 0; s0 < nd;) {
+		int w = 1;
+		while (w < 3 && s0 + w < nd && offs[s0 + w] == offs[s0] + w) ++w;
+		A->dia_grp_h[2 * ng] = ndp; A->dia_grp_h[2 * ng + 1] = w;
+		A->dia_off_h[ng] = (int)offs[s0];                          // first offset of the run
+		for (int j = 0; j < w; ++j) slot_of[s0 + j] = ndp + j;
+		ndp += (w + 1) & ~1; ++ng; s0 += w;
+	}
+	// padded to whole row blocks of the SpMM kernel (zero values), so its bulk copies of a block's
+	// image are always full size and in bounds
+	const size_t npad = (((size_t)nloc + B200_DIA_PAD - 1) / B200_DIA_PAD) * B200_DIA_PAD;
+	std::vector<double> val(npad * ndp, 0.0);
+	std::vector<unsigned> mask((size_t)nloc, 0u);
+	for (int r = 0; r < nloc; ++r)
+		for (int e = rp[r]; e < rp[r + 1]; ++e) {
+			const long long d = gcol(ci[e]) - (lo + r);
+			const int s = (int)(std::lower_bound(offs.begin(), offs.end(), d) - offs.begin());
+			if (mask[r] & (1u << s)) return 0;                    // duplicate entry: keep the CSR semantics
+			val[(size_t)r * ndp + slot_of[s]] = va[e]; mask[r] |= 1u << s;
+		}
+	cudaStream_t st = g_b200.stream;
+	B200_CUDA(cudaMalloc(&A->dia_off, sizeof(int) * 32));
+	B200_CUDA(cudaMalloc(&A->dia_grp, sizeof(int) * 64));
+	B200_CUDA(cudaMalloc(&A->dia_val, sizeof(double) * npad * ndp));
+	B200_CUDA(cudaMemcpyAsync(A->dia_off, A->dia_off_h, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->dia_grp, A->dia_grp_h, sizeof(int) * 2 * ng, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->dia_val, val.data(), sizeof(double) * npad * ndp, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaStreamSynchronize(st));       // val is a local
+	A->dia_ndp = ndp;
+	A->dia_nd = nd; A->dia_ng = ng;
 	return 0;
 }
 
@@ -222,7 +330,9 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 		note_halo_capacity(A->ncols_global, A->nhalo);
 	}
 	B200_CUDA(cudaStreamSynchronize(st));
+	const int rc_dia = dia_build(A, rp, ci, va, nranks);
 	free(rp); free(ci); free(va);
+	if (rc_dia) { b200_mat_destroy(A); return 1; }
 	*out = A;
 	return 0;
 }
@@ -234,6 +344,9 @@ extern "C" int b200_mat_destroy(b200_mat *A)
 	if (!A->t_shared && A->t_rp) { cudaFree(A->t_rp); cudaFree(A->t_ci); cudaFree(A->t_va); }
 	cudaFree(A->rp); cudaFree(A->ci); cudaFree(A->va);
 	if (A->send_rows_dev) cudaFree(A->send_rows_dev);
+	if (A->dia_off) cudaFree(A->dia_off);
+	if (A->dia_grp) cudaFree(A->dia_grp);
+	if (A->dia_val) cudaFree(A->dia_val);
 	free(A->nbr); free(A->halo_cols); free(A->recv_off); free(A->send_off); free(A->send_rows);
 	free(A);
 	return 0;
@@ -273,7 +386,8 @@ extern "C" int b200_mat_local_csr(const b200_mat *A, int *rp, int *ci, double *v
 	}
 	B200_CUDA(cudaStreamSynchronize(st));
 	if (A->nhalo || A->row0)
-		for (int e = 0; e < A->nnz; ++e) ci[e] = ci[e] < A->nrows ? ci[e] + A->row0 : A->halo_cols[ci[e] - A->nrows];
+		for (int e = 0; e < A->nnz; ++e)
+			ci[e] = (A->halo_contiguous || ci[e] < A->nrows) ? ci[e] + A->row0 : A->halo_cols[ci[e] - A->nrows];
 	return 0;
 }
 
@@ -316,6 +430,14 @@ extern "C" int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200
 	                                                                      : g_b200.num_sms * 8;
 	mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->va, beta, Y->va);
 	B200_KERNEL_CHECK();
+	if (Y->dia_nd) {
+		// identical patterns => identical diagonal structure; the slots absent from the pattern stay 0
+		B200_CHECK(X->dia_nd == Y->dia_nd, "b200_mat_axpby: diagonal images differ");
+		const long long cnt = (long long)Y->nrows * Y->dia_ndp;
+		B200_CHECK(cnt < 0x7fffffffLL, "b200_mat_axpby: diagonal image too large");
+		mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>((int)cnt, alpha, X->dia_val, beta, Y->dia_val);
+		B200_KERNEL_CHECK();
+	}
 	if (!Y->t_shared && Y->t_va) {
 		B200_CHECK(X->t_va, "b200_mat_axpby: internal");
 		mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->t_va, beta, Y->t_va);

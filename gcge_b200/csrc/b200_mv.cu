@@ -29,13 +29,14 @@ extern "C" int b200_mv_create(int nrows, int ncols, b200_mv **out)
 	x->nrows_global = nrows; x->row0 = lo; x->halo_cap = halo;
 	nrows = (int)(hi - lo);
 	x->nrows = nrows; x->ncols = ncols; x->ld = mv_ld_for(ncols); x->owner = 1;
-	size_t bytes = sizeof(double) * (size_t)(nrows + halo > 0 ? nrows + halo : 1) * (size_t)x->ld;
-	cudaError_t e = cudaMalloc(&x->d, bytes);
+	size_t bytes = sizeof(double) * (size_t)(nrows + 2 * halo > 0 ? nrows + 2 * halo : 1) * (size_t)x->ld;
+	cudaError_t e = cudaMalloc(&x->alloc, bytes);
 	if (e != cudaSuccess) {
 		free(x);
 		return b200_fail("b200_mv_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
 	}
-	B200_CUDA(cudaMemsetAsync(x->d, 0, bytes, g_b200.stream));
+	x->d = x->alloc + (size_t)halo * x->ld;
+	B200_CUDA(cudaMemsetAsync(x->alloc, 0, bytes, g_b200.stream));
 	*out = x;
 	return 0;
 }
@@ -45,7 +46,7 @@ extern "C" int b200_mv_destroy(b200_mv *x)
 	if (!x) return 0;
 	if (x->owner) {
 		if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
-		cudaFree(x->d);
+		cudaFree(x->alloc);
 	}
 	free(x);
 	return 0;
@@ -56,7 +57,7 @@ extern "C" int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view
 	B200_CHECK(x && view && start >= 0 && start <= end && end <= x->ncols, "b200_mv_view: bad arguments");
 	b200_mv *v = (b200_mv *)calloc(1, sizeof(b200_mv));
 	*v = *x;
-	v->ncols = end - start; v->d = x->d + start; v->owner = 0;
+	v->ncols = end - start; v->d = x->d + start; v->owner = 0; v->alloc = nullptr;
 	*view = v;
 	return 0;
 }
@@ -135,13 +136,29 @@ int b200k_rm_to_cm(long long n, int k, const double *rm, int ld_rm, double *cm, 
 // host column-major <-> device, staged through scratch[2] in column chunks
 static const size_t kStageBytes = (size_t)256 << 20;
 
+static int mv_upload_rows(b200_mv *x, int start, int end, const double *host, int ld);
+static int mv_download_rows(const b200_mv *x, int start, int end, double *host, int ld);
+
 extern "C" int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld)
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows_global,
 	           "b200_mv_upload: bad arguments");
 	// host is the GLOBAL column-major block; this rank takes its rows [row0, row0 + nrows)
-	host += x->row0;
+	return mv_upload_rows(x, start, end, host + x->row0, ld);
+}
+
+// host holds this rank's rows only (nrows_local x (end-start), column-major, ld >= nrows_local)
+extern "C" int b200_mv_upload_local(b200_mv *x, int start, int end, const double *host, int ld)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	           "b200_mv_upload_local: bad arguments");
+	return mv_upload_rows(x, start, end, host, ld);
+}
+
+static int mv_upload_rows(b200_mv *x, int start, int end, const double *host, int ld)
+{
 	const long long n = x->nrows;
 	if (n == 0 || end == start) return 0;
 	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));
@@ -166,7 +183,19 @@ extern "C" int b200_mv_download(const b200_mv *x, int start, int end, double *ho
 	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows_global,
 	           "b200_mv_download: bad arguments");
 	// host is the GLOBAL column-major block; this rank fills its rows [row0, row0 + nrows) only
-	host += x->row0;
+	return mv_download_rows(x, start, end, host + x->row0, ld);
+}
+
+extern "C" int b200_mv_download_local(const b200_mv *x, int start, int end, double *host, int ld)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(x && host && start >= 0 && end <= x->ncols && start <= end && ld >= x->nrows,
+	           "b200_mv_download_local: bad arguments");
+	return mv_download_rows(x, start, end, host, ld);
+}
+
+static int mv_download_rows(const b200_mv *x, int start, int end, double *host, int ld)
+{
 	const long long n = x->nrows;
 	if (n == 0 || end == start) return 0;
 	int chunk = (int)(kStageBytes / (sizeof(double) * (size_t)n));

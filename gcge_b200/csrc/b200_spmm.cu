@@ -11,6 +11,7 @@
 // ascending column order -- the same operation sequence as the reference's serial scatter,
 // so the result is bit-identical to the reference on every input.
 #include "b200_internal.h"
+#include <cuda.h>      // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 
 // Matrix entries are fetched cooperatively: the G lanes of a row group load G consecutive
 // (value, column) pairs with one coalesced request each and hand them round with shuffles,
@@ -311,6 +312,249 @@ static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va
 	return 0;
 }
 
+// ============================================================================= diagonal SpMM
+// For matrices with a diagonal image (b200_mat.cu: dia_build) -- stencils and FEM operators on
+// lattices.  The CSR kernels above are bound by the L1 path: every (row, entry) pair is a
+// 3-line gather and L1 retires about one line per two cycles (profiles/ncu_r1c_spmm: l1tex 85 %,
+// DRAM 22 %).  Here the x rows a block of matrix rows needs never go through L1 at all:
+//
+//   * Offsets come in runs of consecutive values ({-1,0,1}, {m, m+1}, ...).  For a CTA that owns
+//     the rows [R, R + ROWS) and a run starting at offset d, the x rows needed are the CONTIGUOUS
+//     range [R + d, R + d + ROWS + 2): one 2-D box of the row-major multi-vector.  One elected
+//     thread issues one TMA tile copy (cp.async.bulk.tensor.2d) per run -- all runs up front,
+//     ~75 KB in flight per CTA, no registers, no LSU wavefronts -- each signalling its own
+//     mbarrier.  Rows outside the matrix (Dirichlet rows at the ends; halo limits) are
+//     zero-filled by the TMA unit and never used (presence mask).
+//   * A row group of G lanes (lane = one column pair) owns RB consecutive matrix rows with their
+//     2 RB accumulators in registers, and slides along the box: x row t of a run feeds matrix
+//     rows t - j, j < run width, so each x row is read from shared memory once per run instead
+//     of once per matrix row that touches it.
+//   * The diagonal values of the CTA's rows are one contiguous range of the image: a coalesced
+//     sweep into shared memory, then broadcast reads.
+//
+// Arithmetic is unchanged: per matrix row the runs, and the offsets inside a run, are visited in
+// ascending order = ascending column order, separate multiply and add, entries absent from the
+// CCS input are skipped by the presence mask (not multiplied by a stored zero) -- bit-identical
+// to the reference's scatter loop (app/app_ccs.c:116-131).
+constexpr int DIA_WMAX = 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// One run of width W on the RB rows of a row group: x rows t = 0 .. RB + W - 2 of the run's box are
+// read once (128-bit) and x row t feeds matrix rows t - j, j < W.  The run's values of a matrix
+// row sit 16-byte aligned in the image (runs are padded to an even number of slots), so they
+// come as one 128-bit broadcast load (+ one 64-bit load for W == 3).
+template <int RB, int W>
+__device__ __forceinline__ void dia_run(double (&acc)[RB][2], const double *tile, int k, const double *vrow, int ndp)
+{
+	double2 xv[RB + W - 1];
+#pragma unroll
+	for (int t = 0; t < RB + W - 1; ++t) xv[t] = *reinterpret_cast<const double2 *>(tile + (size_t)t * k);
+#pragma unroll
+	for (int i = 0; i < RB; ++i) {
+		const double2 a01 = *reinterpret_cast<const double2 *>(vrow + i * ndp);
+		acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a01.x, xv[i].x));
+		acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a01.x, xv[i].y));
+		if (W >= 2) {
+			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)].x));
+			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)].y));
+		}
+		if (W >= 3) {
+			const double a2 = vrow[i * ndp + 2];
+			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].x));
+			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].y));
+		}
+	}
+}
+
+// tmx: 2-D tensor map of the x block: dim0 = the k columns, dim1 = the hb + nloc + ha rows of the
+// window (halo rows in front of and behind the local rows), box = (k, ROWS + 2).
+// Persistent CTAs walk the flattened sequence of (row block, run) items through a ring of NS
+// shared-memory tiles: while the warps consume the x box of one run, the TMA unit fills the
+// tiles of the next NS-1 items (one mbarrier per tile).  The diagonal values of a row block come
+// by one 1-D bulk copy into a double buffer.  Accumulators stay in registers across the runs of
+// a block.  Entries absent from the CCS input are stored as +0.0 in the image: 0.0 * x adds a
+// signed zero, which never changes an accumulator (it starts at +0.0 and can never become
+// -0.0), so the result is bit-identical to the reference for every finite x.
+template <int G, int RB, int NS>
+__global__ void __launch_bounds__(256)
+spmm_dia_tma_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblocks, int nd, const int *__restrict__ off,
+                    const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes,
+                    double *y, int ldy, int k, const int *__restrict__ gate)
+{
+	if (gate != nullptr && *gate == 0) return;
+	constexpr int CPW = 32 / G;                      // row chunks per warp
+	constexpr int ROWS = 8 * CPW * RB;               // rows per block
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// [NS x-tiles of tile_bytes][2 value buffers of ROWS x nd doubles]
+	__shared__ unsigned long long bars[NS], vbars[2];
+	__shared__ int grp_s[64];
+	__shared__ int d0_s[32];
+	if (threadIdx.x < 2 * ng) grp_s[threadIdx.x] = __ldg(grp + threadIdx.x);
+	if (threadIdx.x < ng) d0_s[threadIdx.x] = __ldg(off + threadIdx.x);      // first offset of each run
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+		mbar_init(vbars, 1); mbar_init(vbars + 1, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	const unsigned x_bytes = (unsigned)((ROWS + DIA_WMAX - 1) * k * 8);
+	const unsigned val_bytes = (unsigned)(ROWS * nd * 8);
+	unsigned char *vbuf = smem_raw + (size_t)NS * tile_bytes;
+	const int my_blocks = (nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+	const int items = my_blocks * ng;
+	auto issue_x = [&](int item) {                   // one thread
+		const int blk = blockIdx.x + (item / ng) * gridDim.x, g = item % ng, slot = item % NS;
+		mbar_expect_tx(bars + slot, x_bytes);
+		tma_load_2d(smem_raw + (size_t)slot * tile_bytes, &tmx, 0, blk * ROWS + d0_s[g] + hb, bars + slot);
+	};
+	auto issue_val = [&](int lb) {                    // one thread; lb = local block counter
+		const int blk = blockIdx.x + lb * gridDim.x;
+		mbar_expect_tx(vbars + (lb & 1), val_bytes);
+		// the image is padded to whole blocks (b200_mat.cu): full-size copies are always in bounds
+		bulk_load_1d(vbuf + (size_t)(lb & 1) * val_bytes, val + (size_t)blk * ROWS * nd, val_bytes, vbars + (lb & 1));
+	};
+	if (threadIdx.x == 0) {
+		if (my_blocks > 0) issue_val(0);
+		for (int i = 0; i < NS - 1 && i < items; ++i) issue_x(i);
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int gl = lane % G, chunk = warp * CPW + lane / G;
+	int c = 2 * gl;
+	const bool in_cols = c < k;
+	if (c > k - 2) c = k - 2;
+	const int lr0 = chunk * RB;                      // first row of this group inside the block
+	double acc[RB][2];
+	int item = 0;
+	for (int lb = 0; lb < my_blocks; ++lb) {
+		if (threadIdx.x == 0 && lb + 1 < my_blocks) issue_val(lb + 1);   // its buffer was released with block lb-1
+		mbar_wait(vbars + (lb & 1), (unsigned)((lb >> 1) & 1));
+		const double *vrow = reinterpret_cast<const double *>(vbuf + (size_t)(lb & 1) * val_bytes) + (size_t)lr0 * nd;
+#pragma unroll
+		for (int i = 0; i < RB; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+		for (int g = 0; g < ng; ++g, ++item) {
+			// refill the tile released by the barrier at the end of the previous item
+			if (threadIdx.x == 0 && item + NS - 1 < items) issue_x(item + NS - 1);
+			const int slot = item % NS;
+			mbar_wait(bars + slot, (unsigned)((item / NS) & 1));
+			const int sp = grp_s[2 * g], w = grp_s[2 * g + 1];     // padded first slot, width
+			const double *tile = reinterpret_cast<const double *>(smem_raw + (size_t)slot * tile_bytes) + (size_t)lr0 * k + c;
+			if (w == 2)      dia_run<RB, 2>(acc, tile, k, vrow + sp, nd);
+			else if (w == 3) dia_run<RB, 3>(acc, tile, k, vrow + sp, nd);
+			else             dia_run<RB, 1>(acc, tile, k, vrow + sp, nd);
+			__syncthreads();                         // every warp is done with this tile
+		}
+		if (in_cols) {
+			const long long r0 = ((long long)blockIdx.x + (long long)lb * gridDim.x) * ROWS + lr0;
+#pragma unroll
+			for (int i = 0; i < RB; ++i)
+				if (r0 + i < nrows)
+					*reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c) = make_double2(acc[i][0], acc[i][1]);
+		}
+	}
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tmap_encode_fn tmap_encoder()
+{
+	static tmap_encode_fn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+		    q == cudaDriverEntryPointSuccess)
+			fn = (tmap_encode_fn)p;
+		else
+			cudaGetLastError();
+	}
+	return fn;
+}
+
+// returns 0 launched, 1 error, 2 not applicable (caller falls back to the CSR kernels)
+template <int G, int RB, int NS>
+static int launch_spmm_dia(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	constexpr int ROWS = 8 * (32 / G) * RB;
+	static_assert(ROWS <= B200_DIA_PAD && B200_DIA_PAD % ROWS == 0, "diagonal image padding does not fit the row block");
+	const int ng = M->dia_ng, nd = M->dia_ndp;               // slots per row incl. the run padding
+	const int tile_bytes = (((ROWS + DIA_WMAX - 1) * k * 8) + 127) & ~127;
+	const size_t smem = (size_t)NS * tile_bytes + 2 * (size_t)ROWS * nd * 8;
+	if (smem > 200 * 1024) return 2;
+	tmap_encode_fn enc = tmap_encoder();
+	if (!enc) return 2;
+	const int hb = M->halo_below, span = M->nrows + M->nhalo;
+	const double *base = x - (size_t)hb * ldx;               // first row of the window
+	CUtensorMap tm;
+	const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)span};
+	const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 8};
+	const cuuint32_t box[2] = {(cuuint32_t)k, (cuuint32_t)(ROWS + DIA_WMAX - 1)};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+	                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return 2;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(spmm_dia_tma_kernel<G, RB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		attr_set = true;
+	}
+	const int nblocks = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
+	int per_sm = (int)((224 * 1024) / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
+	int grid = g_b200.num_sms * per_sm; if (grid > nblocks) grid = nblocks;
+	spmm_dia_tma_kernel<G, RB, NS><<<grid, 256, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off, M->dia_val, ng,
+		M->dia_grp, hb, tile_bytes, y, ldy, k, gate);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// diagonal image, at most 64 columns
+static int spmm_dia_dispatch(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
+	if (!vec) return 2;
+	// row-block heights and ring depths measured on B200 (profiles/spmm_sweep_r1_dia_tma.log)
+	if (k <= 16) return launch_spmm_dia<8, 4, 4>(M, x, ldx, y, ldy, k, gate);
+	if (k <= 32) return launch_spmm_dia<16, 4, 4>(M, x, ldx, y, ldy, k, gate);
+	return launch_spmm_dia<32, 8, 4>(M, x, ldx, y, ldy, k, gate);
+}
+
 // sendbuf[i, 0:k] = x[rows[i], 0:k]
 __global__ void halo_pack_kernel(int nsend, int k, const int *__restrict__ rows, const double *__restrict__ x, int ldx,
                                  double *__restrict__ buf)
@@ -353,27 +597,24 @@ static int halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 		ro[i] = (size_t)M->recv_off[i] * k; rc[i] = (size_t)(M->recv_off[i + 1] - M->recv_off[i]) * k;
 	}
 	if (b200k_neighbor_exchange(M->nnbr, M->nbr, sbuf, so, sc, rbuf, ro, rc)) return 1;
+	if (nrecv > 0 && M->halo_contiguous) {
+		// the receive buffer is ordered like the halo list: the rows below the slab, then above
+		const int hb = M->halo_below, ha = nrecv - hb;
+		if (hb > 0 && b200k_axpby(hb, k, 1.0, rbuf, k, 0.0, x - (size_t)hb * ldx, ldx)) return 1;
+		if (ha > 0 && b200k_axpby(ha, k, 1.0, rbuf + (size_t)hb * k, k, 0.0, x + (size_t)M->nrows * ldx, ldx)) return 1;
+		return 0;
+	}
 	if (nrecv > 0) return b200k_axpby(nrecv, k, 1.0, rbuf, k, 0.0, x + (size_t)M->nrows * ldx, ldx);
 	return 0;
 }
 
-int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
-               const int *gate)
+// local multiply with the CSR kernels (any matrix, any alignment)
+static int spmm_csr_local(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
+                          const int *gate)
 {
-	if (trans && !M->t_rp) {
-		// row-partitioned matrix: only the forward image is kept; A^T x == A x when A is symmetric
-		// (the reference assumes that for every matrix, app/app_ccs.c:140-150)
-		B200_CHECK(M->symmetric, "transposed SpMM of a non-symmetric matrix is not available across ranks");
-		trans = 0;
-	}
 	const int nrows = trans ? M->ncols : M->nrows;
 	const int *rp = trans ? M->t_rp : M->rp, *ci = trans ? M->t_ci : M->ci;
 	const double *va = trans ? M->t_va : M->va;
-	if (k <= 0) return 0;
-	if (b200_multi() && halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
-	if (nrows <= 0) return 0;
-	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
-	              2.0 * M->nnz * k);
 	if (k == 1)       return launch_spmm<1, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k == 2)  return launch_spmm<2, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
 	else if (k <= 4)  return launch_spmm<4, 1>(nrows, rp, ci, va, x, ldx, y, ldy, k, gate);
@@ -400,6 +641,37 @@ int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y
 		if (rc) return rc;
 	}
 	return 0;
+}
+
+int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
+               const int *gate)
+{
+	if (trans && !M->t_rp) {
+		// row-partitioned matrix: only the forward image is kept; A^T x == A x when A is symmetric
+		// (the reference assumes that for every matrix, app/app_ccs.c:140-150)
+		B200_CHECK(M->symmetric, "transposed SpMM of a non-symmetric matrix is not available across ranks");
+		trans = 0;
+	}
+	const int nrows = trans ? M->ncols : M->nrows;
+	if (k <= 0) return 0;
+	if (b200_multi() && halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
+	if (nrows <= 0) return 0;
+	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
+	              2.0 * M->nnz * k);
+	if (!trans && M->dia_nd > 0 && k > 4) {
+		// diagonal image, 64 columns per pass; whatever it cannot take (misaligned block, a tail of
+		// at most 4 columns) goes to the CSR kernels
+		int c0 = 0;
+		for (; c0 < k; c0 += 64) {
+			const int kc = k - c0 < 64 ? k - c0 : 64;
+			const int rc = (kc > 4) ? spmm_dia_dispatch(M, x + c0, ldx, y + c0, ldy, kc, gate) : 2;
+			if (rc == 1) return 1;
+			if (rc == 2) break;
+		}
+		if (c0 >= k) return 0;
+		return spmm_csr_local(M, 0, x + c0, ldx, y + c0, ldy, k - c0, gate);
+	}
+	return spmm_csr_local(M, trans, x, ldx, y, ldy, k, gate);
 }
 
 extern "C" int b200_mat_dot_multivec(const b200_mat *A, int trans, const b200_mv *x, b200_mv *y,

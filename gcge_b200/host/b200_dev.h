@@ -16,10 +16,12 @@ extern "C" {
 
 /* Multi-GPU (b200_comm.cu): every rank owns the row block [row0, row0 + nrows) of a matrix
  * with nrows_global rows.  nrows / ncols / nnz below are LOCAL; column indices of the local
- * CSR are remapped: a column owned by this rank becomes (column - row0), any other column
- * becomes nrows + (its position in the sorted halo list).  SpMM therefore reads x rows
- * [0, nrows) (local) and [nrows, nrows + nhalo) (halo), which every multi-vector keeps right
- * behind its local rows.  Single GPU: row0 = 0, nhalo = 0, local == global. */
+ * CSR are remapped.  Banded matrices (halo_contiguous): column c becomes c - row0, so the halo
+ * is the two row ranges [-halo_below, 0) and [nrows, nrows + nhalo - halo_below) around the
+ * local rows -- the x block is ONE contiguous window of the global vector.  Otherwise a column
+ * owned by this rank becomes (column - row0) and any other column nrows + (its position in the
+ * sorted halo list).  Every multi-vector keeps room for the halo rows in front of and behind its
+ * local rows.  Single GPU: row0 = 0, nhalo = 0, local == global. */
 struct b200_mat_ {
 	int nrows, ncols, nnz;
 	/* CSR of A: row r holds entries rp[r]..rp[r+1] in ascending column order -- the order
@@ -35,6 +37,8 @@ struct b200_mat_ {
 	int symmetric;                    /* CSR image == CCS image (A == A^T bit for bit) */
 	/* halo exchange plan (nranks > 1) */
 	int nhalo;                        /* halo rows of x this matrix needs */
+	int halo_contiguous;              /* halo = [row0 - halo_below, row0) U [row0 + nrows, ...): two contiguous column ranges */
+	int halo_below;
 	int nnbr;                         /* ranks exchanged with, ascending */
 	int *nbr;                         /* [nnbr] */
 	int *halo_cols;                   /* host, [nhalo] global column of each halo slot, ascending */
@@ -43,6 +47,18 @@ struct b200_mat_ {
 	int *send_rows;                   /* host, [send_off[nnbr]] LOCAL row sent to nbr[i], ascending per neighbour */
 	int *send_rows_dev;               /* device copy */
 	long long t_col0;                 /* first CCS column kept in the t_ arrays (== row0) */
+	/* Diagonal image (b200_mat.cu: dia_build), present when the matrix is a sum of at most 32
+	 * diagonals -- stencils and FEM operators on lattices in natural ordering.  The offsets are
+	 * grouped into runs of consecutive values (at most 3 wide); run g starts at the even slot
+	 * dia_grp_h[2g] of a row of the image, has width dia_grp_h[2g+1] and first offset dia_off_h[g];
+	 * entry (r, r + off_g + j) is dia_val[r*dia_ndp + start_g + j], +0.0 where the CCS input has no
+	 * such entry.  Rows are padded to a multiple of B200_DIA_PAD. */
+	int dia_nd;                       /* distinct offsets; 0: no image */
+	int dia_ndp;                      /* slots per row of the image (runs padded to even widths) */
+	int dia_ng;                       /* runs */
+	int dia_off_h[32], dia_grp_h[64];
+	int *dia_off, *dia_grp;           /* device copies */
+	double *dia_val;                  /* device [rows padded][dia_ndp] */
 };
 
 /* host-side partition plan, usable without a device (tests): fills a zeroed b200_mat with
@@ -56,7 +72,8 @@ struct b200_mv_ {
 	double *d;
 	int owner;          /* 0: view into another multi-vector's storage */
 	int nrows_global;
-	int halo_cap;       /* rows allocated behind the local ones for SpMM halos */
+	int halo_cap;       /* rows allocated in FRONT of and BEHIND the local ones for SpMM halos */
+	double *alloc;      /* start of the allocation (d = alloc + halo_cap*ld); NULL for views */
 	int dist;           /* rows are a slab of a distributed object (Gram blocks need an allreduce) */
 	long long row0;
 };

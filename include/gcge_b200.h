@@ -82,14 +82,16 @@ int  b200_comm_size(void);
 void b200_partition_range(long long n, int rank, int nranks, long long *lo, long long *hi);
 /* host-only: lay out as rank `rank` of `nranks` without a communicator (partition tests) */
 int  b200_comm_set_layout(int rank, int nranks);
-/* host-only view of one rank's partition plan: local CSR slab with remapped columns (local
- * column = global - row0; halo column = nrows_local + slot), the sorted halo list, the neighbour
+/* host-only view of one rank's partition plan: local CSR slab with remapped columns (banded
+ * matrices, halo_contiguous: column = global - row0, the halo being the halo_below rows in front
+ * of and the rest behind the local rows; otherwise local column = global - row0 and halo column
+ * = nrows_local + slot), the sorted halo list, the neighbour
  * ranks and, per neighbour, the halo slots received from it and the local rows sent to it */
 typedef struct b200_plan_ b200_plan;
 int  b200_plan_create(int nrows, int ncols, const int *j_col, const int *i_row, const double *data,
                       int rank, int nranks, b200_plan **out);
 int  b200_plan_sizes(const b200_plan *p, int *row0, int *nrows_local, int *nnz_local, int *nhalo, int *nnbr,
-                     int *nsend, int *symmetric);
+                     int *nsend, int *symmetric, int *halo_contiguous, int *halo_below);
 int  b200_plan_copy(const b200_plan *p, int *rp, int *ci, double *va, int *halo_cols, int *nbr,
                     int *recv_off, int *send_off, int *send_rows);
 int  b200_plan_destroy(b200_plan *p);
@@ -123,6 +125,9 @@ int b200_mv_view(const b200_mv *x, int start, int end, b200_mv **view);
  * each process moves its own rows [row0, row0 + nrows_local) of the host block only */
 int b200_mv_upload(b200_mv *x, int start, int end, const double *host, int ld);
 int b200_mv_download(const b200_mv *x, int start, int end, double *host, int ld);
+/* same, but `host` holds this rank's row block only (nrows_local rows, ld >= nrows_local) */
+int b200_mv_upload_local(b200_mv *x, int start, int end, const double *host, int ld);
+int b200_mv_download_local(const b200_mv *x, int start, int end, double *host, int ld);
 /* x[row,col] = rand()/(RAND_MAX+1.0), column-major fill order, consuming the process's
  * glibc rand() stream exactly like reference app/app_lapack.c:322-333.  The values are
  * generated ON DEVICE by jump-ahead of glibc's lagged-Fibonacci recurrence from the live

@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from gcge_b200 import api, problems as P          # noqa: E402
 sys.path.insert(0, str(ROOT / "tests"))
-from test_partition import local_spmm, oracle_spmm          # noqa: E402
+from test_partition import extended_x, local_spmm, oracle_spmm          # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -22,7 +22,7 @@ for M in (P.p1_fem_kuhn(6).A, P.laplace3d_7pt(7).A):
     p = api.partition_plan(M, rank, world)
     x = np.asfortranarray(np.random.default_rng(11).standard_normal((n, k)))      # same on both ranks
     xloc = x[p["row0"]:p["row0"] + p["nloc"]].copy()
-    xext = np.zeros((p["nloc"] + p["nhalo"], k)); xext[:p["nloc"]] = xloc
+    halo = np.zeros((p["nhalo"], k))
     reqs, recvs = [], []
     for i, q in enumerate(p["nbr"]):
         rows = p["send_rows"][p["send_off"][i]:p["send_off"][i + 1]]
@@ -32,9 +32,10 @@ for M in (P.p1_fem_kuhn(6).A, P.laplace3d_7pt(7).A):
         recvs.append((i, rbuf))
     for r in reqs:
         r.wait()
-    for i, rbuf in recvs:                                                          # unpack behind the local rows
-        xext[p["nloc"] + p["recv_off"][i]:p["nloc"] + p["recv_off"][i + 1]] = rbuf.numpy()
-    y = local_spmm(p, xext)
+    for i, rbuf in recvs:                                                          # unpack in halo-list order
+        halo[p["recv_off"][i]:p["recv_off"][i + 1]] = rbuf.numpy()
+    xext, shift = extended_x(p, xloc, halo)
+    y = local_spmm(p, xext, shift)
     # Gram block: local partial + allreduce (the NCCL path does the same on the device)
     gl = torch.from_numpy(xloc.T @ y); dist.all_reduce(gl)
     parts = [None] * world

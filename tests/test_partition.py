@@ -34,7 +34,24 @@ def oracle_spmm(M, x):
     return y
 
 
-def local_spmm(plan, xext):
+def global_cols(p):
+    """columns of the local CSR slab mapped back to global indices"""
+    if p["halo_contiguous"] or not p["nhalo"]:
+        return p["ci"] + p["row0"]
+    return np.where(p["ci"] < p["nloc"], p["ci"] + p["row0"], p["halo_cols"][np.maximum(p["ci"] - p["nloc"], 0)])
+
+
+def extended_x(p, xloc, halo_rows):
+    """the x block a slab multiplies with, laid out as the device lays it out, plus the index shift:
+    banded matrices keep the halo_below rows in FRONT of the local rows (one contiguous window
+    of the global vector), otherwise all halo rows follow the local rows in halo-list order."""
+    if p["halo_contiguous"]:
+        hb = p["halo_below"]
+        return np.vstack([halo_rows[:hb], xloc, halo_rows[hb:]]), hb
+    return np.vstack([xloc, halo_rows]), 0
+
+
+def local_spmm(plan, xext, shift=0):
     """Row-by-row gather in entry order with separate multiply and add -- the arithmetic of the
     device SpMM kernel (gcge_b200/csrc/b200_spmm.cu)."""
     y = np.zeros((plan["nloc"], xext.shape[1]))
@@ -42,7 +59,7 @@ def local_spmm(plan, xext):
     for r in range(plan["nloc"]):
         acc = np.zeros(xext.shape[1])
         for e in range(rp[r], rp[r + 1]):
-            acc = acc + va[e] * xext[ci[e]]
+            acc = acc + va[e] * xext[ci[e] + shift]
         y[r] = acc
     return y
 
@@ -65,9 +82,7 @@ def test_partition_plan_roundtrip_and_exchange_lists(name, make, nranks):
     csr = M.to_scipy().tocsr(); csr.sort_indices()
     rp_all, ci_all, va_all = [0], [], []
     for p in plans:
-        gcol = np.where(p["ci"] < p["nloc"], p["ci"] + p["row0"], p["halo_cols"][np.maximum(p["ci"] - p["nloc"], 0)]
-                        if p["nhalo"] else p["ci"] + p["row0"])
-        rp_all.extend((p["rp"][1:] + rp_all[-1]).tolist()); ci_all.append(gcol); va_all.append(p["va"])
+        rp_all.extend((p["rp"][1:] + rp_all[-1]).tolist()); ci_all.append(global_cols(p)); va_all.append(p["va"])
     assert np.array_equal(np.array(rp_all), csr.indptr)
     assert np.array_equal(np.concatenate(ci_all), csr.indices)
     assert np.array_equal(np.concatenate(va_all), csr.data)          # identical bits
@@ -85,9 +100,11 @@ def test_partition_plan_roundtrip_and_exchange_lists(name, make, nranks):
     x = np.asfortranarray(np.random.default_rng(7).standard_normal((n, 3)))
     want = oracle_spmm(M, x)
     for p in plans:
-        xext = np.vstack([x[p["row0"]:p["row0"] + p["nloc"]], x[p["halo_cols"]]]) if p["nhalo"] else x[p["row0"]:p["row0"] + p["nloc"]]
-        got = local_spmm(p, xext)
+        xext, shift = extended_x(p, x[p["row0"]:p["row0"] + p["nloc"]], x[p["halo_cols"]] if p["nhalo"] else x[:0])
+        got = local_spmm(p, xext, shift)
         assert np.array_equal(got, want[p["row0"]:p["row0"] + p["nloc"]])
+    # all ranks of one matrix use the same halo mode (the exchange would not match otherwise)
+    assert len({p["halo_contiguous"] for p in plans}) == 1
 
 
 def test_partition_rejects_rectangular_across_ranks():

@@ -130,6 +130,55 @@ def test_spmm_bitexact(b200, refmod, pencil, k):
     assert np.array_equal(Y.numpy()[:, :k], x[:, :k])
 
 
+def _random_unsymmetric(n=413, density=0.03, seed=5):
+    import scipy.sparse as sp
+    m = sp.random(n, n, density=density, random_state=np.random.default_rng(seed), format="csc") + 3.0 * sp.identity(n, format="csc")
+    m = m.tocsc(); m.sort_indices()
+    return P.CCS(n, n, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.astype(np.float64))
+
+
+@pytest.mark.parametrize("name", ["7pt", "27pt", "p1_mass", "1d", "unsym_random", "ragged_banded"])
+@pytest.mark.parametrize("k", [5, 6, 16, 22, 40, 64, 80, 130])
+def test_spmm_bitexact_both_storage_paths(b200, name, k):
+    """The diagonal-image kernel (lattice operators: 7/15/27 diagonals, Dirichlet rows with missing
+    neighbours) and the CSR kernels (irregular matrices) must both reproduce the reference's CCS
+    scatter bit for bit, at aligned and unaligned column offsets."""
+    from gcge_b200 import api
+    if name == "7pt":
+        M = P.laplace3d_7pt(11).A
+    elif name == "27pt":
+        M = P.q1_27pt(9).A
+    elif name == "p1_mass":
+        M = P.p1_fem_kuhn(10).B
+    elif name == "1d":
+        M = P.laplace1d_pencil(1001).A
+    elif name == "unsym_random":
+        M = _random_unsymmetric()
+    else:   # banded, but every third row lacks some of its diagonals and a few rows are empty
+        import scipy.sparse as sp
+        n = 700
+        rng = np.random.default_rng(2)
+        d = {o: rng.standard_normal(n - abs(o)) for o in (-30, -29, -1, 0, 1, 2, 29, 31)}
+        m = sp.diags(list(d.values()), list(d.keys()), shape=(n, n), format="lil")
+        m[3::3, :] = m[3::3, :].multiply(sp.random(1, n, density=0.5, random_state=rng, format="csr") != 0)
+        m[10, :] = 0; m[500, :] = 0
+        m = m.tocsc(); m.eliminate_zeros(); m.sort_indices()
+        M = P.CCS(n, n, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.astype(np.float64))
+    n = M.ncols
+    x = np.asfortranarray(np.random.default_rng(k).standard_normal((n, k + 3)))
+    A = b200.Mat(M)
+    X = b200.MultiVec.from_numpy(x)
+    for xo, yo in ((0, 0), (1, 2), (2, 1), (3, 4)):
+        if xo + k > k + 3:
+            continue
+        Y = b200.MultiVec(n, k + 5)
+        api.mat_dot_multivec(A, X, Y, (xo, yo), (xo + k, yo + k))
+        got = Y.numpy()
+        want = oracle_spmm(M, np.asfortranarray(x[:, xo:xo + k]))
+        assert np.array_equal(got[:, yo:yo + k], want), (name, k, xo, yo)
+        assert not got[:, :yo].any() and not got[:, yo + k:].any()
+
+
 def test_axpby_semantics(b200, refmod):
     """MultiVecAxpby (reference app/app_lapack.c:334-395; call shapes of
     reference test/test_multi_vec.c:103-116)."""
