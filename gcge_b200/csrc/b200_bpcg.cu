@@ -336,6 +336,47 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
 	return 0;
 }
 
+// p^T w from the per-CTA partials the fused SpMM left in st.partials[part][k]
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_ptw_parts_kernel(int nparts, int k, int defer, b200_bpcg_state st)
+{
+	if (st.counters[0] == 0) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int c = warp; c < k; c += ST_THREADS / 32) {
+		const double s = stream_total<1>(st.partials, nparts, k, 0, c);
+		if (lane == 0) st.totals[c] = s;
+	}
+	__syncthreads();
+	if (!defer) bpcg_scalar_phase(1, k, st, 0.0, 0, 0.0);
+}
+
+int b200k_spmm_dot(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate,
+                   double *dot_part, int dot_cap, int *nparts);
+
+// w = A p and ptw = diag(p^T w) in one pass over p (SpMM with the dot in its epilogue) when the
+// matrix has a diagonal image; otherwise the SpMM followed by the streaming dot kernel.
+extern "C" int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bpcg_state *st, const double *p, int ldp,
+                                   double *w, int ldw)
+{
+	const int k = st->k;
+	const int defer = b200_multi() ? 1 : 0;
+	const int cap = g_b200.num_sms * BPCG_CTAS_PER_SM;       // rows of k doubles available in st->partials (x2)
+	int nparts = 0;
+	const int rc = b200k_spmm_dot(A, p, ldp, w, ldw, k, st->counters, st->partials, cap, &nparts);
+	if (rc == 1) return 1;
+	if (rc == 2) {
+		if (b200k_spmm(A, 0, p, ldp, w, ldw, k, st->counters)) return 1;
+		return b200k_bpcg_ptw(n, st, p, ldp, w, ldw, 0.0, nullptr, 0);
+	}
+	{
+		B200Prof prof(B200_PROF_BPCG, 8.0 * nparts * k, 1.0 * nparts * k);
+		bpcg_ptw_parts_kernel<<<1, ST_THREADS, 0, g_b200.stream>>>(nparts, k, defer, *st);
+		B200_KERNEL_CHECK();
+	}
+	if (defer) return bpcg_finish(1, 1, st, 0.0, 0, 0.0);
+	return 0;
+}
+
 extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, const double *p, int ldp,
                                     const double *w, int ldw, double *x, int ldx, double *r, int ldr,
                                     double rate, double tol)

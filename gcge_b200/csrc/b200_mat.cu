@@ -254,9 +254,10 @@ static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va
 		for (int j = 0; j < w; ++j) slot_of[s0 + j] = ndp + j;
 		ndp += (w + 1) & ~1; ++ng; s0 += w;
 	}
-	// padded to whole row blocks of the SpMM kernel (zero values), so its bulk copies of a block's
-	// image are always full size and in bounds
-	const size_t npad = (((size_t)nloc + B200_DIA_PAD - 1) / B200_DIA_PAD) * B200_DIA_PAD;
+	// padded behind the last row by at least one row block of the SpMM kernels (zero values; their
+	// block heights need not divide the row count), so their bulk copies of a block's image are
+	// always full size and in bounds
+	const size_t npad = (((size_t)nloc + B200_DIA_PAD - 1) / B200_DIA_PAD) * B200_DIA_PAD + B200_DIA_PAD;
 	std::vector<double> val(npad * ndp, 0.0);
 	std::vector<unsigned> mask((size_t)nloc, 0u);
 	for (int r = 0; r < nloc; ++r)

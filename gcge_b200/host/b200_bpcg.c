@@ -4,7 +4,8 @@
  * CG iteration, one single-column MultiVecAxpby per column for p, one SpMM and one 'D'
  * inner product per contiguous index block, two more single-column axpbys per column, and
  * decides convergence on the host from scalars it pulled back.  Here one iteration is a
- * fixed sequence of four launches on the whole block (update_p, SpMM, ptw, update_xr);
+ * fixed sequence of launches on the whole block (update_p, SpMM with p^T w in its epilogue,
+ * update_xr; with a shift: update_p, SpMM, SpMM, ptw, update_xr);
  * rho/alpha/beta, the residual norms, the active-column masks and the iteration counter
  * stay in HBM, and every launch returns at once when no column is active any more, so the
  * host never reads anything back inside the loop.  Converged columns are frozen exactly as
@@ -38,18 +39,20 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	if (b200k_bpcg_begin(n, &st, b, ldb, r, ldr, prm->tol, prm->tol_type == 1)) return 1;
 	for (int it = 0; it < prm->max_iter; ++it) {
 		if (b200k_bpcg_update_p(n, &st, r, ldr, p, ldp, it == 0)) return 1;
+		if (shift == 0.0) {
+			/* w = A p with p^T w in the SpMM epilogue */
+			if (b200k_bpcg_spmm_ptw(A, n, &st, p, ldp, w, ldw)) return 1;
+			if (b200k_bpcg_update_xr(n, &st, p, ldp, w, ldw, x, ldx, r, ldr, prm->rate, prm->tol)) return 1;
+			continue;
+		}
 		if (b200k_spmm(A, 0, p, ldp, w, ldw, k, st.counters)) return 1;
-		if (shift != 0.0) {
-			if (B) {
-				/* the right-hand side is dead after the initial residual: use it as B p, like the
-				 * reference's MatDotMultiVecShift does (src/ops_eig_sol_gcg.c:63-96) */
-				if (b200k_spmm(B, 0, p, ldp, b, ldb, k, st.counters)) return 1;
-				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, b, ldb)) return 1;
-			} else {
-				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, p, ldp)) return 1;
-			}
+		if (B) {
+			/* the right-hand side is dead after the initial residual: use it as B p, like the
+			 * reference's MatDotMultiVecShift does (src/ops_eig_sol_gcg.c:63-96) */
+			if (b200k_spmm(B, 0, p, ldp, b, ldb, k, st.counters)) return 1;
+			if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, b, ldb)) return 1;
 		} else {
-			if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, 0.0, NULL, 0)) return 1;
+			if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, p, ldp)) return 1;
 		}
 		if (b200k_bpcg_update_xr(n, &st, p, ldp, w, ldw, x, ldx, r, ldr, prm->rate, prm->tol)) return 1;
 	}

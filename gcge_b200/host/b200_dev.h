@@ -154,6 +154,10 @@ int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const double *r,
 /* w += shift * z (optional), ptw = diag(p^T w) */
 int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const double *p, int ldp,
                    double *w, int ldw, double shift, const double *z, int ldz);
+/* w = A p and ptw = diag(p^T w): one fused pass when A has a diagonal image (b200_spmm.cu),
+ * otherwise SpMM + b200k_bpcg_ptw */
+int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bpcg_state *st, const double *p, int ldp,
+                        double *w, int ldw);
 /* alpha = rho2/ptw; x += alpha p; r -= alpha w; rho1 = rho2; rho2 = diag(r^T r);
  * then the per-column stop test (reference src/ops_lin_sol.c:383-394) and ++iterations */
 int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, const double *p, int ldp,

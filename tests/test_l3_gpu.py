@@ -104,6 +104,37 @@ def test_block_pcg_like_reference_TestMultiLinearSolver(b200, refmod):
             assert np.abs(got - x3).max() < 1e-11 * np.abs(x3).max()
 
 
+@pytest.mark.parametrize("k", [10, 40])
+def test_block_pcg_fused_dot_matches_streaming_dot(b200, k):
+    """The SpMM with diag(p^T A p) in its epilogue (b200_spmm.cu: spmm_dia_ws_kernel<.., DOT>)
+    against the SpMM + streaming dot kernel pair: same iteration count, same iterate up to the
+    rounding of the differently ordered dot products."""
+    import os
+    pen = P.p1_fem_kuhn(14)
+    n = pen.A.ncols
+    A = b200.Mat(pen.A)
+    rng = np.random.default_rng(11)
+    bh = np.asfortranarray(rng.random((n, k)))
+    out = []
+    for env in ("", "1"):
+        if env:
+            os.environ["B200_NO_FUSED_DOT"] = env
+        else:
+            os.environ.pop("B200_NO_FUSED_DOT", None)
+        try:
+            X = b200.MultiVec(n, k)
+            niter, res = b200.block_pcg(A, b200.MultiVec.from_numpy(bh), X, (0, 0), (k, k), max_iter=30, rate=1e-2,
+                                        tol=1e-14)
+            out.append((niter, X.numpy()))
+        finally:
+            os.environ.pop("B200_NO_FUSED_DOT", None)
+    assert out[0][0] == out[1][0]
+    assert np.abs(out[0][1] - out[1][1]).max() < 1e-11 * np.abs(out[1][1]).max()
+    # and it solves the system: 30 iterations at rate 1e-2 bring the residual down by > 10
+    Ad = pen.A.to_scipy()
+    assert np.linalg.norm(Ad @ out[0][1] - bh) < 0.1 * np.linalg.norm(bh)
+
+
 def test_block_pcg_shifted_operator(b200):
     """(A + sigma B) x = b, the operator of reference src/ops_eig_sol_gcg.c:63-96."""
     pen = P.p1_fem_kuhn(8)
@@ -136,6 +167,29 @@ def test_dense_syev_vs_lapack(b200, n):
     assert np.abs(w - wl).max() < 1e-13 * scale
     assert np.all(np.diff(w) >= 0)
     assert np.abs(z.T @ z - np.eye(n)).max() < 1e-12      # ~ n * eps * sweeps
+    assert np.abs(a @ z - z * w).max() < 1e-12 * scale
+    assert 1 <= sweeps <= 15
+
+
+@pytest.mark.parametrize("n", [100, 280, 480])
+def test_dense_syev_projected_matrix_shape(b200, n):
+    """The matrix the solver actually sees (reference src/ops_eig_sol_gcg.c:1013-1033): a diagonal
+    X block (the previous Ritz values, with clusters), a dense border and a dense P/W block; order
+    up to nevMax + 2 block_size = 480 at the headline configuration."""
+    rng = np.random.default_rng(n)
+    nx = (n * 5) // 6
+    a = np.zeros((n, n))
+    lam = np.sort(rng.uniform(30, 650, nx)); lam[3:6] = lam[3]          # a triple eigenvalue
+    a[np.arange(nx), np.arange(nx)] = lam
+    bw = n - nx
+    e = rng.standard_normal((nx, bw)) * 5
+    c = rng.standard_normal((bw, bw)); c = c @ c.T * 50 + np.eye(bw) * 700
+    a[:nx, nx:] = e; a[nx:, :nx] = e.T; a[nx:, nx:] = c
+    w, z, sweeps = b200.dense_syev(a)
+    wl = np.linalg.eigvalsh(a)
+    scale = np.abs(wl).max()
+    assert np.abs(w - wl).max() < 1e-12 * scale
+    assert np.abs(z.T @ z - np.eye(n)).max() < 2e-12
     assert np.abs(a @ z - z * w).max() < 1e-12 * scale
     assert 1 <= sweeps <= 15
 
