@@ -57,10 +57,14 @@ constexpr int GR_STAGE_DBL = 2 * GR_BK * GR_S;          // Xs + Ys of one stage
 // halves of the staged rows.  Global -> shared through a 3-stage cp.async ring, so the
 // tensor pipe works on stage i while stages i+1, i+2 are in flight.  Partials go to
 // part[chunk][q][p]; a second kernel sums the chunks in a fixed order (deterministic).
-template <bool AL16>
-__global__ void __launch_bounds__(256, 2)
-gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
-                    long long rows_per_chunk, double *part)
+// NQ8 = 8-column groups of Y this CTA's tile really has (1..8), a compile-time constant: a DMMA
+// that is merely predicated off still occupies the tensor pipe (measured: with a run-time
+// `if (j < nq8)` the pipe was 80 % busy at 17 TFLOP/s for q = 40, i.e. doing 64-column work),
+// so the narrow tiles get their own instantiation instead of a predicate.
+template <bool AL16, int NQ8>
+__device__ __forceinline__ void
+gram_partial_body(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
+                  long long rows_per_chunk, double *part)
 {
 	extern __shared__ __align__(16) double gsm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,7 +72,7 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 	const int pw = warp & 3, kh = warp >> 2;
 	const int p0 = blockIdx.x * GR_BP, q0 = blockIdx.z * GR_BQ;
 	const int pt = min(GR_BP, p - p0), qt = min(GR_BQ, q - q0);
-	const int nq8 = (qt + 7) >> 3;                       // active 8-column groups of Y
+	const bool p_live = pw * 16 < pt;                    // this warp's 16 X columns exist (warp-uniform)
 	const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
 	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
 	const int ntiles = (int)((r_end - r_begin + GR_BK - 1) / GR_BK);
@@ -83,8 +87,8 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 				const bool ok = (r < r_end) && (cc < pt);          // pt is even on this path
 				cp_async16(Xs + rr * GR_S + cc, ok ? x + (size_t)r * ldx + p0 + cc : x, ok);
 			}
-			for (int i = tid; i < GR_BK * (GR_BQ / 2); i += 256) {
-				const int rr = i / (GR_BQ / 2), cc = (i - rr * (GR_BQ / 2)) * 2;
+			for (int i = tid; i < GR_BK * (NQ8 * 4); i += 256) {
+				const int rr = i / (NQ8 * 4), cc = (i - rr * (NQ8 * 4)) * 2;
 				const long long r = r0 + rr;
 				const bool ok = (r < r_end) && (cc < qt);
 				cp_async16(Ys + rr * GR_S + cc, ok ? y + (size_t)r * ldy + q0 + cc : y, ok);
@@ -96,8 +100,8 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 				const bool ok = (r < r_end) && (cc < pt);
 				cp_async8(Xs + rr * GR_S + cc, ok ? x + (size_t)r * ldx + p0 + cc : x, ok);
 			}
-			for (int i = tid; i < GR_BK * GR_BQ; i += 256) {
-				const int rr = i / GR_BQ, cc = i - rr * GR_BQ;
+			for (int i = tid; i < GR_BK * (NQ8 * 8); i += 256) {
+				const int rr = i / (NQ8 * 8), cc = i - rr * (NQ8 * 8);
 				const long long r = r0 + rr;
 				const bool ok = (r < r_end) && (cc < qt);
 				cp_async8(Ys + rr * GR_S + cc, ok ? y + (size_t)r * ldy + q0 + cc : y, ok);
@@ -105,11 +109,11 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 		}
 	};
 
-	double acc[2][8][2];
+	double acc[2][NQ8][2];
 #pragma unroll
 	for (int i = 0; i < 2; ++i)
 #pragma unroll
-		for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+		for (int j = 0; j < NQ8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
 #pragma unroll
 	for (int s = 0; s < GR_STAGES - 1; ++s) {
@@ -125,14 +129,14 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 			cp_async_commit();
 		}
 		const double *Xs = gsm + (size_t)(tile % GR_STAGES) * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
+		if (p_live) {
 #pragma unroll
-		for (int ks = 0; ks < GR_BK / 2; ks += 4) {
-			const int kr = kh * (GR_BK / 2) + ks + t;
-			const double a0 = Xs[kr * GR_S + pw * 16 + g];
-			const double a1 = Xs[kr * GR_S + pw * 16 + 8 + g];
+			for (int ks = 0; ks < GR_BK / 2; ks += 4) {
+				const int kr = kh * (GR_BK / 2) + ks + t;
+				const double a0 = Xs[kr * GR_S + pw * 16 + g];
+				const double a1 = Xs[kr * GR_S + pw * 16 + 8 + g];
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				if (j < nq8) {
+				for (int j = 0; j < NQ8; ++j) {
 					const double b = Ys[kr * GR_S + j * 8 + g];
 					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
 					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
@@ -148,7 +152,7 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 #pragma unroll
 		for (int i = 0; i < 2; ++i)
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
+			for (int j = 0; j < NQ8; ++j) {
 				const int cr = pw * 16 + i * 8 + g;        // row of the C tile (0..63)
 				red[cr * GR_S + j * 8 + 2 * t]     = acc[i][j][0];
 				red[cr * GR_S + j * 8 + 2 * t + 1] = acc[i][j][1];
@@ -160,7 +164,7 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 #pragma unroll
 		for (int i = 0; i < 2; ++i)
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
+			for (int j = 0; j < NQ8; ++j) {
 				const int cr = pw * 16 + i * 8 + g;
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
@@ -169,6 +173,24 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 						out[(size_t)(q0 + cc) * p + (p0 + cr)] = acc[i][j][h] + red[cr * GR_S + cc];
 				}
 			}
+	}
+}
+
+template <bool AL16>
+__global__ void __launch_bounds__(256, 2)
+gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
+                    long long rows_per_chunk, double *part)
+{
+	const int qt = min(GR_BQ, q - (int)blockIdx.z * GR_BQ);
+	switch ((qt + 7) >> 3) {                             // uniform over the CTA
+	case 1: gram_partial_body<AL16, 1>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 2: gram_partial_body<AL16, 2>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 3: gram_partial_body<AL16, 3>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 4: gram_partial_body<AL16, 4>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 5: gram_partial_body<AL16, 5>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 6: gram_partial_body<AL16, 6>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 7: gram_partial_body<AL16, 7>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	default: gram_partial_body<AL16, 8>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
 	}
 }
 
@@ -346,10 +368,10 @@ constexpr int LC_STAGE_DBL = LC_BM * LC_SX + LC_BK * LC_SC;
 // C: element (k,j) at c[k*c_rs + j*c_cs].  blockIdx.x = column tile (fastest: the CTAs that
 // re-read one X row tile run together), blockIdx.y = row tile.  8 warps, warp w owns rows
 // [16w,16w+16) x 64 columns; 3-stage cp.async ring over the contraction dimension.
-template <bool HAS_BETA, bool AL16>
-__global__ void __launch_bounds__(256, 2)
-lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double *__restrict__ c, int c_rs,
-               int c_cs, const double *__restrict__ beta, int incb, double *y, int ldy)
+template <bool HAS_BETA, bool AL16, int NQ8>
+__device__ __forceinline__ void
+lincomb_body(long long n, int p, int q, const double *x, int ldx, const double *__restrict__ c, int c_rs,
+             int c_cs, const double *__restrict__ beta, int incb, double *y, int ldy)
 {
 	extern __shared__ __align__(16) double lsm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -357,7 +379,6 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 	const long long r0 = (long long)blockIdx.y * LC_BM;
 	const int n0 = blockIdx.x * LC_BN;
 	const int nt = min(LC_BN, q - n0);
-	const int nq8 = (nt + 7) >> 3;
 	const int ktiles = (p + LC_BK - 1) / LC_BK;
 
 	auto load_stage = [&](int stage, int kt) {
@@ -379,25 +400,25 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 			}
 		}
 		if (c_rs == 1) {             // column-major C: walk down columns
-			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
+			for (int i = tid; i < LC_BK * (NQ8 * 8); i += 256) {
 				const int cc = i / LC_BK, kk = i - cc * LC_BK;
 				const bool ok = (k0 + kk < p) && (cc < nt);
 				cp_async8(Cs + kk * LC_SC + cc, ok ? c + (size_t)(n0 + cc) * c_cs + k0 + kk : c, ok);
 			}
 		} else {                     // row-major (or general strides): walk along rows
-			for (int i = tid; i < LC_BK * LC_BN; i += 256) {
-				const int kk = i / LC_BN, cc = i - kk * LC_BN;
+			for (int i = tid; i < LC_BK * (NQ8 * 8); i += 256) {
+				const int kk = i / (NQ8 * 8), cc = i - kk * (NQ8 * 8);
 				const bool ok = (k0 + kk < p) && (cc < nt);
 				cp_async8(Cs + kk * LC_SC + cc, ok ? c + (size_t)(k0 + kk) * c_rs + (size_t)(n0 + cc) * c_cs : c, ok);
 			}
 		}
 	};
 
-	double acc[2][8][2];
+	double acc[2][NQ8][2];
 #pragma unroll
 	for (int i = 0; i < 2; ++i)
 #pragma unroll
-		for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+		for (int j = 0; j < NQ8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
 #pragma unroll
 	for (int s = 0; s < LC_STAGES - 1; ++s) {
@@ -418,12 +439,10 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 			const double a0 = Xs[(warp * 16 + g) * LC_SX + ks + t];
 			const double a1 = Xs[(warp * 16 + 8 + g) * LC_SX + ks + t];
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				if (j < nq8) {
-					const double b = Cs[(ks + t) * LC_SC + j * 8 + g];
-					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
-					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
-				}
+			for (int j = 0; j < NQ8; ++j) {
+				const double b = Cs[(ks + t) * LC_SC + j * 8 + g];
+				dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
+				dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
 			}
 		}
 	}
@@ -433,7 +452,7 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 		const long long r = r0 + warp * 16 + i * 8 + g;
 		if (r >= n) continue;
 #pragma unroll
-		for (int j = 0; j < 8; ++j)
+		for (int j = 0; j < NQ8; ++j)
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
 				const int cc = j * 8 + 2 * t + h;
@@ -447,6 +466,26 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 					*yp = v;
 				}
 			}
+	}
+}
+
+// the column tile's width in 8-column groups is a compile-time constant of the body: see
+// gram_partial_body (predicated-off DMMAs still occupy the tensor pipe)
+template <bool HAS_BETA, bool AL16>
+__global__ void __launch_bounds__(256, 2)
+lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double *__restrict__ c, int c_rs,
+               int c_cs, const double *__restrict__ beta, int incb, double *y, int ldy)
+{
+	const int nt = min(LC_BN, q - (int)blockIdx.x * LC_BN);
+	switch ((nt + 7) >> 3) {                             // uniform over the CTA
+	case 1: lincomb_body<HAS_BETA, AL16, 1>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 2: lincomb_body<HAS_BETA, AL16, 2>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 3: lincomb_body<HAS_BETA, AL16, 3>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 4: lincomb_body<HAS_BETA, AL16, 4>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 5: lincomb_body<HAS_BETA, AL16, 5>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 6: lincomb_body<HAS_BETA, AL16, 6>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	case 7: lincomb_body<HAS_BETA, AL16, 7>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
+	default: lincomb_body<HAS_BETA, AL16, 8>(n, p, q, x, ldx, c, c_rs, c_cs, beta, incb, y, ldy); break;
 	}
 }
 

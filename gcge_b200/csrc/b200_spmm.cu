@@ -546,43 +546,53 @@ static int launch_spmm_dia(const b200_mat *M, const double *x, int ldx, double *
 
 
 // ============================================================ diagonal SpMM, warp-specialised
-// Second generation of the kernel above for the common even block widths (k = 2 KP known at
-// compile time).  What the first one left on the table (profiles/ncu_r1d_spmm: 248 warp
-// instructions per matrix row of which 60 are FP64, FP64 pipe 43 % busy, stalls on the CTA
-// barrier after every run):
+// Second generation of the kernel above for the common even block widths (k known at compile
+// time).  What the first one left on the table (profiles/ncu_r1d_spmm: 248 warp instructions per
+// matrix row of which 60 are FP64, FP64 pipe 43 % busy, stalls on the CTA barrier after every
+// run) and what this one does about it:
 //
 //   * lane map: a row group is KP consecutive THREADS (not a power-of-two slice of a warp), so at
-//     k = 40 a CTA runs 12 groups on 240 of its 256 threads instead of 8 groups on 160 -- the
-//     FP64 pipe, which the separate multiply and add of the bit-exact accumulation load twice as
-//     hard as an FMA would, sees 94 % useful lanes instead of 62 %;
+//     k = 40 no lane idles -- the FP64 pipe, which the separate multiply and add of the
+//     bit-exact accumulation load twice as hard as an FMA would, sees > 90 % useful lanes
+//     instead of 62 %;
 //   * every shared-memory offset (tile pitch k*8, row t of the box) is an immediate;
 //   * a dedicated producer warp issues the TMA box copies; consumer warps hand a tile back
 //     with one mbarrier arrive per warp (full/empty barrier pair per ring slot) -- no
 //     __syncthreads anywhere in the main loop;
+//   * CP column pairs per lane (template; shipped with CP = 1): the kernel runs at 88 % of the
+//     shared-memory pipe (profiles/ncu_r1e_spmm) -- per matrix row 2880 B of x-row reads, 2333 B
+//     of TMA writes and 2560 B of broadcast matrix values.  Two pairs per lane halve the value
+//     traffic but measured slower (0.226 vs 0.204 ms at k = 40): fewer, fatter warps hide the
+//     shared-memory latency worse than the saved wavefronts gain;
 //   * DOT: the CG step needs diag(p^T A p) right after w = A p (reference
 //     src/ops_lin_sol.c:300-325).  The accumulators hold the finished w rows, the p rows were
 //     just pulled through L2 by the TMA unit, so the dot is a few FMAs in the epilogue and the
 //     separate 16nk-byte streaming pass over p and w disappears.  Per-CTA partial sums go to
 //     dot_part[cta][k]; the caller adds them in a fixed order (deterministic).
-template <int RB, int W, int K>
-__device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2], const double *tile, const double *vrow, int ndp)
+template <int RB, int W, int K, int KP, int CP>
+__device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2 * CP], const double *tile, const double *vrow, int ndp)
 {
-	double2 xv[RB + W - 1];
+	double2 xv[RB + W - 1][CP];
 #pragma unroll
-	for (int t = 0; t < RB + W - 1; ++t) xv[t] = *reinterpret_cast<const double2 *>(tile + t * K);
+	for (int t = 0; t < RB + W - 1; ++t)
+#pragma unroll
+		for (int j = 0; j < CP; ++j) xv[t][j] = *reinterpret_cast<const double2 *>(tile + t * K + 2 * KP * j);
 #pragma unroll
 	for (int i = 0; i < RB; ++i) {
 		const double2 a01 = *reinterpret_cast<const double2 *>(vrow);
-		acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a01.x, xv[i].x));
-		acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a01.x, xv[i].y));
-		if (W >= 2) {
-			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)].x));
-			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)].y));
-		}
-		if (W >= 3) {
-			const double a2 = vrow[2];
-			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].x));
-			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].y));
+		const double a2 = (W >= 3) ? vrow[2] : 0.0;
+#pragma unroll
+		for (int j = 0; j < CP; ++j) {
+			acc[i][2 * j]     = __dadd_rn(acc[i][2 * j],     __dmul_rn(a01.x, xv[i][j].x));
+			acc[i][2 * j + 1] = __dadd_rn(acc[i][2 * j + 1], __dmul_rn(a01.x, xv[i][j].y));
+			if (W >= 2) {
+				acc[i][2 * j]     = __dadd_rn(acc[i][2 * j],     __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)][j].x));
+				acc[i][2 * j + 1] = __dadd_rn(acc[i][2 * j + 1], __dmul_rn(a01.y, xv[i + (W >= 2 ? 1 : 0)][j].y));
+			}
+			if (W >= 3) {
+				acc[i][2 * j]     = __dadd_rn(acc[i][2 * j],     __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)][j].x));
+				acc[i][2 * j + 1] = __dadd_rn(acc[i][2 * j + 1], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)][j].y));
+			}
 		}
 		vrow += ndp;
 	}
@@ -608,28 +618,31 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int DIA2_CONSUMERS = 256;                    // consumer threads (8 warps); warp 8 is the producer
+constexpr int DIA2_MAX_NS = 8;                         // deepest tile ring
 
-template <int KP, int RB, int NS, bool DOT>
-__global__ void __launch_bounds__(DIA2_CONSUMERS + 32)
+// k = 2 KP CP columns; NT consumer threads (NT / 32 warps) + one producer warp; a row group is KP
+// consecutive threads and owns RB consecutive rows; lane gl of a group owns the column pairs
+// gl, gl + KP, ... (so every 128-bit request of a warp covers one contiguous piece of an x row).
+template <int KP, int CP, int RB, int NT, bool DOT>
+__global__ void __launch_bounds__(NT + 32)
 spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblocks, int nd, const int *__restrict__ off,
-                   const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes,
+                   const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes, int NS,
                    const double *x, int ldx, double *y, int ldy, const int *__restrict__ gate, double *dot_part)
 {
 	if (gate != nullptr && *gate == 0) return;
-	constexpr int K = 2 * KP;
-	constexpr int NG = DIA2_CONSUMERS / KP;            // row groups per CTA
+	constexpr int K = 2 * KP * CP;
+	constexpr int NG = NT / KP;                        // row groups per CTA
 	constexpr int ROWS = NG * RB;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	// [NS x-tiles of tile_bytes][2 value buffers of ROWS x nd doubles]
-	__shared__ unsigned long long full[NS], empty[NS], vfull[2], vempty[2];
+	__shared__ unsigned long long full[DIA2_MAX_NS], empty[DIA2_MAX_NS], vfull[2], vempty[2];
 	__shared__ int grp_s[64];
 	__shared__ int d0_s[32];
 	if (threadIdx.x < 2 * ng) grp_s[threadIdx.x] = __ldg(grp + threadIdx.x);
 	if (threadIdx.x < ng) d0_s[threadIdx.x] = __ldg(off + threadIdx.x);      // first offset of each run
 	if (threadIdx.x == 0) {
-		for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, DIA2_CONSUMERS / 32); }
-		for (int s = 0; s < 2; ++s) { mbar_init(vfull + s, 1); mbar_init(vempty + s, DIA2_CONSUMERS / 32); }
+		for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NT / 32); }
+		for (int s = 0; s < 2; ++s) { mbar_init(vfull + s, 1); mbar_init(vempty + s, NT / 32); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -639,21 +652,21 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	unsigned char *vbuf = smem_raw + (size_t)NS * tile_bytes;
 	const int my_blocks = (nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-	if (threadIdx.x >= DIA2_CONSUMERS) {
+	if (threadIdx.x >= NT) {
 		// ------------------------------------------------------------------ producer warp
-		if (threadIdx.x == DIA2_CONSUMERS) {
-			int item = 0;
+		if (threadIdx.x == NT) {
+			int slot = 0; unsigned phase = 0;
 			for (int lb = 0; lb < my_blocks; ++lb) {
 				const int blk = blockIdx.x + lb * gridDim.x;
 				mbar_spin(vempty + (lb & 1), (unsigned)(((lb >> 1) & 1) ^ 1));
 				mbar_expect_tx(vfull + (lb & 1), val_bytes);
 				// the image is padded behind its last row (b200_mat.cu): full-size copies stay in bounds
 				bulk_load_1d(vbuf + (size_t)(lb & 1) * val_bytes, val + (size_t)blk * ROWS * nd, val_bytes, vfull + (lb & 1));
-				for (int g = 0; g < ng; ++g, ++item) {
-					const int slot = item % NS;
-					mbar_spin(empty + slot, (unsigned)(((item / NS) & 1) ^ 1));
+				for (int g = 0; g < ng; ++g) {
+					mbar_spin(empty + slot, phase ^ 1u);
 					mbar_expect_tx(full + slot, x_bytes);
 					tma_load_2d(smem_raw + (size_t)slot * tile_bytes, &tmx, 0, blk * ROWS + d0_s[g] + hb, full + slot);
+					if (++slot == NS) { slot = 0; phase ^= 1u; }
 				}
 			}
 		}
@@ -662,29 +675,33 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	// ---------------------------------------------------------------------- consumer warps
 	const int lane = threadIdx.x & 31;
 	const int group = threadIdx.x / KP, gl = threadIdx.x - group * KP;
-	const bool live = group < NG;                      // the 256 % KP leftover threads only keep the barriers company
+	const bool live = group < NG;                      // the NT % KP leftover threads only keep the barriers company
 	const int c = 2 * gl;
 	const int lr0 = (live ? group : 0) * RB;           // first row of this group inside the block
-	double acc[RB][2];
-	double dot0 = 0.0, dot1 = 0.0;
-	int item = 0;
+	double acc[RB][2 * CP];
+	double dot[2 * CP];
+#pragma unroll
+	for (int j = 0; j < 2 * CP; ++j) dot[j] = 0.0;
+	int slot = 0; unsigned phase = 0;
 	for (int lb = 0; lb < my_blocks; ++lb) {
 		mbar_spin(vfull + (lb & 1), (unsigned)((lb >> 1) & 1));
 		const double *vrow = reinterpret_cast<const double *>(vbuf + (size_t)(lb & 1) * val_bytes) + (size_t)lr0 * nd;
 #pragma unroll
-		for (int i = 0; i < RB; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-		for (int g = 0; g < ng; ++g, ++item) {
-			const int slot = item % NS;
-			mbar_spin(full + slot, (unsigned)((item / NS) & 1));
+		for (int i = 0; i < RB; ++i)
+#pragma unroll
+			for (int j = 0; j < 2 * CP; ++j) acc[i][j] = 0.0;
+		for (int g = 0; g < ng; ++g) {
+			mbar_spin(full + slot, phase);
 			const int sp = grp_s[2 * g], w = grp_s[2 * g + 1];     // padded first slot, width
 			const double *tile = reinterpret_cast<const double *>(smem_raw + (size_t)slot * tile_bytes) + lr0 * K + c;
 			if (live) {
-				if (w == 2)      dia_run_ct<RB, 2, K>(acc, tile, vrow + sp, nd);
-				else if (w == 3) dia_run_ct<RB, 3, K>(acc, tile, vrow + sp, nd);
-				else             dia_run_ct<RB, 1, K>(acc, tile, vrow + sp, nd);
+				if (w == 2)      dia_run_ct<RB, 2, K, KP, CP>(acc, tile, vrow + sp, nd);
+				else if (w == 3) dia_run_ct<RB, 3, K, KP, CP>(acc, tile, vrow + sp, nd);
+				else             dia_run_ct<RB, 1, K, KP, CP>(acc, tile, vrow + sp, nd);
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty + slot);          // this warp is done with the tile
+			if (++slot == NS) { slot = 0; phase ^= 1u; }
 		}
 		__syncwarp();
 		if (lane == 0) mbar_arrive(vempty + (lb & 1));         // ... and with the block's values
@@ -693,11 +710,15 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 #pragma unroll
 			for (int i = 0; i < RB; ++i) {
 				if (r0 + i < nrows) {
-					*reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c) = make_double2(acc[i][0], acc[i][1]);
-					if (DOT) {
-						const double2 pv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)(r0 + i) * ldx + c));
-						dot0 = fma(pv.x, acc[i][0], dot0);
-						dot1 = fma(pv.y, acc[i][1], dot1);
+#pragma unroll
+					for (int j = 0; j < CP; ++j) {
+						*reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c + 2 * KP * j) =
+							make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+						if (DOT) {
+							const double2 pv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)(r0 + i) * ldx + c + 2 * KP * j));
+							dot[2 * j] = fma(pv.x, acc[i][2 * j], dot[2 * j]);
+							dot[2 * j + 1] = fma(pv.y, acc[i][2 * j + 1], dot[2 * j + 1]);
+						}
 					}
 				}
 			}
@@ -705,11 +726,17 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	}
 	if (DOT) {
 		// per-CTA column sums in a fixed order: groups 0 .. NG-1 (the tiles are dead: reuse tile 0)
-		asm volatile("bar.sync 1, %0;" ::"n"(DIA2_CONSUMERS));
+		asm volatile("bar.sync 1, %0;" ::"n"(NT));
 		double *red = reinterpret_cast<double *>(smem_raw);
-		if (live) { red[group * K + c] = dot0; red[group * K + c + 1] = dot1; }
-		asm volatile("bar.sync 1, %0;" ::"n"(DIA2_CONSUMERS));
-		for (int cc = threadIdx.x; cc < K; cc += DIA2_CONSUMERS) {
+		if (live) {
+#pragma unroll
+			for (int j = 0; j < CP; ++j) {
+				red[group * K + c + 2 * KP * j] = dot[2 * j];
+				red[group * K + c + 2 * KP * j + 1] = dot[2 * j + 1];
+			}
+		}
+		asm volatile("bar.sync 1, %0;" ::"n"(NT));
+		for (int cc = threadIdx.x; cc < K; cc += NT) {
 			double s = 0.0;
 			for (int gq = 0; gq < NG; ++gq) s += red[gq * K + cc];
 			dot_part[(size_t)blockIdx.x * K + cc] = s;
@@ -717,24 +744,33 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	}
 }
 
-// rows per group for a given pair count: blocks of ~48-128 rows, TMA boxes of at most 256 rows
-template <int KP> struct Dia2Cfg {
-	static constexpr int NG = DIA2_CONSUMERS / KP;
-	static constexpr int RB = (NG * 8 <= 128) ? 8 : ((NG * 4 <= 160) ? 4 : ((NG * 2 <= 200) ? 2 : 1));
-};
+static int env_int(const char *name, int dflt)
+{
+	const char *e = getenv(name);
+	return (e && *e) ? atoi(e) : dflt;
+}
 
 // returns 0 launched, 1 error, 2 not applicable; *nparts = number of per-CTA dot partials written
-template <int KP, int RB, int NS, bool DOT>
+template <int KP, int CP, int RB, int NT, bool DOT>
 static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
                               double *dot_part, int dot_cap, int *nparts)
 {
-	constexpr int K = 2 * KP;
-	constexpr int ROWS = (DIA2_CONSUMERS / KP) * RB;
+	constexpr int K = 2 * KP * CP;
+	constexpr int ROWS = (NT / KP) * RB;
 	static_assert(ROWS + DIA_WMAX - 1 <= 256, "TMA box too tall");
 	static_assert(ROWS <= B200_DIA_PAD, "diagonal image padding does not cover the row block");
 	const int ng = M->dia_ng, nd = M->dia_ndp;
 	const int tile_bytes = (((ROWS + DIA_WMAX - 1) * K * 8) + 127) & ~127;
-	const size_t smem = (size_t)NS * tile_bytes + 2 * (size_t)ROWS * nd * 8;
+	const size_t val_smem = 2 * (size_t)ROWS * nd * 8;
+	// ring depth: the deepest that still lets `want_ctas` CTAs share an SM (measured at k = 40: three
+	// CTAs with 3 tiles each 0.201 ms, two with 6 tiles 0.205 ms, one with 8 tiles 0.29 ms, four with
+	// 2 tiles 0.32 ms)
+	static const int want_ctas = env_int("B200_SPMM_CTAS", 3), ns_env = env_int("B200_SPMM_NS", 0);
+	const size_t budget = (size_t)(224 * 1024) / (want_ctas > 0 ? want_ctas : 1) - 2048;
+	int NS = ns_env > 0 ? ns_env : (budget > val_smem ? (int)((budget - val_smem) / tile_bytes) : 0);
+	if (NS > DIA2_MAX_NS) NS = DIA2_MAX_NS;
+	if (NS < 2) NS = 2;
+	const size_t smem = (size_t)NS * tile_bytes + val_smem;
 	if (smem > 200 * 1024) return 2;
 	tmap_encode_fn enc = tmap_encoder();
 	if (!enc) return 2;
@@ -751,63 +787,65 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 	if (r != CUDA_SUCCESS) return 2;
 	static bool attr_set = false;
 	if (!attr_set) {
-		B200_CUDA(cudaFuncSetAttribute(spmm_dia_ws_kernel<KP, RB, NS, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		B200_CUDA(cudaFuncSetAttribute(spmm_dia_ws_kernel<KP, CP, RB, NT, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr_set = true;
 	}
 	const int nblocks = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
-	int per_sm = (int)((224 * 1024) / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 3) per_sm = 3;
+	int per_sm = (int)((224 * 1024) / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
 	int grid = g_b200.num_sms * per_sm; if (grid > nblocks) grid = nblocks;
 	if (DOT) {
 		if (grid > dot_cap) return 2;
 		*nparts = grid;
 	}
-	spmm_dia_ws_kernel<KP, RB, NS, DOT><<<grid, DIA2_CONSUMERS + 32, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off,
-		M->dia_val, ng, M->dia_grp, hb, tile_bytes, x, ldx, y, ldy, gate, dot_part);
+	spmm_dia_ws_kernel<KP, CP, RB, NT, DOT><<<grid, NT + 32, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off,
+		M->dia_val, ng, M->dia_grp, hb, tile_bytes, NS, x, ldx, y, ldy, gate, dot_part);
 	B200_KERNEL_CHECK();
 	return 0;
 }
 
-static int spmm_variant()
-{
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("B200_SPMM_VARIANT"); v = e ? atoi(e) : 0; }
-	return v;
-}
+// rows per group: 4 (the x rows of a run are then read 1.25 - 1.5 times), 2 where four would make
+// the TMA box taller than 256 rows
+template <int KP, int NT> struct Dia2Cfg {
+	static constexpr int NG = NT / KP;
+	static constexpr int RB = (NG * 4 + DIA_WMAX - 1 <= 256) ? 4 : 2;
+};
 
-template <int KP>
+template <int KP, int CP, int NT = 256>
 static int launch_spmm_dia_ws_kp(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
                                  double *dot_part, int dot_cap, int *nparts)
 {
-	constexpr int RB = Dia2Cfg<KP>::RB;
-	if (dot_part) return launch_spmm_dia_ws<KP, RB, 4, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	if constexpr (KP == 20) {          // tuning variants of the headline width (B200_SPMM_VARIANT)
-		if (spmm_variant() == 1) return launch_spmm_dia_ws<KP, 4, 4, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
-		if (spmm_variant() == 2) return launch_spmm_dia_ws<KP, 8, 3, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
-		if (spmm_variant() == 3) return launch_spmm_dia_ws<KP, 6, 4, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
-		if (spmm_variant() == 4) return launch_spmm_dia_ws<KP, 8, 2, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
-		if (spmm_variant() == 5) return launch_spmm_dia_ws<KP, 4, 6, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
-	}
-	return launch_spmm_dia_ws<KP, RB, 4, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
+	constexpr int RB = Dia2Cfg<KP, NT>::RB;
+	if (dot_part) return launch_spmm_dia_ws<KP, CP, RB, NT, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
+	return launch_spmm_dia_ws<KP, CP, RB, NT, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
 }
 
-// the block widths with a compile-time kernel; anything else takes the generic kernel above
+// The block widths with a compile-time kernel; anything else takes the generic kernel above.
+// One column pair per lane, 8 consumer warps, three CTAs per SM: measured best at every width
+// (n = 1 M P1-FEM, k = 40: 0.204 ms; two pairs per lane 0.226 ms; 4-warp CTAs 0.216 - 0.249 ms;
+// gpurun_out/spmm_variants3.log, summarised in profiles/).
 static int spmm_dia_ws_dispatch(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate,
                                 double *dot_part, int dot_cap, int *nparts)
 {
 	if (getenv("B200_SPMM_OLD_DIA")) return 2;
+#define WS(KP_) launch_spmm_dia_ws_kp<KP_, 1>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts)
 	switch (k) {
-	case 8:  return launch_spmm_dia_ws_kp<4>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 10: return launch_spmm_dia_ws_kp<5>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 16: return launch_spmm_dia_ws_kp<8>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 20: return launch_spmm_dia_ws_kp<10>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 24: return launch_spmm_dia_ws_kp<12>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 32: return launch_spmm_dia_ws_kp<16>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 40: return launch_spmm_dia_ws_kp<20>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 48: return launch_spmm_dia_ws_kp<24>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 50: return launch_spmm_dia_ws_kp<25>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	case 64: return launch_spmm_dia_ws_kp<32>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
+	case 8:  return WS(4);
+	case 10: return WS(5);
+	case 12: return WS(6);
+	case 16: return WS(8);
+	case 20: return WS(10);
+	case 24: return WS(12);
+	case 30: return WS(15);
+	case 32: return WS(16);
+	case 40: return WS(20);
+	case 48: return WS(24);
+	case 50: return WS(25);
+	case 56: return WS(28);
+	case 60: return WS(30);
+	case 64: return WS(32);
 	default: return 2;
 	}
+#undef WS
 }
 
 // diagonal image, at most 64 columns

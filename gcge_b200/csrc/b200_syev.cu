@@ -47,18 +47,24 @@ __device__ __forceinline__ int jac_player(int pos, int r, int N)
 	return v;
 }
 
+// |a_pq| <= eps sqrt(|a_pp a_qq|), compared in squares (no square root on the critical path)
 __device__ __forceinline__ bool jac_small(double app, double aqq, double apq)
 {
-	const double eps = 2.220446049250313e-16;
-	return fabs(apq) <= eps * sqrt(fabs(app) * fabs(aqq)) || fabs(apq) < 1e-300;
+	const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+	return apq * apq <= eps2 * fabs(app * aqq) || fabs(apq) < 1e-150;      // (squares underflow below ~1e-154)
 }
 
+// Rotation that annihilates a_pq: t = tan(theta) is the smaller root of t^2 + 2 tau t - 1 = 0,
+// tau = (a_qq - a_pp) / (2 a_pq), written as t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)) so
+// that the dependent chain is one square root, one division and one reciprocal square root
+// (the textbook form through tau has two of each; the chain latency is what a round costs).
 __device__ __forceinline__ bool jac_rotation(double app, double aqq, double apq, double &c, double &s)
 {
 	if (jac_small(app, aqq, apq)) { c = 1.0; s = 0.0; return false; }
-	const double tau = (aqq - app) / (2.0 * apq);
-	const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-	c = rsqrt(1.0 + t * t);
+	const double d = aqq - app, num = 2.0 * apq;
+	const double h = fma(d, d, num * num);
+	const double t = (d >= 0.0 ? num : -num) / (fabs(d) + sqrt(h));
+	c = rsqrt(fma(t, t, 1.0));
 	s = t * c;
 	return true;
 }
@@ -77,8 +83,10 @@ __device__ __forceinline__ int bj_glob(int l, int P, int Q) { return (l < BJ_B ?
 // Phase 1 on one pivot matrix held in S0 (32 x 32, stride BJ_LD): rotate every pair of the
 // inner ordering once.  Thread (a, b) of the 16 x 16 thread grid owns the 2 x 2 block (rows of
 // inner pair a) x (columns of inner pair b) and rows a, a + 16 of J for the columns of pair b;
-// it recomputes the two rotations it needs from the diagonal 2 x 2 blocks (a few flops) instead
-// of waiting for a broadcast.  S is double buffered (one barrier per inner round); J is
+// it computes the rotation of its column pair from that pair's diagonal 2 x 2 block and gets the
+// rotation of its row pair by a shuffle (the first version had every thread compute both:
+// 2 x ~250 dependent FP64 instructions per round, 1 us per round with 8 warps on an SM).
+// S is double buffered (one barrier per inner round); J is
 // updated in place (every thread owns its entries).  Returns the number of rotations applied
 // (the same value in every thread); the result is in S0.
 __device__ int bj_pivot_sweep(double *S0, double *S1, double *Jm, bool full)
@@ -102,9 +110,13 @@ __device__ int bj_pivot_sweep(double *S0, double *S1, double *Jm, bool full)
 		int pa, qa, pb, qb;
 		bj_pair(a, r, full, pa, qa);
 		bj_pair(b, r, full, pb, qb);
+		// one rotation per thread (its column pair b); the row pair's comes from lane a of the warp
+		// (lane = 16 (a & 1) + b, so lanes 0..15 hold the pairs 0..15)
 		double ca, sa, cb, sb;
-		const bool rot = jac_rotation(cur[pa * BJ_LD + pa], cur[qa * BJ_LD + qa], cur[pa * BJ_LD + qa], ca, sa);
-		jac_rotation(cur[pb * BJ_LD + pb], cur[qb * BJ_LD + qb], cur[pb * BJ_LD + qb], cb, sb);
+		const bool rotb = jac_rotation(cur[pb * BJ_LD + pb], cur[qb * BJ_LD + qb], cur[pb * BJ_LD + qb], cb, sb);
+		ca = __shfl_sync(0xffffffffu, cb, a);
+		sa = __shfl_sync(0xffffffffu, sb, a);
+		const bool rot = rotb;                                 // used only where a == b
 		if (a == b && rot) ++rotated;
 		const double b00 = cur[pa * BJ_LD + pb], b01 = cur[pa * BJ_LD + qb];
 		const double b10 = cur[qa * BJ_LD + pb], b11 = cur[qa * BJ_LD + qb];
@@ -151,27 +163,23 @@ __device__ __forceinline__ void bj_mm(const double *X, const double *Y, double *
 	for (int j = 0; j < 4; ++j) D[i * BJ_LD + j0 + j] = acc[j];
 }
 
-__device__ __forceinline__ void bj_load_J(double *dst, const double *jbuf, int pair, int nrot)
-{
-	for (int i = threadIdx.x; i < BJ_T * BJ_T; i += 256) {
-		const int r = i >> 5, c = i & 31;
-		dst[r * BJ_LD + c] = nrot ? jbuf[(size_t)pair * BJ_T * BJ_T + i] : (r == c ? 1.0 : 0.0);
-	}
-}
-
 // Mg: Np x Np symmetric matrix, Vg: Np x Np accumulated transformations (both row-major, ld Np,
 // Np = 16 NB, NB even; indices >= n are padding: zero rows and columns that never rotate).
 // On exit w ascending, z[i*ldz + j] = component i of eigenvector j, *sweeps_out = sweeps done.
 __global__ void __launch_bounds__(256)
 syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, int *nrot, double *w, double *z, int ldz,
-                         int max_sweeps, int *rot_count, int *rank_of, int *sweeps_out)
+                         int max_sweeps, int *rot_count, int *rank_of, int *sweeps_out, long long *cycles)
 {
 	cg::grid_group grid = cg::this_grid();
 	__shared__ double sm[4 * BJ_TILE];
 	double *T0 = sm, *T1 = sm + BJ_TILE, *T2 = sm + 2 * BJ_TILE, *T3 = sm + 3 * BJ_TILE;
 	const int tid = threadIdx.x;
 	const int Np = NB * BJ_B, m = NB / 2;
-	const int a_jobs = m * (m - 1) / 2, v_jobs = (Np / BJ_T) * m;
+	const int vrb = (Np / BJ_T + 1) / 2;                   // V jobs take two 32-row tiles each
+	const int a_jobs = m * (m - 1) / 2, v_jobs = vrb * m;
+	// where the time goes (block 0's view, clock64 ticks): [0] phase 1, [1] barrier, [2] phase 2, [3] barrier
+	long long cyc[4] = {0, 0, 0, 0}, t_prev = clock64();
+	auto lap = [&](int slot) { const long long t = clock64(); cyc[slot] += t - t_prev; t_prev = t; };
 	int sweep = 0;
 	for (; sweep < max_sweeps; ++sweep) {
 		for (int R = 0; R < NB - 1; ++R) {
@@ -197,7 +205,9 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 				}
 				__syncthreads();
 			}
+			lap(0);
 			grid.sync();
+			lap(1);
 			// ---- phase 2: the rest of A (upper tiles, mirrored) and V
 			for (int job = blockIdx.x; job < a_jobs + v_jobs; job += gridDim.x) {
 				if (job < a_jobs) {
@@ -209,12 +219,21 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 					if (nI == 0 && nJ == 0) continue;
 					const int PI = jac_player(2 * I, R, NB), QI = jac_player(2 * I + 1, R, NB);
 					const int PJ = jac_player(2 * J, R, NB), QJ = jac_player(2 * J + 1, R, NB);
-					for (int i = tid; i < BJ_T * BJ_T; i += 256) {
-						const int r = i >> 5, c = i & 31;
-						T0[r * BJ_LD + c] = Mg[(size_t)bj_glob(r, PI, QI) * Np + bj_glob(c, PJ, QJ)];
+					{   // all twelve loads of a thread in flight at once: one L2 round trip, not three
+						double tv[4], ji[4], jj[4];
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const int i = tid + u * 256, r = i >> 5, c = i & 31;
+							tv[u] = Mg[(size_t)bj_glob(r, PI, QI) * Np + bj_glob(c, PJ, QJ)];
+							ji[u] = nI ? jbuf[(size_t)I * BJ_T * BJ_T + i] : (r == c ? 1.0 : 0.0);
+							jj[u] = nJ ? jbuf[(size_t)J * BJ_T * BJ_T + i] : (r == c ? 1.0 : 0.0);
+						}
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const int i = tid + u * 256, r = i >> 5, c = i & 31;
+							T0[r * BJ_LD + c] = tv[u]; T1[r * BJ_LD + c] = ji[u]; T2[r * BJ_LD + c] = jj[u];
+						}
 					}
-					bj_load_J(T1, jbuf, I, nI);
-					bj_load_J(T2, jbuf, J, nJ);
 					__syncthreads();
 					bj_mm<true>(T1, T0, T3);               // U = J_I^T T
 					__syncthreads();
@@ -229,26 +248,41 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 					}
 					__syncthreads();
 				} else {
-					const int vj = job - a_jobs, rb = vj / m, J = vj - rb * m;
+					const int vj = job - a_jobs, rb2 = vj / m, J = vj - rb2 * m;
 					const int nJ = nrot[J];
 					if (nJ == 0) continue;
 					const int PJ = jac_player(2 * J, R, NB), QJ = jac_player(2 * J + 1, R, NB);
-					for (int i = tid; i < BJ_T * BJ_T; i += 256) {
-						const int r = i >> 5, c = i & 31;
-						T0[r * BJ_LD + c] = Vg[(size_t)(rb * BJ_T + r) * Np + bj_glob(c, PJ, QJ)];
+					const int nt = (2 * rb2 + 1 < Np / BJ_T) ? 2 : 1;
+					{
+						double tv[2][4], jj[4];
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const int i = tid + u * 256, r = i >> 5, c = i & 31;
+							tv[0][u] = Vg[(size_t)((2 * rb2) * BJ_T + r) * Np + bj_glob(c, PJ, QJ)];
+							tv[1][u] = (nt == 2) ? Vg[(size_t)((2 * rb2 + 1) * BJ_T + r) * Np + bj_glob(c, PJ, QJ)] : 0.0;
+							jj[u] = jbuf[(size_t)J * BJ_T * BJ_T + i];
+						}
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const int i = tid + u * 256, r = i >> 5, c = i & 31;
+							T0[r * BJ_LD + c] = tv[0][u]; T1[r * BJ_LD + c] = tv[1][u]; T2[r * BJ_LD + c] = jj[u];
+						}
 					}
-					bj_load_J(T2, jbuf, J, nJ);
 					__syncthreads();
-					bj_mm<false>(T0, T2, T3);              // T' = T J_J
-					__syncthreads();
-					for (int i = tid; i < BJ_T * BJ_T; i += 256) {
-						const int r = i >> 5, c = i & 31;
-						Vg[(size_t)(rb * BJ_T + r) * Np + bj_glob(c, PJ, QJ)] = T3[r * BJ_LD + c];
+					for (int h = 0; h < nt; ++h) {
+						bj_mm<false>(h ? T1 : T0, T2, T3);      // T' = T J_J
+						__syncthreads();
+						for (int i = tid; i < BJ_T * BJ_T; i += 256) {
+							const int r = i >> 5, c = i & 31;
+							Vg[(size_t)((2 * rb2 + h) * BJ_T + r) * Np + bj_glob(c, PJ, QJ)] = T3[r * BJ_LD + c];
+						}
+						__syncthreads();
 					}
-					__syncthreads();
 				}
 			}
+			lap(2);
 			grid.sync();
+			lap(3);
 		}
 		// end of sweep: did anything rotate?
 		const int rotated = *((volatile int *)rot_count);
@@ -274,7 +308,10 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 		const int i = idx / n, j = idx - i * n;
 		z[(size_t)i * ldz + rank_of[j]] = Vg[(size_t)i * Np + j];
 	}
-	if (gtid == 0) *sweeps_out = sweep;
+	if (gtid == 0) {
+		*sweeps_out = sweep;
+		for (int i = 0; i < 4; ++i) cycles[i] = cyc[i];
+	}
 }
 
 // padded copies: Mg = A (zero padded), Vg = I
@@ -298,10 +335,11 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 	const int Np = NB * BJ_B, m = NB / 2;
 	const size_t nn = (size_t)Np * Np;
 	const size_t dbl = 2 * nn + (size_t)m * BJ_T * BJ_T;
-	char *base = (char *)b200_scratch(5, sizeof(double) * dbl + sizeof(int) * ((size_t)m + Np + 8));
+	char *base = (char *)b200_scratch(5, sizeof(double) * (dbl + 4) + sizeof(int) * ((size_t)m + Np + 8));
 	if (!base) return 1;
 	double *Mg = (double *)base, *Vg = Mg + nn, *jbuf = Vg + nn;
-	int *nrot = (int *)(jbuf + (size_t)m * BJ_T * BJ_T), *rank_of = nrot + m, *ctr = rank_of + Np;
+	long long *cycles = (long long *)(jbuf + (size_t)m * BJ_T * BJ_T);
+	int *nrot = (int *)(cycles + 4), *rank_of = nrot + m, *ctr = rank_of + Np;
 	B200_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), st));
 	syev_init_kernel<<<b200_ceil_div((long long)Np * Np, 256), 256, 0, st>>>(n, Np, a_dev, lda, Mg, Vg);
 	B200_KERNEL_CHECK();
@@ -309,18 +347,24 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 	B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, syev_block_jacobi_kernel, 256, 0));
 	B200_CHECK(per_sm >= 1, "syev: kernel does not fit on an SM");
 	if (per_sm > 2) per_sm = 2;
-	const long long jobs = (long long)m * (m - 1) / 2 + (long long)(Np / BJ_T) * m;
+	const long long jobs = (long long)m * (m - 1) / 2 + (long long)((Np / BJ_T + 1) / 2) * m;
 	long long want = jobs > m ? jobs : m;
 	const long long cap = (long long)per_sm * g_b200.num_sms;
 	int blocks = (int)(want < cap ? want : cap);
 	if (blocks < 1) blocks = 1;
 	int max_sweeps = 40;
 	int *rot = ctr, *sw = ctr + 1;
-	void *args[] = {&n, &NB, &Mg, &Vg, &jbuf, &nrot, &w_dev, &z_dev, &ldz, &max_sweeps, &rot, &rank_of, &sw};
+	void *args[] = {&n, &NB, &Mg, &Vg, &jbuf, &nrot, &w_dev, &z_dev, &ldz, &max_sweeps, &rot, &rank_of, &sw, &cycles};
 	B200_CUDA(cudaLaunchCooperativeKernel((void *)syev_block_jacobi_kernel, dim3(blocks), dim3(256), args, 0, st));
 	B200_LAUNCHED();
 	if (sweeps_host) {
 		if (b200k_d2h(sweeps_host, sw, sizeof(int))) return 1;
+	}
+	if (getenv("B200_SYEV_PROF")) {
+		long long cyc[4];
+		if (b200k_d2h(cyc, cycles, sizeof(cyc))) return 1;
+		fprintf(stderr, "syev n=%d grid=%d clock64 ticks: phase1 %lld barrier %lld phase2 %lld barrier %lld\n", n, blocks,
+		        cyc[0], cyc[1], cyc[2], cyc[3]);
 	}
 	return 0;
 }

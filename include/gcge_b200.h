@@ -48,6 +48,9 @@ int  b200_timer_stop(double *ms);
 /* measured FP64 tensor-core (DMMA m8n8k4) issue ceiling of this GPU, TFLOP/s: the roofline
  * denominator of the Gram / LinearComb kernels */
 int  b200_measure_dmma_peak(double *tflops);
+/* out[0..4] TFLOP/s: DMMA with one shared operand pair; DMMA with the 2 A x 8 B fragment pattern of the
+ * Gram / LinearComb inner loops in two issue orders; the plain DFMA pipe; DMMA and DFMA interleaved. */
+int  b200_measure_fp64_peaks(double *out5);
 /* overwrite a buffer larger than L2 so the next timed kernel starts cold */
 int  b200_flush_l2(void);
 /* Per-kernel-class device timing for bench.py's roofline: while enabled, every kernel call of

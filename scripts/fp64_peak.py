@@ -6,6 +6,9 @@ api.init(0)
 t = C.c_double(0)
 assert api.lib().b200_measure_dmma_peak(C.byref(t)) == 0
 print("DMMA register-resident peak TFLOP/s:", round(t.value, 2))
+out = (C.c_double * 5)()
+assert api.lib().b200_measure_fp64_peaks(out) == 0
+print("FP64 pipes TFLOP/s: dmma_shared_operands %.2f  dmma_2Ax8B_interleaved %.2f  dmma_2Ax8B_rowwise %.2f  dfma %.2f  dmma+dfma %.2f" % tuple(out))
 import torch
 a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
 torch.matmul(a, b); torch.cuda.synchronize()
