@@ -218,6 +218,10 @@ extern "C" int b200_plan_destroy(b200_plan *p)
 // rows r and r+1 share the x rows of adjacent offsets, so a thread that walks a block of rows
 // loads every x row once instead of once per matrix row that touches it (b200_spmm.cu).
 // rp/ci/va: the local CSR slab with REMAPPED columns (see b200_partition_build).
+int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_row, const double *data, int rank,
+                           int nranks, b200_mat *A);
+void b200_note_halo_capacity(long long n_global, int nhalo);
+
 static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va, int nranks)
 {
 	const int nloc = A->nrows;
@@ -280,7 +284,7 @@ static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va
 	return 0;
 }
 
-static void note_halo_capacity(long long n_global, int nhalo)
+void b200_note_halo_capacity(long long n_global, int nhalo)
 {
 	for (int i = 0; i < 8; ++i) {
 		if (g_b200.halo_n[i] == n_global || g_b200.halo_n[i] == 0) {
@@ -298,6 +302,13 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	B200_CHECK(out && j_col && nrows >= 0 && ncols >= 0, "b200_mat_create_from_ccs: bad arguments");
 	const int nranks = g_b200.nranks > 1 ? g_b200.nranks : 1;
 	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
+	{
+		// fast path: the whole construction on the device (b200_matbuild.cu); 2 = not applicable
+		const int rc = b200k_mat_build_device(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A);
+		if (rc == 0) { *out = A; return 0; }
+		if (rc == 1) { free(A); return 1; }
+		memset(A, 0, sizeof(*A));
+	}
 	int *rp = nullptr, *ci = nullptr; double *va = nullptr;
 	if (b200_partition_build(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A, &rp, &ci, &va)) { free(A); return 1; }
 	const int nnz = A->nnz, nloc = A->nrows;
@@ -328,7 +339,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 		const int ns = A->send_off[A->nnbr];
 		B200_CUDA(cudaMalloc(&A->send_rows_dev, sizeof(int) * (size_t)(ns > 0 ? ns : 1)));
 		B200_CUDA(cudaMemcpyAsync(A->send_rows_dev, A->send_rows, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
-		note_halo_capacity(A->ncols_global, A->nhalo);
+		b200_note_halo_capacity(A->ncols_global, A->nhalo);
 	}
 	B200_CUDA(cudaStreamSynchronize(st));
 	const int rc_dia = dia_build(A, rp, ci, va, nranks);

@@ -598,6 +598,16 @@ __device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2 * CP], const doub
 	}
 }
 
+// 1-D bulk copy whose lines are the first to leave L2: the matrix values are read once per SpMM,
+// the x rows pulled by the neighbouring TMA boxes up to 2 m^2 rows later must stay
+__device__ __forceinline__ void bulk_load_1d_evict_first(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
 {
 	unsigned ok;
@@ -661,7 +671,7 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 				mbar_spin(vempty + (lb & 1), (unsigned)(((lb >> 1) & 1) ^ 1));
 				mbar_expect_tx(vfull + (lb & 1), val_bytes);
 				// the image is padded behind its last row (b200_mat.cu): full-size copies stay in bounds
-				bulk_load_1d(vbuf + (size_t)(lb & 1) * val_bytes, val + (size_t)blk * ROWS * nd, val_bytes, vfull + (lb & 1));
+				bulk_load_1d_evict_first(vbuf + (size_t)(lb & 1) * val_bytes, val + (size_t)blk * ROWS * nd, val_bytes, vfull + (lb & 1));
 				for (int g = 0; g < ng; ++g) {
 					mbar_spin(empty + slot, phase ^ 1u);
 					mbar_expect_tx(full + slot, x_bytes);
@@ -712,8 +722,9 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 				if (r0 + i < nrows) {
 #pragma unroll
 					for (int j = 0; j < CP; ++j) {
-						*reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c + 2 * KP * j) =
-							make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+						// streaming store: y is not read again by this kernel and must not push x rows out of L2
+						__stcs(reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c + 2 * KP * j),
+						       make_double2(acc[i][2 * j], acc[i][2 * j + 1]));
 						if (DOT) {
 							const double2 pv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)(r0 + i) * ldx + c + 2 * KP * j));
 							dot[2 * j] = fma(pv.x, acc[i][2 * j], dot[2 * j]);
