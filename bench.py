@@ -7,10 +7,13 @@ metric   GCG solve seconds (lower is better): wall time of one whole block-GCG s
          pencil A x = lambda B x on the Kuhn triangulation, n = m^3 (default m = 200, n = 8.0 M,
          ~15 nnz/row), nev = 200 (nevMax 400, block_size 40), reference default tolerances.
 step     one whole solve of that pencil from srand(0).
-value    seconds per solve, inputs (A, B) resident in HBM, CUDA events on the library stream.
+value    seconds per solve, inputs (A, B) resident in HBM and the four GCG workspaces created
+         beforehand (the reference's driver creates gcg_mv_ws[0..3] before its clock starts,
+         test/test_eig_sol_gcg.c:57-68,88), CUDA events on the library stream.
 e2e      the same solve through the C-ABI with HOST buffers: CCS arrays of A and B uploaded
-         from page-locked host memory, solve, eigenvalues + the nev converged eigenvectors
-         copied back to the host -- all inside the timed region.
+         from page-locked host memory and turned into device matrices, workspaces allocated,
+         solve, eigenvalues + the nev converged eigenvectors copied back to the host, workspaces
+         freed -- all inside the timed region.
 roofline the dominant kernel class of the timed region (device time from CUDA events around
          every launch of the class, algorithmic bytes/flops of SURVEY.md 8d / DESIGN.md).
 cpu_baseline / --impl reference
@@ -208,11 +211,14 @@ def run_b200(a) -> int:
         torch.cuda.synchronize()
         api.sync()
 
-    def solve(Am, Bm):
-        return api.gcg_solve(Am, Bm, nev=a.nev, evec=evec, seed=0, numIterMax=a.max_iter if a.max_iter > 0 else 500)
+    def solve(Am, Bm, ws=None):
+        return api.gcg_solve(Am, Bm, nev=a.nev, evec=evec, seed=0, ws=ws, numIterMax=a.max_iter if a.max_iter > 0 else 500)
 
+    # the four GCG workspaces are created before the clock starts, as in the reference's driver
+    # (test/test_eig_sol_gcg.c:57-68 allocates gcg_mv_ws[0..3] ahead of `time_start`, :88)
+    ws = api.gcg_workspace(n, prm)
     for _ in range(a.warmup):
-        out = solve(A, B)
+        out = solve(A, B, ws)
     # ---- timed region: K solves, matrices resident ---------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -223,7 +229,7 @@ def run_b200(a) -> int:
     api.timer_start()
     w0 = time.time()
     for _ in range(a.steps):
-        out = solve(A, B)
+        out = solve(A, B, ws)
     ms = api.timer_stop()
     barrier()
     wall = time.time() - w0
@@ -238,8 +244,10 @@ def run_b200(a) -> int:
         sec = float(t.item())
     stats = out["stats"]
 
-    # ---- e2e: host CCS arrays -> upload -> solve -> eigenpairs back on the host ------------
+    # ---- e2e: host CCS arrays -> upload -> workspaces -> solve -> eigenpairs back on the host
     A.close(); B.close()
+    for w in ws:
+        w.close()
     nev_out = a.nev
     _, nloc = evec.local_range()
     host_vec = np.zeros((nloc, nev_out), order="F")          # this rank's rows of the eigenvectors
@@ -260,7 +268,7 @@ def run_b200(a) -> int:
         t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = float(t.item())
-    h2d = sum(h.nbytes for h in host_arrays)
+    h2d = sum(h.nbytes for h in host_arrays) * world      # every rank receives the whole CCS and cuts out its slab on the device
     d2h = 8 * n * nev_out + 8 * prm.nevMax            # all ranks together
 
     if rank != 0:
@@ -281,7 +289,8 @@ def run_b200(a) -> int:
     classes = {k: {"ms": round(v["ms"] / a.steps, 3), "calls": v["calls"] // a.steps,
                    "share": round(v["ms"] / tot_ms, 4),
                    "GBs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 else None,
-                   "TFs": round(v["flops"] / v["ms"] / 1e9, 2) if v["ms"] > 0 else None}
+                   "TFs": round(v["flops"] / v["ms"] / 1e9, 2) if v["ms"] > 0 else None,
+                   "gap_before_ms": round(v.get("gap_before_ms", 0.0) / a.steps, 3)}
                for k, v in prof.items()}
     top = max(prof, key=lambda k: prof[k]["ms"])
     tv = prof[top]

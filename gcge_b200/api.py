@@ -155,7 +155,10 @@ def prof_report() -> dict:
     for c in range(lib().b200_prof_classes()):
         name = C.c_char_p(); ms = C.c_double(); calls = C.c_longlong(); by = C.c_double(); fl = C.c_double()
         _chk(lib().b200_prof_get(c, C.byref(name), C.byref(ms), C.byref(calls), C.byref(by), C.byref(fl)))
-        out[name.value.decode()] = {"ms": ms.value, "calls": calls.value, "bytes": by.value, "flops": fl.value}
+        gap = C.c_double()
+        _chk(lib().b200_prof_get_gap(c, C.byref(gap)))
+        out[name.value.decode()] = {"ms": ms.value, "calls": calls.value, "bytes": by.value, "flops": fl.value,
+                                    "gap_before_ms": gap.value}
     return out
 
 
@@ -405,8 +408,15 @@ def default_params(nev: int) -> GCGParams:
     return p
 
 
+def gcg_workspace(n: int, p) -> list:
+    """The four multi-vector workspaces of EigenSolverSetup_GCG (reference
+    test/test_eig_sol_gcg.c:57-68: nevMax + 2 block_size, block_size, block_size, block_size
+    columns), created by the caller before the solve like the reference's driver does."""
+    return [MultiVec(n, p.nevMax + 2 * p.block_size)] + [MultiVec(n, p.block_size) for _ in range(3)]
+
+
 def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=None, max_iter=0, verbose=False,
-              evec=None, seed=0, **overrides):
+              evec=None, seed=0, ws=None, **overrides):
     """slot EigenSolver (reference src/ops.h:146-147) through b200_gcg_solve, with the driver
     defaults of reference test/test_eig_sol_gcg.c:33-115.  ``A``/``B`` are :class:`Mat`.
     Seeds glibc rand() like the reference driver unless seed is None."""
@@ -434,8 +444,11 @@ def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=None, 
     ev = np.zeros(p.nevMax)
     nconv = C.c_int(nev)
     st = _GCGStats()
+    ws_c = None
+    if ws is not None:
+        ws_c = (C.c_void_p * 4)(*[w.h for w in ws])
     _chk(lib().b200_gcg_solve(A.h, None if B is None else B.h, _dp(ev), evec.h, 0, C.byref(nconv), C.byref(p),
-                              None, C.byref(st)))
+                              ws_c, C.byref(st)))
     out = {"eval": ev, "num_iter": st.numIter, "nev_conv": nconv.value, "evec_mv": evec,
            "stats": {k: getattr(st, k) for k, _ in _GCGStats._fields_}}
     return out

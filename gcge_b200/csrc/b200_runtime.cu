@@ -207,6 +207,7 @@ struct ProfState {
 	std::vector<ProfRec> pend;          // recorded, not yet resolved
 	std::vector<cudaEvent_t> pool;      // free events
 	double ms[B200_PROF_NCLS] = {}, bytes[B200_PROF_NCLS] = {}, flops[B200_PROF_NCLS] = {};
+	double gap_ms[B200_PROF_NCLS] = {};  // stream time between the previous scope's end and this scope's start
 	long long calls[B200_PROF_NCLS] = {};
 } g_prof;
 const char *g_prof_names[B200_PROF_NCLS] = {"spmm", "gram", "lincomb", "axpby", "dots", "bpcg_fused",
@@ -222,9 +223,14 @@ void prof_resolve()
 {
 	if (g_prof.pend.empty()) return;
 	cudaEventSynchronize(g_prof.pend.back().b);
-	for (const ProfRec &r : g_prof.pend) {
+	for (size_t i = 0; i < g_prof.pend.size(); ++i) {
+		const ProfRec &r = g_prof.pend[i];
 		float f = 0.f;
 		if (cudaEventElapsedTime(&f, r.a, r.b) == cudaSuccess) g_prof.ms[r.cls] += f;
+		// what ran (or idled) on the stream between two scopes: unclassified kernels, copies, NCCL, host latency
+		if (i > 0 && cudaEventElapsedTime(&f, g_prof.pend[i - 1].b, r.a) == cudaSuccess) g_prof.gap_ms[r.cls] += f;
+	}
+	for (const ProfRec &r : g_prof.pend) {
 		g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b);
 	}
 	g_prof.pend.clear();
@@ -256,7 +262,7 @@ extern "C" int b200_prof_enable(int on)
 	B200_REQUIRE_INIT();
 	prof_resolve();
 	if (on) {
-		for (int i = 0; i < B200_PROF_NCLS; ++i) { g_prof.ms[i] = g_prof.bytes[i] = g_prof.flops[i] = 0.0; g_prof.calls[i] = 0; }
+		for (int i = 0; i < B200_PROF_NCLS; ++i) { g_prof.ms[i] = g_prof.bytes[i] = g_prof.flops[i] = g_prof.gap_ms[i] = 0.0; g_prof.calls[i] = 0; }
 	}
 	g_prof.on = on != 0;
 	return 0;
@@ -273,6 +279,16 @@ extern "C" int b200_prof_get(int cls, const char **name, double *ms, long long *
 	if (calls) *calls = g_prof.calls[cls];
 	if (bytes) *bytes = g_prof.bytes[cls];
 	if (flops) *flops = g_prof.flops[cls];
+	return 0;
+}
+
+// stream time that elapsed between the end of the previous profiled call and the start of the
+// calls of class `cls`: kernels outside the classes, copies, collectives, and idle stream time
+extern "C" int b200_prof_get_gap(int cls, double *ms)
+{
+	B200_CHECK(cls >= 0 && cls < B200_PROF_NCLS && ms, "b200_prof_get_gap: bad arguments");
+	prof_resolve();
+	*ms = g_prof.gap_ms[cls];
 	return 0;
 }
 

@@ -64,6 +64,9 @@ int  b200_host_unregister(void *host);
 int  b200_prof_enable(int on);
 int  b200_prof_classes(void);
 int  b200_prof_get(int cls, const char **name, double *ms, long long *calls, double *bytes, double *flops);
+/* stream time between the end of the previous profiled call and the start of the calls of class cls
+ * (unclassified kernels, copies, collectives, idle time): where the step's time outside the classes goes */
+int  b200_prof_get_gap(int cls, double *ms);
 
 /* ---- several GPUs: one process per GPU, 1-D contiguous row blocks -----------
  * The scheme of the reference's MPI back ends (every rank owns a row slab of A, B and of
