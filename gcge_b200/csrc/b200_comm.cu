@@ -13,6 +13,7 @@
 // by whatever it has (torch.distributed in bench.py / tests), every rank calls b200_comm_init().
 #include "b200_internal.h"
 #include <dlfcn.h>
+#include <vector>
 
 namespace {
 
@@ -25,6 +26,7 @@ struct NcclApi {
 	int (*GetUniqueId)(nccl_uid *) = nullptr;
 	int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
 	int (*CommDestroy)(nccl_comm) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
 	int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
 	int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
 	int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
@@ -51,9 +53,12 @@ int load_nccl()
 		*(void **)(&g_nccl.field) = dlsym(g_nccl.handle, sym);                  \
 		if (!g_nccl.field) return b200_fail("NCCL: symbol %s missing", sym);    \
 	} while (0)
+#define LOAD2(field, sym) LOAD(field, sym)
 	LOAD(GetUniqueId, "ncclGetUniqueId"); LOAD(CommInitRank, "ncclCommInitRank"); LOAD(CommDestroy, "ncclCommDestroy");
 	LOAD(AllReduce, "ncclAllReduce"); LOAD(Send, "ncclSend"); LOAD(Recv, "ncclRecv");
 	LOAD(GroupStart, "ncclGroupStart"); LOAD(GroupEnd, "ncclGroupEnd"); LOAD(GetErrorString, "ncclGetErrorString");
+	LOAD2(AllGather, "ncclAllGather");
+#undef LOAD2
 #undef LOAD
 	return 0;
 }
@@ -65,6 +70,8 @@ int load_nccl()
 	} while (0)
 
 }  // namespace
+
+namespace { void p2p_release(); }
 
 extern "C" int b200_comm_unique_id(char *id128)
 {
@@ -87,6 +94,14 @@ extern "C" int b200_comm_init(int rank, int nranks, const char *id128)
 	nccl_uid u; memcpy(u.internal, id128, 128);
 	B200_NCCL(g_nccl.CommInitRank(&g_comm, nranks, u, rank));
 	g_b200.rank = rank; g_b200.nranks = nranks;
+	// side stream for the SpMM halo exchange (copy engines over NVLink, see p2p_* below), so that it
+	// overlaps the interior rows of the multiply
+	g_b200.comm_stream = nullptr;
+	if (!getenv("B200_NO_OVERLAP")) {
+		B200_CUDA(cudaStreamCreateWithFlags(&g_b200.comm_stream, cudaStreamNonBlocking));
+		B200_CUDA(cudaEventCreateWithFlags(&g_b200.ev_x_ready, cudaEventDisableTiming));
+		B200_CUDA(cudaEventCreateWithFlags(&g_b200.ev_halo_done, cudaEventDisableTiming));
+	}
 	return 0;
 }
 
@@ -94,6 +109,13 @@ extern "C" int b200_comm_finalize(void)
 {
 	if (g_comm) {
 		cudaStreamSynchronize(g_b200.stream);
+		if (g_b200.comm_stream) {
+			cudaStreamSynchronize(g_b200.comm_stream);
+			p2p_release();
+			cudaStreamDestroy(g_b200.comm_stream);
+			cudaEventDestroy(g_b200.ev_x_ready); cudaEventDestroy(g_b200.ev_halo_done);
+			g_b200.comm_stream = nullptr;
+		}
 		g_nccl.CommDestroy(g_comm);
 		g_comm = nullptr;
 	}
@@ -144,6 +166,215 @@ int b200k_neighbor_exchange(int nnbr, const int *nbr, const double *send_dev, co
 		if (recv_cnt[i]) B200_NCCL(g_nccl.Recv(recv_dev + recv_off[i], recv_cnt[i], NCCL_FLOAT64, nbr[i], g_comm, g_b200.stream));
 	}
 	B200_NCCL(g_nccl.GroupEnd());
+	B200_LAUNCHED();
+	return 0;
+}
+
+// ================================================================ halo exchange by copy engines
+// The slab neighbours' halo rows over NVLink WITHOUT kernels: a peer-to-peer 2-D copy
+// (cudaMemcpy2DAsync into the neighbour's IPC-mapped mailbox) and stream memory operations
+// (cuStreamWriteValue32 / cuStreamWaitValue32 on IPC-mapped flags) for the hand-shake.  Nothing of
+// it needs an SM, so it runs underneath the persistent SpMM CTAs working on the interior rows --
+// an NCCL send/recv kernel on a side stream would simply queue behind them.
+//
+//   sender s -> receiver r, message e (the e-th exchange of the process; all ranks count alike):
+//     s: wait  s.free[r]    >= e-1      r has unpacked my previous message
+//        copy  x rows -> r.mailbox[slot of s]        (2-D: k*8 bytes wide, pitch ldx*8 -> k*8)
+//        write r.arrived[s] =  e
+//     r: wait  r.arrived[s] >= e
+//        copy  r.mailbox[slot of s] -> halo rows of x
+//        write s.free[r]    =  e
+//
+// Applies to banded matrices split into slabs whose halos come from the two adjacent ranks only
+// (stencils, FEM on lattices): slot 0 = the rank below, slot 1 = the rank above.  Everything else
+// uses the NCCL exchange above on the library stream.
+#include <cuda.h>
+namespace {
+typedef CUresult (*stream_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct P2P {
+	bool ok = false;
+	size_t region_bytes = 0;            // per slot
+	double *mailbox = nullptr;          // 2 regions
+	unsigned *flags = nullptr;          // [0..1] arrived from below / above, [2..3] free of below / above
+	double *peer_mailbox[2] = {nullptr, nullptr};     // below, above
+	unsigned *peer_flags[2] = {nullptr, nullptr};
+	unsigned epoch = 0;
+	stream_value32_fn wait32 = nullptr, write32 = nullptr;
+} g_p2p;
+
+void p2p_release()
+{
+	for (int i = 0; i < 2; ++i) {
+		if (g_p2p.peer_mailbox[i]) cudaIpcCloseMemHandle(g_p2p.peer_mailbox[i]);
+		if (g_p2p.peer_flags[i]) cudaIpcCloseMemHandle(g_p2p.peer_flags[i]);
+		g_p2p.peer_mailbox[i] = nullptr; g_p2p.peer_flags[i] = nullptr;
+	}
+	if (g_p2p.mailbox) cudaFree(g_p2p.mailbox);
+	if (g_p2p.flags) cudaFree(g_p2p.flags);
+	g_p2p.mailbox = nullptr; g_p2p.flags = nullptr; g_p2p.region_bytes = 0; g_p2p.ok = false; g_p2p.epoch = 0;
+	cudaGetLastError();
+}
+
+bool p2p_resolve_driver()
+{
+	if (g_p2p.wait32 && g_p2p.write32) return true;
+	void *a = nullptr, *b = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &a, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+	if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &b, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+	g_p2p.wait32 = (stream_value32_fn)a; g_p2p.write32 = (stream_value32_fn)b;
+	return true;
+}
+}  // namespace
+
+// Collective (called by every rank while it creates a row-partitioned matrix): make sure the mailbox
+// holds `rows` halo rows of 64 columns per neighbour; (re)allocates and re-exchanges the IPC handles
+// when some rank needs more.  rows < 0: this rank cannot take the matrix through the mailboxes (its
+// halos are not the two adjacent slabs, no diagonal image) -- then no rank does (*all_ranks_ok = 0)
+// and an existing registration stays as it is.  Failure is not an error: the NCCL exchange stays.
+int b200k_p2p_register(int rows, int *all_ranks_ok)
+{
+	*all_ranks_ok = 0;
+	if (g_b200.nranks <= 1 || !g_comm || !g_b200.comm_stream || getenv("B200_NO_P2P")) return 0;
+	cudaStream_t st = g_b200.stream;
+	// global maximum of the rows needed
+	double *dmax = (double *)b200_scratch(8, 256);
+	if (!dmax) return 1;
+	// max through a sum of one-hot slots would need nranks entries; use nranks doubles and gather
+	std::vector<double> all((size_t)g_b200.nranks, 0.0);
+	{
+		double mine = (double)rows;
+		double *dall = (double *)b200_scratch(8, sizeof(double) * ((size_t)g_b200.nranks + 8));
+		if (!dall) return 1;
+		B200_CUDA(cudaMemsetAsync(dall, 0, sizeof(double) * (size_t)g_b200.nranks, st));
+		B200_CUDA(cudaMemcpyAsync(dall + g_b200.rank, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+		B200_NCCL(g_nccl.AllReduce(dall, dall, (size_t)g_b200.nranks, NCCL_FLOAT64, NCCL_SUM, g_comm, st));
+		B200_CUDA(cudaMemcpyAsync(all.data(), dall, sizeof(double) * (size_t)g_b200.nranks, cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+	}
+	size_t need_rows = 0;
+	bool shapes_ok = true;
+	for (double v : all) {
+		if (v < 0.0) shapes_ok = false;            // some rank cannot take this matrix through the mailboxes
+		else if ((size_t)v > need_rows) need_rows = (size_t)v;
+	}
+	if (!shapes_ok) return 0;
+	const size_t need = need_rows * 64 * sizeof(double);
+	if (need == 0) return 0;
+	if (g_p2p.ok && need <= g_p2p.region_bytes) { *all_ranks_ok = 1; return 0; }
+	if (!p2p_resolve_driver()) return 0;
+	// (re)build: every rank gets here together
+	B200_CUDA(cudaStreamSynchronize(g_b200.comm_stream));
+	p2p_release();
+	if (cudaMalloc(&g_p2p.mailbox, 2 * need) != cudaSuccess || cudaMalloc(&g_p2p.flags, 256) != cudaSuccess) {
+		cudaGetLastError(); p2p_release();
+	}
+	int good = (g_p2p.mailbox && g_p2p.flags) ? 1 : 0;
+	struct Handles { cudaIpcMemHandle_t mb, fl; int good; int pad[3]; };
+	Handles mine; memset(&mine, 0, sizeof(mine));
+	if (good) {
+		B200_CUDA(cudaMemsetAsync(g_p2p.flags, 0, 256, st));
+		if (cudaIpcGetMemHandle(&mine.mb, g_p2p.mailbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.fl, g_p2p.flags) != cudaSuccess) {
+			cudaGetLastError(); good = 0;
+		}
+	}
+	mine.good = good;
+	const size_t hb = sizeof(Handles);
+	char *dh = (char *)b200_scratch(8, hb * ((size_t)g_b200.nranks + 1));
+	if (!dh) return 1;
+	std::vector<Handles> hs((size_t)g_b200.nranks);
+	B200_CUDA(cudaMemcpyAsync(dh + hb * g_b200.nranks, &mine, hb, cudaMemcpyHostToDevice, st));
+	B200_NCCL(g_nccl.AllGather(dh + hb * g_b200.nranks, dh, hb, NCCL_INT8, g_comm, st));
+	B200_CUDA(cudaMemcpyAsync(hs.data(), dh, hb * g_b200.nranks, cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	bool all_good = true;
+	for (const Handles &h : hs) all_good = all_good && h.good;
+	if (all_good) {
+		const int nb[2] = {g_b200.rank - 1, g_b200.rank + 1};
+		for (int i = 0; i < 2 && all_good; ++i) {
+			if (nb[i] < 0 || nb[i] >= g_b200.nranks) continue;
+			void *pm = nullptr, *pf = nullptr;
+			if (cudaIpcOpenMemHandle(&pm, hs[nb[i]].mb, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+			    cudaIpcOpenMemHandle(&pf, hs[nb[i]].fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+				cudaGetLastError(); all_good = false; break;
+			}
+			g_p2p.peer_mailbox[i] = (double *)pm; g_p2p.peer_flags[i] = (unsigned *)pf;
+		}
+	}
+	// a rank that failed to map a peer must stop everybody from using the path
+	{
+		double flag = all_good ? 0.0 : 1.0;
+		double *df = (double *)b200_scratch(8, 256);
+		B200_CUDA(cudaMemcpyAsync(df, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+		B200_NCCL(g_nccl.AllReduce(df, df, 1, NCCL_FLOAT64, NCCL_SUM, g_comm, st));
+		B200_CUDA(cudaMemcpyAsync(&flag, df, sizeof(double), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		all_good = (flag == 0.0);
+	}
+	if (!all_good) { p2p_release(); return 0; }
+	g_p2p.region_bytes = need; g_p2p.ok = true; g_p2p.epoch = 0;
+	*all_ranks_ok = 1;
+	return 0;
+}
+
+// 1 when M's halo exchange can go through the mailboxes (same answer on every rank for a given matrix:
+// the plan is symmetric -- what I receive from a neighbour it sends to me)
+int b200k_p2p_usable(const b200_mat *M, int k)
+{
+	if (!g_p2p.ok || !M->p2p_ok || !M->halo_contiguous || k > 64 || M->nnbr < 1 || M->nnbr > 2) return 0;
+	for (int i = 0; i < M->nnbr; ++i) {
+		if (M->nbr[i] != g_b200.rank - 1 && M->nbr[i] != g_b200.rank + 1) return 0;
+		const int nrecv = M->recv_off[i + 1] - M->recv_off[i], nsend = M->send_off[i + 1] - M->send_off[i];
+		if ((size_t)nrecv * 64 * sizeof(double) > g_p2p.region_bytes) return 0;
+		// the rows sent must be one contiguous range
+		for (int j = M->send_off[i] + 1; j < M->send_off[i + 1]; ++j)
+			if (M->send_rows[j] != M->send_rows[j - 1] + 1) return 0;
+		(void)nsend;
+	}
+	return 1;
+}
+
+#define B200_CU(call)                                                                            \
+	do {                                                                                         \
+		CUresult r_ = (call);                                                                    \
+		if (r_ != CUDA_SUCCESS) return b200_fail("%s:%d %s: CUresult %d", __FILE__, __LINE__, #call, (int)r_); \
+	} while (0)
+
+// Enqueue the exchange of the k-column block x (window layout: halo rows in front of and behind the
+// local rows) on the comm stream, after everything the library stream has enqueued so far; the
+// caller makes the library stream wait for g_b200.ev_halo_done before it touches the halo rows.
+int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
+{
+	cudaStream_t cs = g_b200.comm_stream;
+	B200_CUDA(cudaEventRecord(g_b200.ev_x_ready, g_b200.stream));
+	B200_CUDA(cudaStreamWaitEvent(cs, g_b200.ev_x_ready, 0));
+	const unsigned e = ++g_p2p.epoch;
+	const size_t width = (size_t)k * sizeof(double);
+	// sends
+	for (int i = 0; i < M->nnbr; ++i) {
+		const int side = (M->nbr[i] < g_b200.rank) ? 0 : 1;           // the neighbour is below / above me
+		const int nsend = M->send_off[i + 1] - M->send_off[i];
+		if (nsend <= 0) continue;
+		// at the neighbour I am the rank above (slot 1) if it is below me, and the other way round
+		const int my_slot_there = 1 - side;
+		if (e > 1) B200_CU(g_p2p.wait32((CUstream)cs, (CUdeviceptr)(g_p2p.flags + 2 + side), e - 1, CU_STREAM_WAIT_VALUE_GEQ));
+		double *dst = (double *)((char *)g_p2p.peer_mailbox[side] + (size_t)my_slot_there * g_p2p.region_bytes);
+		const double *src = x + (size_t)M->send_rows[M->send_off[i]] * ldx;
+		B200_CUDA(cudaMemcpy2DAsync(dst, width, src, (size_t)ldx * sizeof(double), width, (size_t)nsend, cudaMemcpyDeviceToDevice, cs));
+		B200_CU(g_p2p.write32((CUstream)cs, (CUdeviceptr)(g_p2p.peer_flags[side] + my_slot_there), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+	}
+	// receives
+	for (int i = 0; i < M->nnbr; ++i) {
+		const int side = (M->nbr[i] < g_b200.rank) ? 0 : 1;
+		const int nrecv = M->recv_off[i + 1] - M->recv_off[i];
+		if (nrecv <= 0) continue;
+		B200_CU(g_p2p.wait32((CUstream)cs, (CUdeviceptr)(g_p2p.flags + side), e, CU_STREAM_WAIT_VALUE_GEQ));
+		const double *src = (const double *)((const char *)g_p2p.mailbox + (size_t)side * g_p2p.region_bytes);
+		double *dst = (side == 0) ? x - (size_t)nrecv * ldx : x + (size_t)M->nrows * ldx;
+		B200_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldx * sizeof(double), src, width, width, (size_t)nrecv, cudaMemcpyDeviceToDevice, cs));
+		B200_CU(g_p2p.write32((CUstream)cs, (CUdeviceptr)(g_p2p.peer_flags[side] + 2 + (1 - side)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+	}
+	B200_CUDA(cudaEventRecord(g_b200.ev_halo_done, cs));
 	B200_LAUNCHED();
 	return 0;
 }

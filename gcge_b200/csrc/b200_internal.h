@@ -29,6 +29,11 @@ struct b200_ctx {
 	char err[512];
 	// multi-GPU layout (b200_comm.cu): rank of this process, number of ranks (0/1 = single GPU)
 	int rank, nranks;
+	// halo exchange off the critical path: a second stream driven by copy engines and stream memory
+	// operations only (b200_comm.cu), and the two events that tie it to the library stream;
+	// comm_stream == nullptr: exchanges run on the library stream through NCCL
+	cudaStream_t comm_stream;
+	cudaEvent_t ev_x_ready, ev_halo_done;
 	// halo rows a multi-vector with n global rows must be able to hold behind its local rows:
 	// the largest halo of any matrix with that many columns created so far
 	long long halo_n[8];
@@ -38,6 +43,10 @@ struct b200_ctx {
 int b200k_allreduce_sum(double *buf_dev, size_t count);
 int b200k_neighbor_exchange(int nnbr, const int *nbr, const double *send_dev, const size_t *send_off,
                             const size_t *send_cnt, double *recv_dev, const size_t *recv_off, const size_t *recv_cnt);
+// halo exchange by copy engines on the comm stream (b200_comm.cu)
+int b200k_p2p_register(int rows, int *all_ranks_ok);
+int b200k_p2p_usable(const b200_mat *M, int k);
+int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k);
 
 extern b200_ctx g_b200;
 static inline bool b200_multi() { return g_b200.nranks > 1; }

@@ -295,6 +295,19 @@ void b200_note_halo_capacity(long long n_global, int nhalo)
 	}
 }
 
+// collective: size the halo mailboxes of the copy-engine exchange for this matrix (b200_comm.cu)
+static int p2p_register_for(b200_mat *A)
+{
+	int rows = 0;
+	bool shape_ok = A->halo_contiguous && A->dia_nd > 0 && A->nnbr <= 2;
+	for (int i = 0; i < A->nnbr && shape_ok; ++i) {
+		if (A->nbr[i] != g_b200.rank - 1 && A->nbr[i] != g_b200.rank + 1) shape_ok = false;
+		const int nr = A->recv_off[i + 1] - A->recv_off[i];
+		if (nr > rows) rows = nr;
+	}
+	return b200k_p2p_register(shape_ok ? rows : -1, &A->p2p_ok);
+}
+
 extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, const int *i_row,
                                         const double *data, b200_mat **out)
 {
@@ -305,7 +318,10 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	{
 		// fast path: the whole construction on the device (b200_matbuild.cu); 2 = not applicable
 		const int rc = b200k_mat_build_device(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A);
-		if (rc == 0) { *out = A; return 0; }
+		if (rc == 0) {
+			if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
+			*out = A; return 0;
+		}
 		if (rc == 1) { free(A); return 1; }
 		memset(A, 0, sizeof(*A));
 	}
@@ -345,6 +361,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	const int rc_dia = dia_build(A, rp, ci, va, nranks);
 	free(rp); free(ci); free(va);
 	if (rc_dia) { b200_mat_destroy(A); return 1; }
+	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
 	*out = A;
 	return 0;
 }

@@ -630,6 +630,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 
 constexpr int DIA2_MAX_NS = 8;                         // deepest tile ring
 
+// The CTAs walk the row blocks blk(idx) = blk_base + idx + (idx >= blk_split ? blk_skip : 0), idx <
+// nblocks: all blocks, only the interior ones (whose x rows are all local) or only the boundary ones
+// (the two ends of the slab) -- several ranks multiply the interior while the halo rows travel.
 // k = 2 KP CP columns; NT consumer threads (NT / 32 warps) + one producer warp; a row group is KP
 // consecutive threads and owns RB consecutive rows; lane gl of a group owns the column pairs
 // gl, gl + KP, ... (so every 128-bit request of a warp covers one contiguous piece of an x row).
@@ -637,7 +640,8 @@ template <int KP, int CP, int RB, int NT, bool DOT>
 __global__ void __launch_bounds__(NT + 32)
 spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblocks, int nd, const int *__restrict__ off,
                    const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes, int NS,
-                   const double *x, int ldx, double *y, int ldy, const int *__restrict__ gate, double *dot_part)
+                   const double *x, int ldx, double *y, int ldy, const int *__restrict__ gate, double *dot_part,
+                   int blk_base, int blk_split, int blk_skip)
 {
 	if (gate != nullptr && *gate == 0) return;
 	constexpr int K = 2 * KP * CP;
@@ -667,7 +671,8 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 		if (threadIdx.x == NT) {
 			int slot = 0; unsigned phase = 0;
 			for (int lb = 0; lb < my_blocks; ++lb) {
-				const int blk = blockIdx.x + lb * gridDim.x;
+				const int idx = blockIdx.x + lb * gridDim.x;
+				const int blk = blk_base + idx + (idx >= blk_split ? blk_skip : 0);
 				mbar_spin(vempty + (lb & 1), (unsigned)(((lb >> 1) & 1) ^ 1));
 				mbar_expect_tx(vfull + (lb & 1), val_bytes);
 				// the image is padded behind its last row (b200_mat.cu): full-size copies stay in bounds
@@ -716,7 +721,8 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 		__syncwarp();
 		if (lane == 0) mbar_arrive(vempty + (lb & 1));         // ... and with the block's values
 		if (live) {
-			const long long r0 = ((long long)blockIdx.x + (long long)lb * gridDim.x) * ROWS + lr0;
+			const int idx = blockIdx.x + lb * gridDim.x;
+			const long long r0 = (long long)(blk_base + idx + (idx >= blk_split ? blk_skip : 0)) * ROWS + lr0;
 #pragma unroll
 			for (int i = 0; i < RB; ++i) {
 				if (r0 + i < nrows) {
@@ -762,9 +768,10 @@ static int env_int(const char *name, int dflt)
 }
 
 // returns 0 launched, 1 error, 2 not applicable; *nparts = number of per-CTA dot partials written
+// mode 0: every row block; 1: interior blocks (no halo row needed); 2: the boundary blocks
 template <int KP, int CP, int RB, int NT, bool DOT>
 static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
-                              double *dot_part, int dot_cap, int *nparts)
+                              double *dot_part, int dot_cap, int *nparts, int mode)
 {
 	constexpr int K = 2 * KP * CP;
 	constexpr int ROWS = (NT / KP) * RB;
@@ -801,7 +808,19 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 		B200_CUDA(cudaFuncSetAttribute(spmm_dia_ws_kernel<KP, CP, RB, NT, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr_set = true;
 	}
-	const int nblocks = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
+	const int nblocks_all = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
+	int nblocks = nblocks_all, blk_base = 0, split = 0x7fffffff, skip = 0;
+	if (mode != 0) {
+		// block b needs halo rows iff b*ROWS < halo_below or (b+1)*ROWS + halo_above > nrows
+		const int ha = M->nhalo - hb;
+		int b_lo = (hb + ROWS - 1) / ROWS, b_hi = (M->nrows - ha) / ROWS;
+		if (b_lo > nblocks_all) b_lo = nblocks_all;
+		if (b_hi < b_lo) b_hi = b_lo;
+		if (mode == 1) { blk_base = b_lo; nblocks = b_hi - b_lo; }
+		else { split = b_lo; skip = b_hi - b_lo; nblocks = b_lo + (nblocks_all - b_hi); }
+	}
+	if (DOT) *nparts = 0;
+	if (nblocks <= 0) return 0;
 	int per_sm = (int)((224 * 1024) / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
 	int grid = g_b200.num_sms * per_sm; if (grid > nblocks) grid = nblocks;
 	if (DOT) {
@@ -809,7 +828,7 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 		*nparts = grid;
 	}
 	spmm_dia_ws_kernel<KP, CP, RB, NT, DOT><<<grid, NT + 32, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off,
-		M->dia_val, ng, M->dia_grp, hb, tile_bytes, NS, x, ldx, y, ldy, gate, dot_part);
+		M->dia_val, ng, M->dia_grp, hb, tile_bytes, NS, x, ldx, y, ldy, gate, dot_part, blk_base, split, skip);
 	B200_KERNEL_CHECK();
 	return 0;
 }
@@ -823,11 +842,20 @@ template <int KP, int NT> struct Dia2Cfg {
 
 template <int KP, int CP, int NT = 256>
 static int launch_spmm_dia_ws_kp(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
-                                 double *dot_part, int dot_cap, int *nparts)
+                                 double *dot_part, int dot_cap, int *nparts, int mode)
 {
 	constexpr int RB = Dia2Cfg<KP, NT>::RB;
-	if (dot_part) return launch_spmm_dia_ws<KP, CP, RB, NT, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts);
-	return launch_spmm_dia_ws<KP, CP, RB, NT, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr);
+	if (dot_part) return launch_spmm_dia_ws<KP, CP, RB, NT, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
+	return launch_spmm_dia_ws<KP, CP, RB, NT, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
+}
+
+static bool dia_ws_has(int k)
+{
+	switch (k) {
+	case 8: case 10: case 12: case 16: case 20: case 24: case 30: case 32: case 40: case 48: case 50: case 56: case 60: case 64:
+		return getenv("B200_SPMM_OLD_DIA") == nullptr;
+	default: return false;
+	}
 }
 
 // The block widths with a compile-time kernel; anything else takes the generic kernel above.
@@ -835,10 +863,10 @@ static int launch_spmm_dia_ws_kp(const b200_mat *M, const double *x, int ldx, do
 // (n = 1 M P1-FEM, k = 40: 0.204 ms; two pairs per lane 0.226 ms; 4-warp CTAs 0.216 - 0.249 ms;
 // gpurun_out/spmm_variants3.log, summarised in profiles/).
 static int spmm_dia_ws_dispatch(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate,
-                                double *dot_part, int dot_cap, int *nparts)
+                                double *dot_part, int dot_cap, int *nparts, int mode = 0)
 {
 	if (getenv("B200_SPMM_OLD_DIA")) return 2;
-#define WS(KP_) launch_spmm_dia_ws_kp<KP_, 1>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts)
+#define WS(KP_) launch_spmm_dia_ws_kp<KP_, 1>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode)
 	switch (k) {
 	case 8:  return WS(4);
 	case 10: return WS(5);
@@ -962,6 +990,16 @@ static int spmm_csr_local(const b200_mat *M, int trans, const double *x, int ldx
 	return 0;
 }
 
+// several ranks, diagonal image, a width the warp-specialised kernel has, and a halo the mailboxes take
+static bool spmm_overlap_ok(const b200_mat *M, int trans, const double *x, int ldx, const double *y, int ldy, int k)
+{
+	if (!b200_multi() || trans || M->nnbr == 0 || M->dia_nd <= 0 || M->nrows <= 0 || !g_b200.comm_stream) return false;
+	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
+	if (!vec || !dia_ws_has(k)) return false;
+	// the dot partials of the two launches must fit the caller's buffer: at most 4 CTAs per SM each
+	return b200k_p2p_usable(M, k) != 0;
+}
+
 int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y, int ldy, int k,
                const int *gate)
 {
@@ -973,6 +1011,15 @@ int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y
 	}
 	const int nrows = trans ? M->ncols : M->nrows;
 	if (k <= 0) return 0;
+	if (spmm_overlap_ok(M, trans, x, ldx, y, ldy, k)) {
+		// the halo rows travel on the comm stream (copy engines) while the interior blocks multiply
+		if (b200k_p2p_halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
+		B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
+		              2.0 * M->nnz * k);
+		if (spmm_dia_ws_dispatch(M, x, ldx, y, ldy, k, gate, nullptr, 0, nullptr, 1)) return 1;
+		B200_CUDA(cudaStreamWaitEvent(g_b200.stream, g_b200.ev_halo_done, 0));
+		return spmm_dia_ws_dispatch(M, x, ldx, y, ldy, k, gate, nullptr, 0, nullptr, 2) ? 1 : 0;
+	}
 	if (b200_multi() && halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
 	if (nrows <= 0) return 0;
 	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
@@ -1003,6 +1050,17 @@ int b200k_spmm_dot(const b200_mat *M, const double *x, int ldx, double *y, int l
 	if (!(M->dia_nd > 0 && k > 4 && k <= 64 && M->nrows > 0) || getenv("B200_NO_FUSED_DOT")) return 2;
 	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
 	if (!vec) return 2;
+	if (spmm_overlap_ok(M, 0, x, ldx, y, ldy, k)) {
+		if (b200k_p2p_halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
+		B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (M->nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
+		              2.0 * M->nnz * k + 2.0 * M->nrows * k);
+		int n1 = 0, n2 = 0;
+		if (spmm_dia_ws_dispatch(M, x, ldx, y, ldy, k, gate, dot_part, dot_cap, &n1, 1)) return 1;
+		B200_CUDA(cudaStreamWaitEvent(g_b200.stream, g_b200.ev_halo_done, 0));
+		if (spmm_dia_ws_dispatch(M, x, ldx, y, ldy, k, gate, dot_part + (size_t)n1 * k, dot_cap - n1, &n2, 2)) return 1;
+		*nparts = n1 + n2;
+		return 0;
+	}
 	if (b200_multi() && halo_exchange(M, const_cast<double *>(x), ldx, k)) return 1;
 	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (M->nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
 	              2.0 * M->nnz * k + 2.0 * M->nrows * k);

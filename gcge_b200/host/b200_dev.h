@@ -47,6 +47,7 @@ struct b200_mat_ {
 	int *send_rows;                   /* host, [send_off[nnbr]] LOCAL row sent to nbr[i], ascending per neighbour */
 	int *send_rows_dev;               /* device copy */
 	long long t_col0;                 /* first CCS column kept in the t_ arrays (== row0) */
+	int p2p_ok;                       /* every rank can exchange this matrix's halos through the copy-engine mailboxes */
 	/* Diagonal image (b200_mat.cu: dia_build), present when the matrix is a sum of at most 32
 	 * diagonals -- stencils and FEM operators on lattices in natural ordering.  The offsets are
 	 * grouped into runs of consecutive values (at most 3 wide); run g starts at the even slot
