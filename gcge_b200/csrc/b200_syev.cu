@@ -32,7 +32,7 @@ namespace cg = cooperative_groups;
 
 constexpr int BJ_B = 16;            // indices per block
 constexpr int BJ_T = 2 * BJ_B;      // order of a pivot matrix
-constexpr int BJ_LD = BJ_T + 1;     // shared-memory row stride (conflict-free column walks)
+constexpr int BJ_LD = BJ_T + 4;     // shared-memory row stride == 4 (mod 16) doubles: two-wavefront DMMA fragment loads
 constexpr int BJ_TILE = BJ_T * BJ_LD;
 
 // circle method: the two members of pair k in round r of a tournament of N players (N even)
@@ -146,21 +146,34 @@ __device__ int bj_pivot_sweep(double *S0, double *S1, double *Jm, bool full)
 	return total;                                         // > 0 iff any rotation was applied
 }
 
-// D(32 x 32) = op(X) Y with X, Y, D in shared memory (stride BJ_LD); TRANS_X: X^T Y.
-// 256 threads, thread -> row i = tid / 8, columns 4 (tid % 8) .. + 3.
+// D(32 x 32) = op(X) Y with X, Y, D in shared memory (stride BJ_LD); TRANS_X: X^T Y.  On the FP64
+// tensor pipe: 16 output tiles of 8 x 8, two per warp, 8 k-steps of mma.m8n8k4 each (fragment
+// layout as in b200_dense.cu: lane = 4 g + t; a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1]).
+// The first version ran these products on the FMA pipe with scalar shared-memory loads: ~2.3 k
+// cycles each, bound by bank conflicts; here a product is ~48 DMMA issue slots per SM sub-partition.
 template <bool TRANS_X>
 __device__ __forceinline__ void bj_mm(const double *X, const double *Y, double *D)
 {
-	const int i = threadIdx.x >> 3, j0 = (threadIdx.x & 7) * 4;
-	double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-	for (int k = 0; k < BJ_T; ++k) {
-		const double x = TRANS_X ? X[k * BJ_LD + i] : X[i * BJ_LD + k];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = lane >> 2, t = lane & 3;
+	const int tr = warp >> 1, tc = 2 * (warp & 1);
+	double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-		for (int j = 0; j < 4; ++j) acc[j] = fma(x, Y[k * BJ_LD + j0 + j], acc[j]);
+	for (int ks = 0; ks < BJ_T / 4; ++ks) {
+		const int kk = 4 * ks + t;
+		const double a = TRANS_X ? X[kk * BJ_LD + 8 * tr + g] : X[(8 * tr + g) * BJ_LD + kk];
+#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			const double b = Y[kk * BJ_LD + 8 * (tc + j) + g];
+			asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+			             : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+		}
 	}
 #pragma unroll
-	for (int j = 0; j < 4; ++j) D[i * BJ_LD + j0 + j] = acc[j];
+	for (int j = 0; j < 2; ++j) {
+		D[(8 * tr + g) * BJ_LD + 8 * (tc + j) + 2 * t] = c[j][0];
+		D[(8 * tr + g) * BJ_LD + 8 * (tc + j) + 2 * t + 1] = c[j][1];
+	}
 }
 
 // Mg: Np x Np symmetric matrix, Vg: Np x Np accumulated transformations (both row-major, ld Np,
@@ -178,7 +191,7 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 	const int vrb = (Np / BJ_T + 1) / 2;                   // V jobs take two 32-row tiles each
 	const int a_jobs = m * (m - 1) / 2, v_jobs = vrb * m;
 	// where the time goes (block 0's view, clock64 ticks): [0] phase 1, [1] barrier, [2] phase 2, [3] barrier
-	long long cyc[4] = {0, 0, 0, 0}, t_prev = clock64();
+	long long cyc[6] = {0, 0, 0, 0, 0, 0}, t_prev = clock64();     // [4], [5]: tile load / rotations inside phase 1
 	auto lap = [&](int slot) { const long long t = clock64(); cyc[slot] += t - t_prev; t_prev = t; };
 	int sweep = 0;
 	for (; sweep < max_sweeps; ++sweep) {
@@ -191,7 +204,9 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 					T0[r * BJ_LD + c] = Mg[(size_t)bj_glob(r, P, Q) * Np + bj_glob(c, P, Q)];
 				}
 				__syncthreads();
+				const long long t_a = clock64();
 				const int cnt = bj_pivot_sweep(T0, T1, T2, R == 0);
+				cyc[4] += t_a - t_prev; cyc[5] += clock64() - t_a;
 				if (cnt > 0) {
 					for (int i = tid; i < BJ_T * BJ_T; i += 256) {
 						const int r = i >> 5, c = i & 31;
@@ -310,7 +325,7 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 	}
 	if (gtid == 0) {
 		*sweeps_out = sweep;
-		for (int i = 0; i < 4; ++i) cycles[i] = cyc[i];
+		for (int i = 0; i < 6; ++i) cycles[i] = cyc[i];
 	}
 }
 
@@ -335,11 +350,11 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 	const int Np = NB * BJ_B, m = NB / 2;
 	const size_t nn = (size_t)Np * Np;
 	const size_t dbl = 2 * nn + (size_t)m * BJ_T * BJ_T;
-	char *base = (char *)b200_scratch(5, sizeof(double) * (dbl + 4) + sizeof(int) * ((size_t)m + Np + 8));
+	char *base = (char *)b200_scratch(5, sizeof(double) * (dbl + 8) + sizeof(int) * ((size_t)m + Np + 8));
 	if (!base) return 1;
 	double *Mg = (double *)base, *Vg = Mg + nn, *jbuf = Vg + nn;
 	long long *cycles = (long long *)(jbuf + (size_t)m * BJ_T * BJ_T);
-	int *nrot = (int *)(cycles + 4), *rank_of = nrot + m, *ctr = rank_of + Np;
+	int *nrot = (int *)(cycles + 8), *rank_of = nrot + m, *ctr = rank_of + Np;
 	B200_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), st));
 	syev_init_kernel<<<b200_ceil_div((long long)Np * Np, 256), 256, 0, st>>>(n, Np, a_dev, lda, Mg, Vg);
 	B200_KERNEL_CHECK();
@@ -361,10 +376,10 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 		if (b200k_d2h(sweeps_host, sw, sizeof(int))) return 1;
 	}
 	if (getenv("B200_SYEV_PROF")) {
-		long long cyc[4];
+		long long cyc[6];
 		if (b200k_d2h(cyc, cycles, sizeof(cyc))) return 1;
-		fprintf(stderr, "syev n=%d grid=%d clock64 ticks: phase1 %lld barrier %lld phase2 %lld barrier %lld\n", n, blocks,
-		        cyc[0], cyc[1], cyc[2], cyc[3]);
+		fprintf(stderr, "syev n=%d grid=%d clock64 ticks: phase1 %lld (tile load %lld, rotations %lld) barrier %lld phase2 %lld barrier %lld\n",
+		        n, blocks, cyc[0], cyc[4], cyc[5], cyc[1], cyc[2], cyc[3]);
 	}
 	return 0;
 }

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdio.h>
 #include "b200_dev.h"
 
 #define BPCG_MAX_K 128
@@ -37,7 +38,18 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 		}
 	}
 	if (b200k_bpcg_begin(n, &st, b, ldb, r, ldr, prm->tol, prm->tol_type == 1)) return 1;
+	/* B200_BPCG_TRACE=1 (diagnostic, synchronises every iteration): column-iterations really needed
+	 * vs. launched -- how much a compaction of the active columns could save */
+	static int trace = -1;
+	if (trace < 0) trace = getenv("B200_BPCG_TRACE") != NULL;
+	long long act_sum = 0, iters_run = 0;
 	for (int it = 0; it < prm->max_iter; ++it) {
+		if (trace) {
+			int c2[2];
+			if (b200k_d2h(c2, st.counters, sizeof(c2))) return 1;
+			if (c2[0] == 0) break;
+			act_sum += c2[0]; ++iters_run;
+		}
 		if (b200k_bpcg_update_p(n, &st, r, ldr, p, ldp, it == 0)) return 1;
 		if (shift == 0.0) {
 			/* w = A p with p^T w in the SpMM epilogue */
@@ -56,6 +68,8 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 		}
 		if (b200k_bpcg_update_xr(n, &st, p, ldp, w, ldw, x, ldx, r, ldr, prm->rate, prm->tol)) return 1;
 	}
+	if (trace) fprintf(stderr, "bpcg k=%d: %lld iterations, active column-iterations %lld of %lld (%.0f %%)\n", k, iters_run,
+	                   act_sum, iters_run * k, iters_run ? 100.0 * act_sum / (iters_run * k) : 0.0);
 	if (niter || residual) {
 		int counters[2];
 		double res[BPCG_MAX_K];
