@@ -48,7 +48,7 @@ class GCGParams(C.Structure):
                 ("compW_orth_zero_tol", C.c_double),
                 ("compW_cg_max_iter", C.c_int), ("compW_cg_rate", C.c_double), ("compW_cg_tol", C.c_double),
                 ("compW_cg_tol_type", C.c_int), ("compW_cg_auto_shift", C.c_int), ("compW_cg_shift", C.c_double),
-                ("compRR_tol", C.c_double), ("verbose", C.c_int)]
+                ("compRR_tol", C.c_double), ("compW_cg_order", C.c_int), ("verbose", C.c_int)]
 
 
 class _GCGStats(C.Structure):
@@ -174,6 +174,27 @@ def measure_dmma_peak() -> float:
     t = C.c_double(0)
     _chk(lib().b200_measure_dmma_peak(C.byref(t)))
     return t.value
+
+
+def read_matrix_market(path: str):
+    """On-disk matrix (MatrixMarket coordinate file) -> problems.CCS, through the library's own reader."""
+    from . import problems as P
+    L = lib()
+    L.b200_ccs_read_matrix_market.argtypes = [C.c_char_p, c_int_p, c_int_p, C.POINTER(c_int_p), C.POINTER(c_int_p),
+                                              C.POINTER(c_dbl_p)]
+    L.b200_ccs_free.argtypes = [c_int_p, c_int_p, c_dbl_p]
+    L.b200_ccs_free.restype = None
+    m, n = C.c_int(0), C.c_int(0)
+    jc, ir, da = c_int_p(), c_int_p(), c_dbl_p()
+    _chk(L.b200_ccs_read_matrix_market(str(path).encode(), C.byref(m), C.byref(n), C.byref(jc), C.byref(ir), C.byref(da)))
+    try:
+        j_col = np.ctypeslib.as_array(jc, shape=(n.value + 1,)).copy()
+        nnz = int(j_col[-1])
+        i_row = np.ctypeslib.as_array(ir, shape=(max(nnz, 1),)).copy()[:nnz]
+        data = np.ctypeslib.as_array(da, shape=(max(nnz, 1),)).copy()[:nnz]
+    finally:
+        L.b200_ccs_free(jc, ir, da)
+    return P.CCS(m.value, n.value, j_col.astype(np.int32), i_row.astype(np.int32), data.astype(np.float64))
 
 
 def partition_plan(ccs, rank: int, nranks: int) -> dict:

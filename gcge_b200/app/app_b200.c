@@ -301,6 +301,7 @@ static void GCG_B200(void *A, void *B, double *eval, void **evec, int nevGiven, 
 	p.compW_cg_tol = s->compW_cg_tol; p.compW_cg_tol_type = tol_type_code(s->compW_cg_tol_type);
 	p.compW_cg_auto_shift = s->compW_cg_auto_shift; p.compW_cg_shift = s->compW_cg_shift;
 	p.compRR_tol = s->compRR_tol;
+	p.compW_cg_order = s->compW_cg_order;
 	p.verbose = 1;
 	b200_mv *ws[4];
 	for (int i = 0; i < 4; ++i) ws[i] = MV(s->mv_ws[i]);

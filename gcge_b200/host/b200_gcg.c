@@ -276,6 +276,73 @@ static int compute_w(gcg_t *g, const int *offset)
 	return 0;
 }
 
+/* ---- ComputeW12, reference :697-923 (-gcge_compW_cg_order 2) ----------------------------------------
+ * W = [W1 | W2]: the inner solve for the first half of the unconverged columns (W1), then the
+ * same systems solved again from W1 as the initial guess (W2 = max_iter more CG steps), both kept
+ * in the search space. */
+static int compute_w12(gcg_t *g, const int *offset)
+{
+	const b200_gcg_params *p = g->p;
+	double t0 = tick(g);
+	const double *ev = g->eval_h;
+	double sigma = 0.0;
+	if (p->compW_cg_auto_shift == 1) {          /* reference :707-713 */
+		if (g->sizeC < 3) { const double d = 3 * (ev[1] - ev[0]); sigma = -ev[g->sizeC] + (d > 1 ? d : 1); }
+		else { const double d = ev[g->sizeC] - ev[g->sizeC - 3]; sigma = -ev[g->sizeC] + (d > 1 ? d : 1); }
+	}
+	sigma += p->compW_cg_shift;
+	int total = 0;
+	for (int b = 0; b < offset[0]; ++b) total += offset[b * 2 + 2] - offset[b * 2 + 1];
+	const int half = total / 2;
+	g->startW = g->endP;
+	const int b0 = offset[1];
+	double scal_h[512];
+	/* x = Ritz vectors, b = (lambda + sigma) B x for the first `half` unconverged columns, :744-772 */
+	int acc = 0;
+	for (int b = 0; b < offset[0] && acc < half; ++b) {
+		int len = offset[b * 2 + 2] - offset[b * 2 + 1];
+		if (acc + len >= half) len = half - acc;
+		const int o1 = offset[b * 2 + 1];
+		TRY(b200k_axpby(g->n, len, 1.0, g->ritz->d + o1, g->ritz->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
+		for (int i = 0; i < len; ++i) scal_h[acc + i] = ev[o1 + i] + sigma;
+		acc += len;
+	}
+	TRY(b200k_h2d(g->scal_d, scal_h, sizeof(double) * (size_t)(acc > 0 ? acc : 1)));
+	for (int pass = 0; pass < 2; ++pass) {
+		/* right-hand side from the Ritz vectors in V (X part), stored in the Ritz-vector block; the
+		 * shifted solve uses it as scratch, so it is rebuilt for the second solve (reference :836-858) */
+		if (pass == 0 || (sigma != 0.0 && g->B)) {
+			int a2 = 0;
+			for (int b = 0; b < offset[0] && a2 < half; ++b) {
+				int len = offset[b * 2 + 2] - offset[b * 2 + 1];
+				if (a2 + len >= half) len = half - a2;
+				const int o1 = offset[b * 2 + 1];
+				TRY(spmm_mv(g->B, g->V->d + o1, g->V->ld, g->ritz->d + b0 + a2, g->ritz->ld, g->n, len));
+				TRY(b200k_colscale(g->n, len, g->scal_d + a2, 0, g->ritz->d + b0 + a2, g->ritz->ld));
+				a2 += len;
+			}
+		}
+		if (pass == 1)      /* initial guess of the second solve = the first solution, :800-804 */
+			TRY(b200k_axpby(g->n, acc, 1.0, g->V->d + g->startW, g->V->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
+		double t1 = tick(g);
+		b200_bpcg_params bp;
+		bp.max_iter = p->compW_cg_max_iter; bp.rate = p->compW_cg_rate; bp.tol = p->compW_cg_tol;
+		bp.tol_type = p->compW_cg_tol_type; bp.shift = sigma;
+		int s[2], e[2];
+		s[0] = b0; e[0] = b0 + acc; s[1] = g->startW + pass * acc; e[1] = s[1] + acc;
+		if (acc > 0) TRY(b200_block_pcg(g->A, g->B, g->ritz, g->V, s, e, &bp, g->ws[0], g->ws[1], g->ws[2], NULL, NULL));
+		g->st.linsol += tick(g) - t1;
+	}
+	g->endW = g->startW + 2 * acc;
+	b200_orth_params op;
+	op.block_size = p->compW_orth_block_size; op.max_reorth = p->compW_orth_max_reorth;
+	op.orth_zero_tol = p->compW_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
+	TRY(b200_mv_orth(g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
+	g->sizeW = g->endW - g->startW;
+	g->st.compW += tick(g) - t0;
+	return 0;
+}
+
 void b200_gcg_default_params(int nevConv, b200_gcg_params *p)
 {
 	/* reference test/test_eig_sol_gcg.c:33-115 */
@@ -292,6 +359,7 @@ void b200_gcg_default_params(int nevConv, b200_gcg_params *p)
 	p->compW_cg_max_iter = 30; p->compW_cg_rate = 1e-2; p->compW_cg_tol = 1e-14; p->compW_cg_tol_type = 0;
 	p->compW_cg_auto_shift = 0; p->compW_cg_shift = 0.0;
 	p->compRR_tol = 2 * DBL_EPSILON;
+	p->compW_cg_order = 1;
 	p->verbose = 0;
 }
 
@@ -380,7 +448,8 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 		TRY(b200k_axpby(g->n, g->endX - g->startN, 1.0, g->ritz->d + g->startN, g->ritz->ld, 0.0,
 		                g->V->d + g->startN, g->V->ld));
 		g->st.compX += tick(g) - t0;
-		TRY(compute_w(g, offsetW));
+		if (p->compW_cg_order != 1) TRY(compute_w12(g, offsetW));      /* reference :1451-1456 */
+		else TRY(compute_w(g, offsetW));
 		{ int *tmp = offsetP; offsetP = offsetW; offsetW = tmp; }
 		TRY(rayleigh_ritz(g, *nevConv));
 		TRY(compute_ritz_vec(g));

@@ -68,6 +68,13 @@ int  b200_prof_get(int cls, const char **name, double *ms, long long *calls, dou
  * (unclassified kernels, copies, collectives, idle time): where the step's time outside the classes goes */
 int  b200_prof_get_gap(int cls, double *ms);
 
+/* ---- on-disk matrices ---------------------------------------------------------
+ * MatrixMarket "matrix coordinate real|integer|pattern general|symmetric|skew-symmetric" into CCS
+ * arrays (malloc'ed; release with b200_ccs_free): rows ascending inside every column, symmetric
+ * files expanded to both triangles.  Host only. */
+int  b200_ccs_read_matrix_market(const char *path, int *nrows, int *ncols, int **j_col, int **i_row, double **data);
+void b200_ccs_free(int *j_col, int *i_row, double *data);
+
 /* ---- several GPUs: one process per GPU, 1-D contiguous row blocks -----------
  * The scheme of the reference's MPI back ends (every rank owns a row slab of A, B and of
  * every multi-vector; reference app/app_slepc.c:610-634, app/app_phg.c:292-357,
@@ -219,6 +226,7 @@ typedef struct b200_gcg_params_ {
 	int    compW_cg_max_iter; double compW_cg_rate, compW_cg_tol; int compW_cg_tol_type;
 	int    compW_cg_auto_shift; double compW_cg_shift;
 	double compRR_tol;
+	int    compW_cg_order;      /* 1: ComputeW; 2: ComputeW12 (W = [W1 W2], reference src/ops_eig_sol_gcg.c:697-923) */
 	int    verbose;
 } b200_gcg_params;
 typedef struct b200_gcg_stats_ {

@@ -105,6 +105,58 @@ def test_tierB_through_ops_table_and_live_reference(b200, refmod, drive_b200):
     assert cluster_angles(pen, r["eval"][:k], r["evec"][:, :k], b["evec"][:, :k]) < 1e-5
 
 
+@pytest.mark.parametrize("argv", [
+    ("-gcge_compW_cg_order", 2),                                                   # ComputeW12
+    ("-gcge_initX_orth_method", "bgs", "-gcge_compP_orth_method", "bgs", "-gcge_compW_orth_method", "bgs"),
+    ("-gcge_compW_cg_auto_shift", 1),                                              # A + sigma B through MatAxpby
+    ("-gcge_compW_cg_shift", 3.0),
+])
+def test_tierA_reference_options_over_ops_b200(b200, refmod, drive_b200, argv):
+    """SURVEY 8f rows 1-2 at tier A: the reference's ComputeW12 (order-2 Krylov W,
+    src/ops_eig_sol_gcg.c:697-923), BinaryGramSchmidt / OrthSelfEVP (src/ops_orth.c:122-201,415-640)
+    and the shifted inner solve (MatAxpby slot, :594-625) run UNCHANGED over OPS_B200_Set; same
+    options to the reference on CCS: iteration count within 1, eigenvalues 1e-10."""
+    if drive_b200 is None:
+        pytest.skip("oracle/_ref (reference + driver) not present on this box")
+    pen = P.p1_fem_kuhn(12)
+    r = refmod.gcg_solve(pen.A, pen.B, nev=10, want_evec=False, argv=argv)
+    a = drive_b200(0, pen.A, pen.B, nev=10, argv=argv)
+    assert a["nev_conv"] >= 10
+    assert abs(a["num_iter"] - r["num_iter"]) <= 1, (a["num_iter"], r["num_iter"])
+    k = min(a["nev_conv"], r["nev_conv"])
+    assert rel(a["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+def test_device_gcg_order2_krylov_W(b200, refmod):
+    """Tier B ComputeW12 (b200_gcg.c: compute_w12) against the live reference with
+    -gcge_compW_cg_order 2: eigenvalues 1e-10, iteration count within 2."""
+    pen = P.p1_fem_kuhn(12)
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    o = b200.gcg_solve(A, B, nev=10, compW_cg_order=2)
+    base = b200.gcg_solve(A, B, nev=10)
+    assert o["nev_conv"] >= 10
+    assert rel(o["eval"][:10], base["eval"][:10]) < 1e-9
+    if refmod is not None:
+        r = refmod.gcg_solve(pen.A, pen.B, nev=10, want_evec=False, argv=("-gcge_compW_cg_order", 2))
+        assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
+        k = min(o["nev_conv"], r["nev_conv"])
+        assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+def test_device_gcg_from_matrix_market_files(b200, tmp_path):
+    """On-disk input: pencil written as MatrixMarket, read by the library's reader,
+    solved on device: the same bits in, so the same eigenvalues out."""
+    import scipy.io, scipy.sparse as sp
+    pen = P.p1_fem_kuhn(10)
+    for name, M in (("A", pen.A), ("B", pen.B)):
+        scipy.io.mmwrite(str(tmp_path / f"{name}.mtx"), sp.coo_matrix(M.to_scipy()), symmetry="symmetric", precision=17)
+    Af = b200.read_matrix_market(tmp_path / "A.mtx"); Bf = b200.read_matrix_market(tmp_path / "B.mtx")
+    assert np.array_equal(Af.data, pen.A.data) and np.array_equal(Bf.i_row, pen.B.i_row)
+    o1 = b200.gcg_solve(b200.Mat(Af), b200.Mat(Bf), nev=8)
+    o2 = b200.gcg_solve(b200.Mat(pen.A), b200.Mat(pen.B), nev=8)
+    assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"][:8], o2["eval"][:8])
+
+
 def test_device_gcg_moving_window_and_shift(b200):
     """nevInit < nevMax (reference src/ops_eig_sol_gcg.c:1400-1428) and the shifted inner
     solve (compW_cg_shift, reference :482-492): same eigenvalues as the plain run."""
