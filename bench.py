@@ -302,7 +302,16 @@ def run_b200(a) -> int:
         roof = {"kernel": top, "bound": "hbm", "achieved": tv["bytes"] / tv["ms"] / 1e6, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": hbm_src}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    # DRAM traffic per launch of the class's main kernel from the committed ncu --set full capture
+    # (profiles/ncu_traffic.json), only when this run is the workload the capture was taken on
     roof["traffic"] = None
+    try:
+        tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if tr.get("workload", {}).get("m") == a.m and world == 1 and top in tr:
+            roof["traffic"] = tr[top]["traffic_bytes_per_launch"]
+            roof["traffic_source"] = f'{tr[top]["kernel"]}: {tr[top]["source"]}'
+    except Exception:
+        pass
     roof["launches"] = tv["calls"] // a.steps
     roof["avg_launch_ms"] = tv["ms"] / max(tv["calls"], 1)
     roof["algorithmic_per_launch"] = (tv["flops"] if roof["bound"] == "tensor" else tv["bytes"]) / max(tv["calls"], 1)
