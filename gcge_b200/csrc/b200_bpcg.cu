@@ -103,7 +103,7 @@ __global__ void bpcg_finish_kernel(int phase, int k, b200_bpcg_state st, double 
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b, int ldb, double *__restrict__ r, int ldr,
-                  double tol, int rel, int defer, b200_bpcg_state st)
+                  double tol, int rel, int defer, b200_bpcg_state st, B200ArCtx ar)
 {
 	const StreamThread t = stream_thread<VEC>(g);
 	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
@@ -137,6 +137,7 @@ bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b
 	}
 	if (!stream_reduce_and_elect<VEC, 2>(acc, k, g, t, st.partials, st.tickets)) return;
 	bpcg_store_totals<2>(k, st);
+	if (ar.nranks > 1) stream_allreduce_cta(ar, st.totals, 2 * k);
 	if (!defer) bpcg_scalar_phase(0, k, st, tol, rel, 0.0);
 }
 
@@ -188,7 +189,7 @@ bpcg_update_p_kernel(long long n, int k, StreamGeom g, const double *__restrict_
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, double *__restrict__ w, int ldw,
-                double shift, const double *z, int ldz, int defer, b200_bpcg_state st)
+                double shift, const double *z, int ldz, int defer, b200_bpcg_state st, B200ArCtx ar)
 {
 	if (st.counters[0] == 0) return;
 	const StreamThread t = stream_thread<VEC>(g);
@@ -226,6 +227,7 @@ bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, doub
 	}
 	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
 	bpcg_store_totals<1>(k, st);
+	if (ar.nranks > 1) stream_allreduce_cta(ar, st.totals, k);
 	if (!defer) bpcg_scalar_phase(1, k, st, 0.0, 0, 0.0);
 }
 
@@ -235,7 +237,7 @@ template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
 bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict__ p, int ldp, const double *__restrict__ w,
                       int ldw, double *__restrict__ x, int ldx, double *__restrict__ r, int ldr, double rate, double tol,
-                      int defer, b200_bpcg_state st)
+                      int defer, b200_bpcg_state st, B200ArCtx ar)
 {
 	if (st.counters[0] == 0) return;
 	const StreamThread t = stream_thread<VEC>(g);
@@ -284,10 +286,19 @@ bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict
 	}
 	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, st.partials, st.tickets)) return;
 	bpcg_store_totals<1>(k, st);
+	if (ar.nranks > 1) stream_allreduce_cta(ar, st.totals, k);
 	if (!defer) bpcg_scalar_phase(2, k, st, tol, 0, rate);
 }
 
 // ------------------------------------------------------------------------- launchers
+// in-kernel allreduce context when the reduction fits it (several ranks, <= B200_AR_MAX_COUNT values)
+static B200ArCtx bpcg_ar(int count)
+{
+	B200ArCtx ar = b200k_ar_ctx();
+	if (count > B200_AR_MAX_COUNT) ar.nranks = 0;
+	return ar;
+}
+
 // several ranks: sum the per-column totals over the ranks, then the scalar step
 static int bpcg_finish(int phase, int nacc, const b200_bpcg_state *st, double tol, int rel, double rate)
 {
@@ -301,11 +312,12 @@ extern "C" int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const do
                                 double *r, int ldr, double tol, int rel)
 {
 	const int k = st->k;
-	const int defer = b200_multi() ? 1 : 0;
+	const B200ArCtx ar = bpcg_ar(2 * k);
+	const int defer = (b200_multi() && ar.nranks == 0) ? 1 : 0;
 	B200_CHECK(k >= 1 && k <= 128, "BlockPCG: %d columns (1..128 supported per block)", k);
 	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 5.0 * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(b, ldb) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, defer, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, defer, *st, ar)));
 	B200_KERNEL_CHECK();
 	if (defer) return bpcg_finish(0, 2, st, tol, rel, 0.0);
 	return 0;
@@ -326,11 +338,12 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
                               double *w, int ldw, double shift, const double *z, int ldz)
 {
 	const int k = st->k;
-	const int defer = b200_multi() ? 1 : 0;
+	const B200ArCtx ar = bpcg_ar(k);
+	const int defer = (b200_multi() && ar.nranks == 0) ? 1 : 0;
 	B200Prof prof(B200_PROF_BPCG, (z ? 32.0 : 16.0) * n * k, (z ? 4.0 : 2.0) * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
 	                                     (!z || stream_aligned16(z, ldz)), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_ptw_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, shift, z, ldz, defer, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_ptw_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, shift, z, ldz, defer, *st, ar)));
 	B200_KERNEL_CHECK();
 	if (defer) return bpcg_finish(1, 1, st, 0.0, 0, 0.0);
 	return 0;
@@ -338,7 +351,7 @@ extern "C" int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const doub
 
 // p^T w from the per-CTA partials the fused SpMM left in st.partials[part][k]
 __global__ void __launch_bounds__(ST_THREADS)
-bpcg_ptw_parts_kernel(int nparts, int k, int defer, b200_bpcg_state st)
+bpcg_ptw_parts_kernel(int nparts, int k, int defer, b200_bpcg_state st, B200ArCtx ar)
 {
 	if (st.counters[0] == 0) return;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,6 +360,7 @@ bpcg_ptw_parts_kernel(int nparts, int k, int defer, b200_bpcg_state st)
 		if (lane == 0) st.totals[c] = s;
 	}
 	__syncthreads();
+	if (ar.nranks > 1) stream_allreduce_cta(ar, st.totals, k);
 	if (!defer) bpcg_scalar_phase(1, k, st, 0.0, 0, 0.0);
 }
 
@@ -359,7 +373,8 @@ extern "C" int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bp
                                    double *w, int ldw)
 {
 	const int k = st->k;
-	const int defer = b200_multi() ? 1 : 0;
+	const B200ArCtx ar = bpcg_ar(k);
+	const int defer = (b200_multi() && ar.nranks == 0) ? 1 : 0;
 	const int cap = g_b200.num_sms * BPCG_CTAS_PER_SM;       // rows of k doubles available in st->partials (x2)
 	int nparts = 0;
 	const int rc = b200k_spmm_dot(A, p, ldp, w, ldw, k, st->counters, st->partials, cap, &nparts);
@@ -370,7 +385,7 @@ extern "C" int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bp
 	}
 	{
 		B200Prof prof(B200_PROF_BPCG, 8.0 * nparts * k, 1.0 * nparts * k);
-		bpcg_ptw_parts_kernel<<<1, ST_THREADS, 0, g_b200.stream>>>(nparts, k, defer, *st);
+		bpcg_ptw_parts_kernel<<<1, ST_THREADS, 0, g_b200.stream>>>(nparts, k, defer, *st, ar);
 		B200_KERNEL_CHECK();
 	}
 	if (defer) return bpcg_finish(1, 1, st, 0.0, 0, 0.0);
@@ -382,11 +397,12 @@ extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, cons
                                     double rate, double tol)
 {
 	const int k = st->k;
-	const int defer = b200_multi() ? 1 : 0;
+	const B200ArCtx ar = bpcg_ar(k);
+	const int defer = (b200_multi() && ar.nranks == 0) ? 1 : 0;
 	B200Prof prof(B200_PROF_BPCG, 48.0 * n * k, 6.0 * n * k);
 	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
 	                                     stream_aligned16(x, ldx) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, defer, *st)));
+	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, defer, *st, ar)));
 	B200_KERNEL_CHECK();
 	if (defer) return bpcg_finish(2, 1, st, tol, 0, rate);
 	return 0;

@@ -71,7 +71,7 @@ int load_nccl()
 
 }  // namespace
 
-namespace { void p2p_release(); }
+namespace { void p2p_release(); int ar_setup(); void ar_release(); }
 
 extern "C" int b200_comm_unique_id(char *id128)
 {
@@ -94,6 +94,7 @@ extern "C" int b200_comm_init(int rank, int nranks, const char *id128)
 	nccl_uid u; memcpy(u.internal, id128, 128);
 	B200_NCCL(g_nccl.CommInitRank(&g_comm, nranks, u, rank));
 	g_b200.rank = rank; g_b200.nranks = nranks;
+	if (!getenv("B200_NO_P2P") && ar_setup()) return 1;
 	// side stream for the SpMM halo exchange (copy engines over NVLink, see p2p_* below), so that it
 	// overlaps the interior rows of the multiply
 	g_b200.comm_stream = nullptr;
@@ -116,6 +117,7 @@ extern "C" int b200_comm_finalize(void)
 			cudaEventDestroy(g_b200.ev_x_ready); cudaEventDestroy(g_b200.ev_halo_done);
 			g_b200.comm_stream = nullptr;
 		}
+		ar_release();
 		g_nccl.CommDestroy(g_comm);
 		g_comm = nullptr;
 	}
@@ -376,5 +378,108 @@ int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 	}
 	B200_CUDA(cudaEventRecord(g_b200.ev_halo_done, cs));
 	B200_LAUNCHED();
+	return 0;
+}
+
+// ================================================================ allreduce inside a kernel
+// The CG step needs two tiny allreduces per iteration (diag(p^T A p) and diag(r^T r), k doubles each).
+// Through NCCL each is a kernel launch of its own (~35 us at 8 GPUs) followed by a one-CTA kernel for the
+// scalar update.  Instead, the last CTA of the streaming kernel that produced the partial sums writes
+// its k values into an inbox on EVERY rank (remote stores over NVLink into IPC-mapped memory), raises
+// a flag there, waits for the flags of all the others in its own memory, adds the nranks
+// contributions in rank order -- the same bits on every rank -- and goes on with the scalar update.
+// Two inbox parities: a rank can run at most one allreduce ahead of the slowest (it needs everybody's
+// flag for the one in between).  A wait that lasts longer than ~4 s records a time-out in a status word
+// (checked by the host at the end of the solve) instead of hanging the GPU.
+namespace {
+struct ArState {
+	bool ok = false;
+	double *inbox = nullptr; unsigned *flags = nullptr;      // local, exported
+	void *peer_inbox[B200_AR_MAX_RANKS] = {}, *peer_flags[B200_AR_MAX_RANKS] = {};
+} g_ar;
+
+void ar_release()
+{
+	for (int q = 0; q < B200_AR_MAX_RANKS; ++q) {
+		if (g_ar.peer_inbox[q]) cudaIpcCloseMemHandle(g_ar.peer_inbox[q]);
+		if (g_ar.peer_flags[q]) cudaIpcCloseMemHandle(g_ar.peer_flags[q]);
+		g_ar.peer_inbox[q] = g_ar.peer_flags[q] = nullptr;
+	}
+	if (g_ar.inbox) cudaFree(g_ar.inbox);
+	if (g_ar.flags) cudaFree(g_ar.flags);
+	g_ar.inbox = nullptr; g_ar.flags = nullptr; g_ar.ok = false;
+	cudaGetLastError();
+}
+
+// collective, from b200_comm_init.  Failure to map is not an error: NCCL stays in place.
+int ar_setup()
+{
+	const int nr = g_b200.nranks;
+	if (nr < 2 || nr > B200_AR_MAX_RANKS) return 0;
+	cudaStream_t st = g_b200.stream;
+	const size_t inbox_bytes = sizeof(double) * 2 * nr * B200_AR_MAX_COUNT, flag_bytes = 1024;
+	int good = 1;
+	if (cudaMalloc(&g_ar.inbox, inbox_bytes) != cudaSuccess || cudaMalloc(&g_ar.flags, flag_bytes) != cudaSuccess) { cudaGetLastError(); good = 0; }
+	struct Handles { cudaIpcMemHandle_t ib, fl; int good; int pad[3]; };
+	Handles mine; memset(&mine, 0, sizeof(mine));
+	if (good) {
+		B200_CUDA(cudaMemsetAsync(g_ar.inbox, 0, inbox_bytes, st));
+		B200_CUDA(cudaMemsetAsync(g_ar.flags, 0, flag_bytes, st));
+		if (cudaIpcGetMemHandle(&mine.ib, g_ar.inbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.fl, g_ar.flags) != cudaSuccess) { cudaGetLastError(); good = 0; }
+	}
+	mine.good = good;
+	const size_t hb = sizeof(Handles);
+	char *dh = (char *)b200_scratch(8, hb * ((size_t)nr + 1));
+	if (!dh) return 1;
+	std::vector<Handles> hs((size_t)nr);
+	B200_CUDA(cudaMemcpyAsync(dh + hb * nr, &mine, hb, cudaMemcpyHostToDevice, st));
+	B200_NCCL(g_nccl.AllGather(dh + hb * nr, dh, hb, NCCL_INT8, g_comm, st));
+	B200_CUDA(cudaMemcpyAsync(hs.data(), dh, hb * nr, cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	bool all_good = true;
+	for (const Handles &h : hs) all_good = all_good && h.good;
+	for (int q = 0; q < nr && all_good; ++q) {
+		if (q == g_b200.rank) continue;
+		if (cudaIpcOpenMemHandle(&g_ar.peer_inbox[q], hs[q].ib, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+		    cudaIpcOpenMemHandle(&g_ar.peer_flags[q], hs[q].fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			cudaGetLastError(); all_good = false;
+		}
+	}
+	{   // everybody or nobody
+		double flag = all_good ? 0.0 : 1.0;
+		double *df = (double *)b200_scratch(8, 256);
+		B200_CUDA(cudaMemcpyAsync(df, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+		B200_NCCL(g_nccl.AllReduce(df, df, 1, NCCL_FLOAT64, NCCL_SUM, g_comm, st));
+		B200_CUDA(cudaMemcpyAsync(&flag, df, sizeof(double), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		all_good = (flag == 0.0);
+	}
+	if (!all_good) { ar_release(); return 0; }
+	g_ar.ok = true;
+	return 0;
+}
+}  // namespace
+
+B200ArCtx b200k_ar_ctx()
+{
+	B200ArCtx c; memset(&c, 0, sizeof(c));
+	if (!g_ar.ok || getenv("B200_NO_KERNEL_ALLREDUCE")) return c;
+	c.nranks = g_b200.nranks; c.rank = g_b200.rank;
+	for (int q = 0; q < g_b200.nranks; ++q) {
+		c.inbox[q] = (q == g_b200.rank) ? g_ar.inbox : (double *)g_ar.peer_inbox[q];
+		c.flags[q] = (q == g_b200.rank) ? g_ar.flags : (unsigned *)g_ar.peer_flags[q];
+	}
+	c.seq = g_ar.flags + 2 * B200_AR_MAX_RANKS;            // behind the [2][nranks] flags
+	c.status = (int *)(g_ar.flags + 2 * B200_AR_MAX_RANKS + 1);
+	return c;
+}
+
+extern "C" int b200k_ar_check(void)
+{
+	if (!g_ar.ok) return 0;
+	int st = 0;
+	B200_CUDA(cudaMemcpyAsync(&st, g_ar.flags + 2 * B200_AR_MAX_RANKS + 1, sizeof(int), cudaMemcpyDeviceToHost, g_b200.stream));
+	B200_CUDA(cudaStreamSynchronize(g_b200.stream));
+	B200_CHECK(st == 0, "in-kernel allreduce: a rank waited more than 4 s for its peers (the ranks no longer run the same sequence of kernels)");
 	return 0;
 }

@@ -43,6 +43,18 @@ struct b200_ctx {
 int b200k_allreduce_sum(double *buf_dev, size_t count);
 int b200k_neighbor_exchange(int nnbr, const int *nbr, const double *send_dev, const size_t *send_off,
                             const size_t *send_cnt, double *recv_dev, const size_t *recv_off, const size_t *recv_cnt);
+// Small allreduce INSIDE a kernel (b200_comm.cu sets it up, b200_stream.cuh has the device side): every
+// rank's inbox and flags are IPC-mapped on every other rank.  nranks == 0: not available (use NCCL).
+constexpr int B200_AR_MAX_RANKS = 8;
+constexpr int B200_AR_MAX_COUNT = 256;
+struct B200ArCtx {
+	int nranks, rank;
+	double *inbox[B200_AR_MAX_RANKS];      // rank q's inbox: [2 parities][nranks][B200_AR_MAX_COUNT]; [rank] is the local one
+	unsigned *flags[B200_AR_MAX_RANKS];    // rank q's flags: [2 parities][nranks]
+	unsigned *seq;                         // local: number of in-kernel allreduces done
+	int *status;                           // local: != 0 after a time-out
+};
+B200ArCtx b200k_ar_ctx();
 // halo exchange by copy engines on the comm stream (b200_comm.cu)
 int b200k_p2p_register(int rows, int *all_ranks_ok);
 int b200k_p2p_usable(const b200_mat *M, int k);

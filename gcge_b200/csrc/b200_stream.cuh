@@ -128,6 +128,44 @@ __device__ __forceinline__ double stream_total(const double *part, int chunks, i
 	return s;
 }
 
+// Sum vals[0..cnt) over the ranks, in place, by the calling CTA (every thread must call; cnt <=
+// B200_AR_MAX_COUNT; vals in global memory).  See b200_comm.cu "allreduce inside a kernel".
+__device__ __forceinline__ void stream_allreduce_cta(const B200ArCtx &ar, double *vals, int cnt)
+{
+	__shared__ unsigned ar_epoch;
+	__syncthreads();
+	if (threadIdx.x == 0) ar_epoch = ++(*ar.seq);
+	__syncthreads();
+	const unsigned e = ar_epoch, par = e & 1u;
+	const size_t slot = ((size_t)par * ar.nranks + ar.rank) * B200_AR_MAX_COUNT;
+	for (int i = threadIdx.x; i < cnt * ar.nranks; i += blockDim.x) {
+		const int q = i / cnt, j = i - q * cnt;
+		ar.inbox[q][slot + j] = vals[j];                    // remote store (local for q == rank)
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x < ar.nranks) {
+		volatile unsigned *f = ar.flags[threadIdx.x] + par * ar.nranks + ar.rank;
+		*f = e;
+	}
+	if (threadIdx.x < ar.nranks) {
+		volatile unsigned *mine = ar.flags[ar.rank] + par * ar.nranks + threadIdx.x;
+		const long long t0 = clock64();
+		while ((int)(*mine - e) < 0) {
+			if (clock64() - t0 > (1ll << 33)) { *ar.status = 1; break; }      // ~4 s: give up instead of hanging
+		}
+	}
+	__threadfence_system();
+	__syncthreads();
+	for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+		double s = 0.0;
+		for (int q = 0; q < ar.nranks; ++q)
+			s += ((volatile double *)ar.inbox[ar.rank])[((size_t)par * ar.nranks + q) * B200_AR_MAX_COUNT + j];
+		vals[j] = s;
+	}
+	__syncthreads();
+}
+
 #define ST_DISPATCH_VEC(g, CALL)                       \
 	do {                                               \
 		if ((g).vec == 2) { constexpr int VEC = 2; CALL; } \

@@ -72,6 +72,7 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	                   act_sum, iters_run * k, iters_run ? 100.0 * act_sum / (iters_run * k) : 0.0);
 	if (niter || residual) {
 		int counters[2];
+		if (b200k_ar_check()) return 1;
 		double res[BPCG_MAX_K];
 		if (b200k_d2h(counters, st.counters, sizeof(counters))) return 1;
 		if (b200k_d2h(res, st.last_res, sizeof(double) * (size_t)k)) return 1;

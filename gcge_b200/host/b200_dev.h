@@ -145,6 +145,8 @@ typedef struct b200_bpcg_state_ {
 	unsigned *tickets;  /* last-block election counters */
 } b200_bpcg_state;
 int b200k_bpcg_state(int k, b200_bpcg_state *st);               /* carve state out of scratch */
+/* several ranks: 0, or an error if an in-kernel allreduce timed out since the communicator was made (synchronises) */
+int b200k_ar_check(void);
 /* r = b - r (r holds A x on entry); rho2 = diag(r^T r); norm_b = 1 or ||b||; then decide the
  * initial active set: init_res > tol*norm_b (reference src/ops_lin_sol.c:221-247) */
 int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const double *b, int ldb,

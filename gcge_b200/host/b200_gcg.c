@@ -455,6 +455,7 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 		TRY(compute_ritz_vec(g));
 		++numIter;
 	} while (numIter < numIterMax);
+	TRY(b200k_ar_check());
 	g->st.numIter = numIter + (p->numIterMax - numIterMax);
 	g->st.nevConv = *nevConv;
 	memcpy(eval, g->eval_h, sizeof(double) * (size_t)g->sizeX);      /* reference :1508 */
