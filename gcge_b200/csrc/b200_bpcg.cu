@@ -7,10 +7,13 @@
 // Nothing crosses to the host inside the CG loop.
 //
 // Per iteration, per column block k (algorithmic HBM traffic):
-//   update_p : read r,p      write p          3 * 8nk
-//   SpMM     : matrix + read p, write w       nnz*12 + 2 * 8nk
-//   ptw      : read p,w                       2 * 8nk     (+ shift: read z, write w)
-//   update_xr: read p,w,x,r  write x,r        6 * 8nk
+//   update_px: read r,p,x    write p,x        5 * 8nk     x += alpha_prev p ; p = r + beta p
+//   SpMM     : matrix + read p, write w       nnz*12 + 2 * 8nk   (+ p^T w in its epilogue, b200_spmm.cu)
+//   ptw      : read p,w                       2 * 8nk     (only with a shift: read z, write w)
+//   update_r : read w,r      write r          3 * 8nk     r -= alpha w ; rho = r^T r ; stop test
+// The x update of iteration i is deferred into the p update of iteration i+1: x does not feed back
+// into the iteration, so the iterates are bit-identical to the textbook order (x += alpha p next to
+// r -= alpha w, 6 + 3 streams), and p is read once for both -- 8 streams instead of 9.
 #include "b200_stream.cuh"
 
 constexpr int BPCG_CTAS_PER_SM = 6;
@@ -18,7 +21,7 @@ constexpr int BPCG_CTAS_PER_SM = 6;
 extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 {
 	const int chunks_max = g_b200.num_sms * BPCG_CTAS_PER_SM + 8;
-	const size_t dbl = (size_t)8 * k + (size_t)chunks_max * 2 * k;
+	const size_t dbl = (size_t)9 * k + (size_t)chunks_max * 2 * k;
 	const size_t bytes = sizeof(double) * dbl + sizeof(int) * ((size_t)k + 8) + 64;
 	char *base = (char *)b200_scratch(4, bytes);
 	if (!base) return 1;
@@ -27,7 +30,8 @@ extern "C" int b200k_bpcg_state(int k, b200_bpcg_state *st)
 	st->norm_b = d; st->rho1 = d + k; st->rho2 = d + 2 * k; st->ptw = d + 3 * k;
 	st->init_res = d + 4 * k; st->last_res = d + 5 * k;
 	st->totals = d + 6 * k;                       /* 2k: per-column sums of the current reduction */
-	st->partials = d + 8 * k;
+	st->alpha = d + 8 * k;                        /* k: step length of the x update still to be applied */
+	st->partials = d + 9 * k;
 	int *ip = (int *)(d + dbl);
 	st->active = ip; st->counters = ip + k; st->tickets = (unsigned *)(ip + k + 4);
 	B200_CUDA(cudaMemsetAsync(st->counters, 0, sizeof(int) * 8, g_b200.stream));
@@ -141,49 +145,6 @@ bpcg_begin_kernel(long long n, int k, StreamGeom g, const double *__restrict__ b
 	if (!defer) bpcg_scalar_phase(0, k, st, tol, rel, 0.0);
 }
 
-// ------------------------------------------------------------------------- update_p
-// p = r + (rho2/rho1) p on active columns; reference src/ops_lin_sol.c:271-284
-template <int VEC>
-__global__ void __launch_bounds__(ST_THREADS)
-bpcg_update_p_kernel(long long n, int k, StreamGeom g, const double *__restrict__ r, int ldr, double *__restrict__ p,
-                     int ldp, int first, b200_bpcg_state st)
-{
-	if (st.counters[0] == 0) return;
-	const StreamThread t = stream_thread<VEC>(g);
-	if (!t.active) return;
-	bool act[VEC]; double beta[VEC]; bool any = false;
-#pragma unroll
-	for (int i = 0; i < VEC; ++i) {
-		act[i] = st.active[t.c + i] != 0;
-		beta[i] = (act[i] && !first) ? st.rho2[t.c + i] / st.rho1[t.c + i] : 0.0;
-		any = any || act[i];
-	}
-	if (!any) return;
-	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
-	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
-	for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
-		StV<VEC> rv[ST_UNROLL], pv[ST_UNROLL];
-#pragma unroll
-		for (int u = 0; u < ST_UNROLL; ++u) {
-			const long long row = row0 + (long long)u * g.rp;
-			if (row < r_end) {
-				rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c);
-				pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);     // also when first: an inactive neighbour column keeps its value
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < ST_UNROLL; ++u) {
-			const long long row = row0 + (long long)u * g.rp;
-			if (row < r_end) {
-#pragma unroll
-				for (int i = 0; i < VEC; ++i)
-					if (act[i]) pv[u].v[i] = first ? rv[u].v[i] : fma(beta[i], pv[u].v[i], rv[u].v[i]);
-				st_st<VEC>(p + (size_t)row * ldp + t.c, pv[u]);
-			}
-		}
-	}
-}
-
 // ------------------------------------------------------------------------------ ptw
 // w += shift z (optional) ; ptw = diag(p^T w)
 template <int VEC>
@@ -231,13 +192,13 @@ bpcg_ptw_kernel(long long n, int k, StreamGeom g, const double *p, int ldp, doub
 	if (!defer) bpcg_scalar_phase(1, k, st, 0.0, 0, 0.0);
 }
 
-// ------------------------------------------------------------------------ update_xr
-// alpha = rho2/ptw ; x += alpha p ; r -= alpha w ; rho1 = rho2 ; rho2 = diag(r^T r) ; stop test
+// ------------------------------------------------------------------------- update_r
+// alpha = rho2/ptw ; r -= alpha w ; rho1 = rho2 ; rho2 = diag(r^T r) ; stop test.  alpha is left in
+// st.alpha for the deferred x update; counters[2] = it + 1 says which iteration it belongs to.
 template <int VEC>
 __global__ void __launch_bounds__(ST_THREADS)
-bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict__ p, int ldp, const double *__restrict__ w,
-                      int ldw, double *__restrict__ x, int ldx, double *__restrict__ r, int ldr, double rate, double tol,
-                      int defer, b200_bpcg_state st, B200ArCtx ar)
+bpcg_update_r_kernel(long long n, int k, StreamGeom g, const double *__restrict__ w, int ldw, double *__restrict__ r, int ldr,
+                     double rate, double tol, int it, int defer, b200_bpcg_state st, B200ArCtx ar)
 {
 	if (st.counters[0] == 0) return;
 	const StreamThread t = stream_thread<VEC>(g);
@@ -252,16 +213,19 @@ bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict
 		alpha[i] = act[i] ? st.rho2[t.c + i] / st.ptw[t.c + i] : 0.0;       // reference src/ops_lin_sol.c:328
 		any = any || act[i];
 	}
+	if (blockIdx.x == 0 && t.active && t.rl == 0) {
+#pragma unroll
+		for (int i = 0; i < VEC; ++i) st.alpha[t.c + i] = alpha[i];
+		if (t.cg == 0) st.counters[2] = it + 1;
+	}
 	if (any) {
 		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
-			StV<VEC> pv[ST_UNROLL], wv[ST_UNROLL], xv[ST_UNROLL], rv[ST_UNROLL];
+			StV<VEC> wv[ST_UNROLL], rv[ST_UNROLL];
 #pragma unroll
 			for (int u = 0; u < ST_UNROLL; ++u) {
 				const long long row = row0 + (long long)u * g.rp;
 				if (row < r_end) {
-					pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);
 					wv[u] = st_ld<VEC>(w + (size_t)row * ldw + t.c);
-					xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c);
 					rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c);
 				}
 			}
@@ -272,13 +236,11 @@ bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict
 #pragma unroll
 					for (int i = 0; i < VEC; ++i) {
 						if (act[i]) {
-							xv[u].v[i] = fma(alpha[i], pv[u].v[i], xv[u].v[i]);
 							const double nr = fma(-alpha[i], wv[u].v[i], rv[u].v[i]);
 							rv[u].v[i] = nr;
 							acc[0][i] = fma(nr, nr, acc[0][i]);
 						}
 					}
-					st_st<VEC>(x + (size_t)row * ldx + t.c, xv[u]);
 					st_st<VEC>(r + (size_t)row * ldr + t.c, rv[u]);
 				}
 			}
@@ -288,6 +250,64 @@ bpcg_update_xr_kernel(long long n, int k, StreamGeom g, const double *__restrict
 	bpcg_store_totals<1>(k, st);
 	if (ar.nranks > 1) stream_allreduce_cta(ar, st.totals, k);
 	if (!defer) bpcg_scalar_phase(2, k, st, tol, 0, rate);
+}
+
+// ------------------------------------------------------------------------ update_px
+// x += alpha p for the step length left by update_r of iteration `expect - 1` (if any), then
+// p = r + (rho2/rho1) p on the columns still active (reference src/ops_lin_sol.c:271-284, :330-340).
+// flush: only the x update (after the last iteration).
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+bpcg_update_px_kernel(long long n, int k, StreamGeom g, const double *__restrict__ r, int ldr, double *__restrict__ p,
+                      int ldp, double *__restrict__ x, int ldx, int first, int expect, int flush, b200_bpcg_state st)
+{
+	const bool pending = !first && st.counters[2] == expect;
+	const bool running = !flush && st.counters[0] != 0;
+	if (!pending && !running) return;
+	const StreamThread t = stream_thread<VEC>(g);
+	if (!t.active) return;
+	bool act[VEC]; double beta[VEC], al[VEC]; bool any_p = false, any_x = false;
+#pragma unroll
+	for (int i = 0; i < VEC; ++i) {
+		act[i] = running && st.active[t.c + i] != 0;
+		beta[i] = (act[i] && !first) ? st.rho2[t.c + i] / st.rho1[t.c + i] : 0.0;
+		al[i] = pending ? st.alpha[t.c + i] : 0.0;
+		any_p = any_p || act[i];
+		any_x = any_x || (al[i] != 0.0);
+	}
+	if (!any_p && !any_x) return;
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+		StV<VEC> rv[ST_UNROLL], pv[ST_UNROLL], xv[ST_UNROLL];
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) {
+				if (any_p) rv[u] = st_ld<VEC>(r + (size_t)row * ldr + t.c);
+				pv[u] = st_ld<VEC>(p + (size_t)row * ldp + t.c);
+				if (any_x) xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) {
+				if (any_x) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i)
+						if (al[i] != 0.0) xv[u].v[i] = fma(al[i], pv[u].v[i], xv[u].v[i]);
+					st_st<VEC>(x + (size_t)row * ldx + t.c, xv[u]);
+				}
+				if (any_p) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i)
+						if (act[i]) pv[u].v[i] = first ? rv[u].v[i] : fma(beta[i], pv[u].v[i], rv[u].v[i]);
+					st_st<VEC>(p + (size_t)row * ldp + t.c, pv[u]);
+				}
+			}
+		}
+	}
 }
 
 // ------------------------------------------------------------------------- launchers
@@ -320,17 +340,6 @@ extern "C" int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const do
 	ST_DISPATCH_VEC(g, (bpcg_begin_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, b, ldb, r, ldr, tol, rel, defer, *st, ar)));
 	B200_KERNEL_CHECK();
 	if (defer) return bpcg_finish(0, 2, st, tol, rel, 0.0);
-	return 0;
-}
-
-extern "C" int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const double *r, int ldr,
-                                   double *p, int ldp, int first)
-{
-	const int k = st->k;
-	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 2.0 * n * k);
-	const StreamGeom g = stream_geometry(n, k, stream_aligned16(r, ldr) && stream_aligned16(p, ldp), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_update_p_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, r, ldr, p, ldp, first, *st)));
-	B200_KERNEL_CHECK();
 	return 0;
 }
 
@@ -392,18 +401,31 @@ extern "C" int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bp
 	return 0;
 }
 
-extern "C" int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, const double *p, int ldp,
-                                    const double *w, int ldw, double *x, int ldx, double *r, int ldr,
-                                    double rate, double tol)
+extern "C" int b200k_bpcg_update_r(long long n, const b200_bpcg_state *st, const double *w, int ldw, double *r, int ldr,
+                                   double rate, double tol, int it)
 {
 	const int k = st->k;
 	const B200ArCtx ar = bpcg_ar(k);
 	const int defer = (b200_multi() && ar.nranks == 0) ? 1 : 0;
-	B200Prof prof(B200_PROF_BPCG, 48.0 * n * k, 6.0 * n * k);
-	const StreamGeom g = stream_geometry(n, k, stream_aligned16(p, ldp) && stream_aligned16(w, ldw) &&
-	                                     stream_aligned16(x, ldx) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
-	ST_DISPATCH_VEC(g, (bpcg_update_xr_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, p, ldp, w, ldw, x, ldx, r, ldr, rate, tol, defer, *st, ar)));
+	B200Prof prof(B200_PROF_BPCG, 24.0 * n * k, 4.0 * n * k);
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(w, ldw) && stream_aligned16(r, ldr), BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_update_r_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, w, ldw, r, ldr, rate, tol, it, defer, *st, ar)));
 	B200_KERNEL_CHECK();
 	if (defer) return bpcg_finish(2, 1, st, tol, 0, rate);
+	return 0;
+}
+
+// it: the iteration whose p is being formed (0 = first: p = r, nothing pending); flush != 0: only the
+// pending x update of iteration it - 1
+extern "C" int b200k_bpcg_update_px(long long n, const b200_bpcg_state *st, const double *r, int ldr, double *p, int ldp,
+                                    double *x, int ldx, int it, int flush)
+{
+	const int k = st->k;
+	B200Prof prof(B200_PROF_BPCG, (flush ? 24.0 : (it == 0 ? 24.0 : 40.0)) * n * k, 4.0 * n * k);
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(r, ldr) && stream_aligned16(p, ldp) && stream_aligned16(x, ldx),
+	                                     BPCG_CTAS_PER_SM);
+	ST_DISPATCH_VEC(g, (bpcg_update_px_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, r, ldr, p, ldp, x, ldx,
+	                                                                                         it == 0, it, flush, *st)));
+	B200_KERNEL_CHECK();
 	return 0;
 }

@@ -4,8 +4,8 @@
  * CG iteration, one single-column MultiVecAxpby per column for p, one SpMM and one 'D'
  * inner product per contiguous index block, two more single-column axpbys per column, and
  * decides convergence on the host from scalars it pulled back.  Here one iteration is a
- * fixed sequence of launches on the whole block (update_p, SpMM with p^T w in its epilogue,
- * update_xr; with a shift: update_p, SpMM, SpMM, ptw, update_xr);
+ * fixed sequence of launches on the whole block (update_px, SpMM with p^T w in its epilogue,
+ * update_r; with a shift: update_px, SpMM, SpMM, ptw, update_r);
  * rho/alpha/beta, the residual norms, the active-column masks and the iteration counter
  * stay in HBM, and every launch returns at once when no column is active any more, so the
  * host never reads anything back inside the loop.  Converged columns are frozen exactly as
@@ -50,24 +50,26 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 			if (c2[0] == 0) break;
 			act_sum += c2[0]; ++iters_run;
 		}
-		if (b200k_bpcg_update_p(n, &st, r, ldr, p, ldp, it == 0)) return 1;
+		/* x += alpha_{it-1} p_{it-1} (deferred), p_it = r + beta p_{it-1} */
+		if (b200k_bpcg_update_px(n, &st, r, ldr, p, ldp, x, ldx, it, 0)) return 1;
 		if (shift == 0.0) {
 			/* w = A p with p^T w in the SpMM epilogue */
 			if (b200k_bpcg_spmm_ptw(A, n, &st, p, ldp, w, ldw)) return 1;
-			if (b200k_bpcg_update_xr(n, &st, p, ldp, w, ldw, x, ldx, r, ldr, prm->rate, prm->tol)) return 1;
-			continue;
-		}
-		if (b200k_spmm(A, 0, p, ldp, w, ldw, k, st.counters)) return 1;
-		if (B) {
-			/* the right-hand side is dead after the initial residual: use it as B p, like the
-			 * reference's MatDotMultiVecShift does (src/ops_eig_sol_gcg.c:63-96) */
-			if (b200k_spmm(B, 0, p, ldp, b, ldb, k, st.counters)) return 1;
-			if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, b, ldb)) return 1;
 		} else {
-			if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, p, ldp)) return 1;
+			if (b200k_spmm(A, 0, p, ldp, w, ldw, k, st.counters)) return 1;
+			if (B) {
+				/* the right-hand side is dead after the initial residual: use it as B p, like the
+				 * reference's MatDotMultiVecShift does (src/ops_eig_sol_gcg.c:63-96) */
+				if (b200k_spmm(B, 0, p, ldp, b, ldb, k, st.counters)) return 1;
+				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, b, ldb)) return 1;
+			} else {
+				if (b200k_bpcg_ptw(n, &st, p, ldp, w, ldw, shift, p, ldp)) return 1;
+			}
 		}
-		if (b200k_bpcg_update_xr(n, &st, p, ldp, w, ldw, x, ldx, r, ldr, prm->rate, prm->tol)) return 1;
+		if (b200k_bpcg_update_r(n, &st, w, ldw, r, ldr, prm->rate, prm->tol, it)) return 1;
 	}
+	/* the x update of the last iteration that ran */
+	if (b200k_bpcg_update_px(n, &st, r, ldr, p, ldp, x, ldx, prm->max_iter, 1)) return 1;
 	if (trace) fprintf(stderr, "bpcg k=%d: %lld iterations, active column-iterations %lld of %lld (%.0f %%)\n", k, iters_run,
 	                   act_sum, iters_run * k, iters_run ? 100.0 * act_sum / (iters_run * k) : 0.0);
 	if (niter || residual) {

@@ -139,8 +139,9 @@ typedef struct b200_bpcg_state_ {
 	int k;
 	double *norm_b, *rho1, *rho2, *ptw, *init_res, *last_res;   /* k doubles each (device) */
 	int *active;        /* k ints (device): 1 while the column is unconverged */
-	int *counters;      /* [0] number of active columns, [1] iterations done (device) */
+	int *counters;      /* [0] number of active columns, [1] iterations done, [2] 1 + iteration of the pending alpha (device) */
 	double *totals;     /* 2k doubles: per-column sums of the current reduction (allreduced across ranks) */
+	double *alpha;      /* k doubles: step length of the x update deferred into the next p update */
 	double *partials;   /* reduction scratch */
 	unsigned *tickets;  /* last-block election counters */
 } b200_bpcg_state;
@@ -151,9 +152,6 @@ int b200k_ar_check(void);
  * initial active set: init_res > tol*norm_b (reference src/ops_lin_sol.c:221-247) */
 int b200k_bpcg_begin(long long n, const b200_bpcg_state *st, const double *b, int ldb,
                      double *r, int ldr, double tol, int rel);
-/* p = r + (rho2/rho1) p on active columns (beta = 0 on the first iteration) */
-int b200k_bpcg_update_p(long long n, const b200_bpcg_state *st, const double *r, int ldr,
-                        double *p, int ldp, int first);
 /* w += shift * z (optional), ptw = diag(p^T w) */
 int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const double *p, int ldp,
                    double *w, int ldw, double shift, const double *z, int ldz);
@@ -161,11 +159,14 @@ int b200k_bpcg_ptw(long long n, const b200_bpcg_state *st, const double *p, int 
  * otherwise SpMM + b200k_bpcg_ptw */
 int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bpcg_state *st, const double *p, int ldp,
                         double *w, int ldw);
-/* alpha = rho2/ptw; x += alpha p; r -= alpha w; rho1 = rho2; rho2 = diag(r^T r);
- * then the per-column stop test (reference src/ops_lin_sol.c:383-394) and ++iterations */
-int b200k_bpcg_update_xr(long long n, const b200_bpcg_state *st, const double *p, int ldp,
-                         const double *w, int ldw, double *x, int ldx, double *r, int ldr,
-                         double rate, double tol);
+/* update_r: alpha = rho2/ptw; r -= alpha w; rho1 = rho2; rho2 = diag(r^T r); the per-column stop test
+ * (reference src/ops_lin_sol.c:383-394) and ++iterations; alpha is left behind, and
+ * update_px: applies x += alpha p of the previous iteration, then p = r + (rho2/rho1) p on the active
+ * columns (it == 0: p = r) -- p is read once for both: bit-identical iterates, 8 streams instead of 9 */
+int b200k_bpcg_update_r(long long n, const b200_bpcg_state *st, const double *w, int ldw, double *r, int ldr,
+                        double rate, double tol, int it);
+int b200k_bpcg_update_px(long long n, const b200_bpcg_state *st, const double *r, int ldr, double *p, int ldp,
+                         double *x, int ldx, int it, int flush);
 
 /* ---- projected eigenproblem (b200_syev.cu) --------------------------------------------
  * All eigenpairs of the symmetric n x n device matrix a (element (i,j) at a[i*lda+j]; both
