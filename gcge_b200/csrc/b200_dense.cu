@@ -16,6 +16,9 @@
 // Shared-memory row strides are == 4 (mod 16) doubles, which makes every fragment load a
 // two-wavefront (conflict-free) 64-bit access.
 #include "b200_internal.h"
+#include "b200_tma.cuh"
+#include <vector>
+#include <cmath>
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
 {
@@ -489,6 +492,173 @@ lincomb_kernel(long long n, int p, int q, const double *x, int ldx, const double
 	}
 }
 
+// ------------------------------------------------------------------ lincomb, TMA-fed
+// The cp.async version above spends 85 % of its instructions outside the DMMAs (address arithmetic of
+// the copies, predicates, stage barriers: ncu profiles/ncu_r1f_*: 5.06 G warp instructions for 0.75 G
+// DMMAs, tensor pipe 77 % busy).  Here a producer warp feeds the ring: the X tile (128 rows x 16
+// columns = 128 bytes per row) by ONE tensor-map copy per stage with the 128-byte swizzle (the 16-byte
+// chunk index of a row is XOR-ed with row % 8, which makes the A-fragment loads -- 8 consecutive rows
+// x 4 consecutive columns -- two-wavefront, i.e. conflict-free), the C tile by one 1-D bulk copy per
+// row into rows padded to 68 doubles (the B-fragment pattern, 4 rows x 8 consecutive columns, needs
+// the padding; no swizzle mode gives it).  The 8 consumer warps do nothing but fragment loads and
+// DMMAs and hand a stage back with one mbarrier arrive per warp.
+// Needs 16-byte aligned operands: x (even column offset and leading dimension), row-major C with even
+// row stride, even column offset and even q; everything else takes the kernel above.
+constexpr int LT_NS = 4;                                     // ring depth
+constexpr int LT_X_BYTES = LC_BM * LC_BK * 8;                // 16 KB, dense (swizzled) rows of 128 bytes
+constexpr int LT_C_BYTES = LC_BK * LC_SC * 8;                // 16 rows padded to 68 doubles
+constexpr int LT_STAGE_BYTES = LT_X_BYTES + LT_C_BYTES;
+
+template <bool HAS_BETA, int NQ8>
+__device__ __forceinline__ void
+lincomb_tma_body(const CUtensorMap *tmx, long long n, int p, int q, const double *__restrict__ c, int c_rs,
+                 const double *__restrict__ beta, int incb, double *y, int ldy)
+{
+	extern __shared__ __align__(1024) unsigned char tsm[];
+	__shared__ unsigned long long full[LT_NS], empty[LT_NS];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const long long r0 = (long long)blockIdx.y * LC_BM;
+	const int n0 = blockIdx.x * LC_BN;
+	const int nt = min(LC_BN, q - n0);
+	const int ktiles = (p + LC_BK - 1) / LC_BK;
+	unsigned char *xs_base = tsm, *cs_base = tsm + LT_NS * LT_X_BYTES;
+	// the C rows of the last k tile beyond p are never copied: make sure no NaN bit pattern sits there
+	// (they meet zero X columns, but 0 * NaN would poison the accumulators)
+	for (int i = tid; i < LT_NS * LC_BK * LC_SC; i += blockDim.x) reinterpret_cast<double *>(cs_base)[i] = 0.0;
+	if (tid == 0) {
+		for (int s = 0; s < LT_NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill before the async-proxy writes
+	__syncthreads();
+
+	if (warp == 8) {
+		// ------------------------------------------------------------------ producer warp
+		int slot = 0; unsigned phase = 0;
+		for (int kt = 0; kt < ktiles; ++kt) {
+			const int k0 = kt * LC_BK;
+			const int krows = min(LC_BK, p - k0);
+			if (lane == 0) {
+				mbar_spin(empty + slot, phase ^ 1u);
+				mbar_expect_tx(full + slot, (unsigned)(LT_X_BYTES + krows * nt * 8));
+				tma_load_2d(xs_base + (size_t)slot * LT_X_BYTES, tmx, k0, (int)r0, full + slot);
+			}
+			__syncwarp();
+			if (lane < krows)
+				bulk_load_1d(cs_base + (size_t)slot * LT_C_BYTES + (size_t)lane * LC_SC * 8,
+				             c + (size_t)(k0 + lane) * c_rs + n0, (unsigned)(nt * 8), full + slot);
+			if (++slot == LT_NS) { slot = 0; phase ^= 1u; }
+		}
+		return;
+	}
+	// ---------------------------------------------------------------------- consumer warps
+	const int g = lane >> 2, t = lane & 3;
+	double acc[2][NQ8][2];
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+#pragma unroll
+		for (int j = 0; j < NQ8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+	// A fragments: element (row, k) of the swizzled X tile sits at row*16 + (((k >> 1) ^ (row & 7)) << 1) + (k & 1)
+	// doubles; rows warp*16 + g and + 8 (both = g mod 8), k = ks + t
+	int aoff[LC_BK / 4];
+#pragma unroll
+	for (int s4 = 0; s4 < LC_BK / 4; ++s4) aoff[s4] = (warp * 16 + g) * 16 + ((((4 * s4 + t) >> 1) ^ g) << 1) + (t & 1);
+	int slot = 0; unsigned phase = 0;
+	for (int kt = 0; kt < ktiles; ++kt) {
+		mbar_spin(full + slot, phase);
+		const double *Xs = reinterpret_cast<const double *>(xs_base + (size_t)slot * LT_X_BYTES);
+		const double *Cs = reinterpret_cast<const double *>(cs_base + (size_t)slot * LT_C_BYTES);
+#pragma unroll
+		for (int s4 = 0; s4 < LC_BK / 4; ++s4) {
+			const double a0 = Xs[aoff[s4]];
+			const double a1 = Xs[aoff[s4] + 8 * 16];
+#pragma unroll
+			for (int j = 0; j < NQ8; ++j) {
+				const double b = Cs[(4 * s4 + t) * LC_SC + j * 8 + g];
+				dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
+				dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
+			}
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(empty + slot);
+		if (++slot == LT_NS) { slot = 0; phase ^= 1u; }
+	}
+#pragma unroll
+	for (int i = 0; i < 2; ++i) {
+		const long long r = r0 + warp * 16 + i * 8 + g;
+		if (r >= n) continue;
+#pragma unroll
+		for (int j = 0; j < NQ8; ++j)
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int cc = j * 8 + 2 * t + h;
+				if (cc < nt) {
+					double v = acc[i][j][h];
+					double *yp = y + (size_t)r * ldy + n0 + cc;
+					if (HAS_BETA) {
+						const double b = beta[(size_t)incb * (n0 + cc)];
+						if (b != 0.0) v += b * (*yp);      // beta == 0 overwrites (no NaN carry-over)
+					}
+					*yp = v;
+				}
+			}
+	}
+}
+
+template <bool HAS_BETA>
+__global__ void __launch_bounds__(288, 2)
+lincomb_tma_kernel(const __grid_constant__ CUtensorMap tmx, long long n, int p, int q, const double *__restrict__ c, int c_rs,
+                   const double *__restrict__ beta, int incb, double *y, int ldy)
+{
+	const int nt = min(LC_BN, q - (int)blockIdx.x * LC_BN);
+	switch ((nt + 7) >> 3) {                             // uniform over the CTA
+	case 1: lincomb_tma_body<HAS_BETA, 1>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 2: lincomb_tma_body<HAS_BETA, 2>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 3: lincomb_tma_body<HAS_BETA, 3>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 4: lincomb_tma_body<HAS_BETA, 4>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 5: lincomb_tma_body<HAS_BETA, 5>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 6: lincomb_tma_body<HAS_BETA, 6>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	case 7: lincomb_tma_body<HAS_BETA, 7>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	default: lincomb_tma_body<HAS_BETA, 8>(&tmx, n, p, q, c, c_rs, beta, incb, y, ldy); break;
+	}
+}
+
+// 0 launched, 1 error, 2 not applicable
+static int lincomb_tma_launch(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
+                              const double *beta_dev, int incb, double *y, int ldy)
+{
+	// OPT-IN (B200_TMA_DENSE=1): on B200 this kernel produced rare wrong entries inside full solves (one
+	// entry in ~10^10, not reproducible call by call: B200_TMA_VERIFY=1 runs it next to the cp.async kernel
+	// and reports differences) although every isolated shape test passes -- a race not yet found.  The
+	// cp.async kernel stays the product path until it is.
+	static const bool on = getenv("B200_TMA_DENSE") != nullptr || getenv("B200_TMA_VERIFY") != nullptr;
+	if (!on || n < LC_BM || c_cs != 1 || (c_rs & 1) || (q & 1) || ((uintptr_t)c_dev % 16) || ((uintptr_t)x % 16) || (ldx & 1) ||
+	    n > 0x7fffffffLL)
+		return 2;
+	tmap_encode_fn enc = tmap_encoder();
+	if (!enc) return 2;
+	CUtensorMap tm;
+	const cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
+	const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 8};
+	const cuuint32_t box[2] = {(cuuint32_t)LC_BK, (cuuint32_t)LC_BM};
+	const cuuint32_t estr[2] = {1, 1};
+	if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+		return 2;
+	const size_t smem = (size_t)LT_NS * LT_STAGE_BYTES;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(lincomb_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B200_CUDA(cudaFuncSetAttribute(lincomb_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	dim3 grid(b200_ceil_div(q, LC_BN), (unsigned)((n + LC_BM - 1) / LC_BM));
+	if (beta_dev) lincomb_tma_kernel<true><<<grid, 288, smem, g_b200.stream>>>(tm, n, p, q, c_dev, c_rs, beta_dev, incb, y, ldy);
+	else          lincomb_tma_kernel<false><<<grid, 288, smem, g_b200.stream>>>(tm, n, p, q, c_dev, c_rs, nullptr, 0, y, ldy);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
 // scaling only: y[:,c] *= beta[incb*c]  (beta == nullptr => y = 0)
 __global__ void colscale_kernel(long long n, int q, int rows_per_cta, const double *__restrict__ beta, int incb,
                                 double *y, int ldy)
@@ -522,6 +692,19 @@ int b200k_lincomb(long long n, int p, int q, const double *x, int ldx, const dou
 		B200_KERNEL_CHECK();
 		return 0;
 	}
+	static const bool verify = getenv("B200_TMA_VERIFY") != nullptr;
+	double *ytmp = nullptr;
+	if (!verify) {
+		const int rc = lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
+		if (rc != 2) return rc;
+	} else {
+		// diagnostic: run the TMA kernel on a copy of y, then the reference kernel on y, compare
+		B200_CUDA(cudaMalloc(&ytmp, sizeof(double) * (size_t)n * q));
+		B200_CUDA(cudaMemcpy2DAsync(ytmp, sizeof(double) * q, y, sizeof(double) * ldy, sizeof(double) * q, (size_t)n, cudaMemcpyDeviceToDevice, st));
+		const int rc = lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, ytmp, q);
+		if (rc == 1) return 1;
+		if (rc == 2) { cudaFree(ytmp); ytmp = nullptr; }
+	}
 	dim3 grid(b200_ceil_div(q, LC_BN), (unsigned)((n + LC_BM - 1) / LC_BM));
 	const size_t smem = sizeof(double) * (size_t)LC_STAGES * LC_STAGE_DBL;
 	static bool attr_set = false;
@@ -541,6 +724,38 @@ int b200k_lincomb(long long n, int p, int q, const double *x, int ldx, const dou
 		else      lincomb_kernel<false, false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, nullptr, 0, y, ldy);
 	}
 	B200_KERNEL_CHECK();
+	if (ytmp) {
+		std::vector<double> a((size_t)n * q), b((size_t)n * q);
+		B200_CUDA(cudaMemcpy2DAsync(a.data(), sizeof(double) * q, y, sizeof(double) * ldy, sizeof(double) * q, (size_t)n, cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaMemcpyAsync(b.data(), ytmp, sizeof(double) * (size_t)n * q, cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		double md = 0, mx = 0; size_t at = 0;
+		for (size_t i = 0; i < a.size(); ++i) {
+			const double d = fabs(a[i] - b[i]);
+			if (d > md || d != d) { md = d; at = i; }
+			if (fabs(a[i]) > mx) mx = fabs(a[i]);
+		}
+		static int calls = 0; ++calls;
+		if (md > 1e-10 * (mx > 0 ? mx : 1) || md != md)
+			fprintf(stderr, "TMA-VERIFY call %d MISMATCH n=%lld p=%d q=%d ldx=%d c_rs=%d ldy=%d beta=%d incb=%d x%%16=%d c%%16=%d y%%16=%d maxdiff=%g maxabs=%g at row %zu col %zu ref=%g tma=%g\n",
+			        calls, n, p, q, ldx, c_rs, ldy, beta_dev != nullptr, incb, (int)((uintptr_t)x % 16), (int)((uintptr_t)c_dev % 16),
+			        (int)((uintptr_t)y % 16), md, mx, at / q, at % q, a[at], b[at]);
+		if (md > 1e-10 * (mx > 0 ? mx : 1) || md != md) {
+			// is it reproducible?  run the TMA kernel again and count the differing entries of both runs
+			std::vector<double> b2((size_t)n * q);
+			lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, ytmp, q);
+			cudaMemcpyAsync(b2.data(), ytmp, sizeof(double) * (size_t)n * q, cudaMemcpyDeviceToHost, st);
+			cudaStreamSynchronize(st);
+			size_t nb1 = 0, nb2 = 0, nsame = 0; int shown = 0;
+			for (size_t i = 0; i < a.size(); ++i) {
+				const bool bad1 = fabs(a[i] - b[i]) > 1e-10 * mx, bad2 = fabs(a[i] - b2[i]) > 1e-10 * mx;
+				nb1 += bad1; nb2 += bad2; nsame += (bad1 && bad2 && b[i] == b2[i]);
+				if (bad1 && shown < 12) { fprintf(stderr, "   bad (%zu,%zu) ref=%.10g tma=%.10g tma2=%.10g\n", i / q, i % q, a[i], b[i], b2[i]); ++shown; }
+			}
+			fprintf(stderr, "   mismatching entries: run1 %zu, run2 %zu, identical wrong values in both %zu\n", nb1, nb2, nsame);
+		}
+		cudaFree(ytmp);
+	}
 	return 0;
 }
 

@@ -110,14 +110,16 @@ extern "C" int b200_mv_linear_comb(const b200_mv *x, b200_mv *y, const int *star
 		double *pin = (double *)b200_pinned(0, sizeof(double) * (ncoef + nbeta));
 		double *dev = (double *)b200_scratch(1, sizeof(double) * (ncoef + nbeta));
 		if (!pin || !dev) return 1;
+		// staged ROW-major (element (i, j) at i*q + j): the transposition costs nothing extra here and
+		// lets the TMA-fed kernel take the call (it wants contiguous coefficient rows)
 		for (int j = 0; gemm && j < q; ++j)
-			memcpy(pin + (size_t)j * p, coef + (size_t)j * ldc, sizeof(double) * p);
+			for (int i = 0; i < p; ++i) pin[(size_t)i * q + j] = coef[(size_t)j * ldc + i];
 		for (int j = 0; beta && j < q; ++j) pin[ncoef + j] = beta[(size_t)incb * j];
 		B200_CUDA(cudaMemcpyAsync(dev, pin, sizeof(double) * (ncoef + nbeta), cudaMemcpyHostToDevice,
 		                          g_b200.stream));
 		if (gemm) c_dev = dev;
 		if (beta) b_dev = dev + ncoef;
 	}
-	return b200k_lincomb(y->nrows, p, q, gemm ? x->d + start[0] : nullptr, gemm ? x->ld : 0, c_dev, 1, p,
+	return b200k_lincomb(y->nrows, p, q, gemm ? x->d + start[0] : nullptr, gemm ? x->ld : 0, c_dev, q, 1,
 	                     b_dev, 1, y->d + start[1], y->ld);
 }

@@ -11,7 +11,7 @@
 // ascending column order -- the same operation sequence as the reference's serial scatter,
 // so the result is bit-identical to the reference on every input.
 #include "b200_internal.h"
-#include <cuda.h>      // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+#include "b200_tma.cuh"
 
 // Matrix entries are fetched cooperatively: the G lanes of a row group load G consecutive
 // (value, column) pairs with one coalesced request each and hand them round with shuffles,
@@ -338,39 +338,6 @@ static int launch_spmm(int nrows, const int *rp, const int *ci, const double *va
 // to the reference's scatter loop (app/app_ccs.c:116-131).
 constexpr int DIA_WMAX = 3;
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"WAIT_LOOP:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra DONE;\n"
-		"bra WAIT_LOOP;\n"
-		"DONE:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-	             ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // One run of width W on the RB rows of a row group: x rows t = 0 .. RB + W - 2 of the run's box are
 // read once (128-bit) and x row t feeds matrix rows t - j, j < W.  The run's values of a matrix
 // row sit 16-byte aligned in the image (runs are padded to an even number of slots), so they
@@ -486,27 +453,6 @@ spmm_dia_tma_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblo
 	}
 }
 
-typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static tmap_encode_fn tmap_encoder()
-{
-	static tmap_encode_fn fn = nullptr;
-	static bool tried = false;
-	if (!tried) {
-		tried = true;
-		void *p = nullptr;
-		cudaDriverEntryPointQueryResult q;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-		    q == cudaDriverEntryPointSuccess)
-			fn = (tmap_encode_fn)p;
-		else
-			cudaGetLastError();
-	}
-	return fn;
-}
-
 // returns 0 launched, 1 error, 2 not applicable (caller falls back to the CSR kernels)
 template <int G, int RB, int NS>
 static int launch_spmm_dia(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate)
@@ -606,26 +552,6 @@ __device__ __forceinline__ void bulk_load_1d_evict_first(void *dst, const void *
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
-{
-	unsigned ok;
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-		"selp.u32 %0, 1, 0, p;\n"
-		"}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-	return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(unsigned long long *bar, unsigned parity)
-{
-	while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 constexpr int DIA2_MAX_NS = 8;                         // deepest tile ring

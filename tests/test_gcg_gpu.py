@@ -157,6 +157,24 @@ def test_device_gcg_from_matrix_market_files(b200, tmp_path):
     assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"][:8], o2["eval"][:8])
 
 
+def test_device_gcg_headline_block_structure(b200, refmod):
+    """nev = 200 (nevMax 400, block_size 40, projected problems of order up to 480) on a small lattice:
+    the shapes of the headline run -- contraction lengths far beyond the kernels' tile rings, several
+    column tiles, locked columns shifting the block offsets -- which the nev = 10 cases never reach.
+    Against the live reference: iteration count within 2, eigenvalues 1e-10."""
+    pen = P.p1_fem_kuhn(24)
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    o = b200.gcg_solve(A, B, nev=200)
+    assert o["nev_conv"] >= 200 and o["num_iter"] < 60, (o["nev_conv"], o["num_iter"])
+    ev = o["eval"][:200]
+    assert np.all(np.diff(ev) > -1e-9 * ev[-1]) and ev[0] > 25.0
+    if refmod is not None:
+        r = refmod.gcg_solve(pen.A, pen.B, nev=200, want_evec=False)
+        assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
+        k = min(o["nev_conv"], r["nev_conv"])
+        assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+
+
 def test_device_gcg_moving_window_and_shift(b200):
     """nevInit < nevMax (reference src/ops_eig_sol_gcg.c:1400-1428) and the shifted inner
     solve (compW_cg_shift, reference :482-492): same eigenvalues as the plain run."""

@@ -397,6 +397,53 @@ def test_linear_comb(b200, refmod, shape):
     assert rel(Y.numpy()[:, 1:1 + q], y[:, 1:1 + q] * bv[::2]) < 1e-15
 
 
+@pytest.mark.parametrize("shape", [(16, 16), (40, 40), (64, 8), (120, 40), (33, 70), (200, 130), (480, 400), (441, 40)])
+@pytest.mark.parametrize("n", [128, 1234, 5001])
+def test_linear_comb_aligned_blocks_tma_kernel(b200, shape, n):
+    """The TMA-fed LinearComb kernel (b200_dense.cu: lincomb_tma_kernel) takes 16-byte aligned blocks
+    with an even number of output columns: contraction lengths beyond the 4-deep tile ring, several
+    column tiles, ragged last tiles in every dimension, with and without beta."""
+    from gcge_b200 import api
+    p, q = shape
+    rng = np.random.default_rng(p + 1000 * q + n)
+    x = np.asfortranarray(rng.standard_normal((n, p + 2))); y = np.asfortranarray(rng.standard_normal((n, q + 6)))
+    coef = np.asfortranarray(rng.standard_normal((p, q)))
+    X = b200.MultiVec.from_numpy(x)
+    base = x[:, 2:2 + p] @ coef
+    scale = np.abs(x[:, 2:2 + p]) @ np.abs(coef)
+    Y = b200.MultiVec.from_numpy(y)
+    api.multivec_linear_comb(X, Y, (2, 4), (2 + p, 4 + q), coef, p, None, 0)
+    got = Y.numpy()
+    assert np.max(np.abs(got[:, 4:4 + q] - base) / scale) < 1e-14
+    assert np.array_equal(got[:, :4], y[:, :4]) and np.array_equal(got[:, 4 + q:], y[:, 4 + q:])
+    bv = rng.standard_normal(q)
+    Y = b200.MultiVec.from_numpy(y)
+    api.multivec_linear_comb(X, Y, (2, 4), (2 + p, 4 + q), coef, p, bv, 1)
+    want = base + y[:, 4:4 + q] * bv
+    assert np.max(np.abs(Y.numpy()[:, 4:4 + q] - want) / (scale + np.abs(y[:, 4:4 + q] * bv))) < 1e-14
+
+
+@pytest.mark.parametrize("n", [440, 3000])
+@pytest.mark.parametrize("s1,kb", [(400, 40), (40, 40), (120, 20), (6, 10)])
+def test_linear_comb_in_place_update_like_orth(b200, n, s1, kb):
+    """The update of the block orthogonalisation (host/b200_orth.c: X1 += X0 C with X0, X1 column
+    ranges of ONE multi-vector, beta a single scalar, incb == 0) at the sizes the solver uses,
+    including the coefficient-space call with n = sizeV rows."""
+    from gcge_b200 import api
+    rng = np.random.default_rng(n + s1 + kb)
+    v = np.asfortranarray(rng.standard_normal((n, 480)))
+    V = b200.MultiVec.from_numpy(v)
+    coef = np.asfortranarray(rng.standard_normal((s1, kb)))
+    one = np.array([1.0])
+    api.multivec_linear_comb(V, V, (0, s1), (s1, s1 + kb), coef, s1, one, 0)
+    want = v.copy()
+    want[:, s1:s1 + kb] += v[:, :s1] @ coef
+    got = V.numpy()
+    scale = np.abs(v[:, :s1]) @ np.abs(coef) + np.abs(v[:, s1:s1 + kb])
+    assert np.max(np.abs(got[:, s1:s1 + kb] - want[:, s1:s1 + kb]) / scale) < 1e-14
+    assert np.array_equal(got[:, :s1], v[:, :s1]) and np.array_equal(got[:, s1 + kb:], v[:, s1 + kb:])
+
+
 def test_linear_comb_in_place_disjoint_columns(b200):
     from gcge_b200 import api
     rng = np.random.default_rng(21)
