@@ -535,18 +535,19 @@ lincomb_tma_body(const CUtensorMap *tmx, long long n, int p, int q, const double
 	if (warp == 8) {
 		// ------------------------------------------------------------------ producer warp
 		int slot = 0; unsigned phase = 0;
+		const int cbytes = nt * 8;                     // nt is even: a multiple of 16 bytes
 		for (int kt = 0; kt < ktiles; ++kt) {
 			const int k0 = kt * LC_BK;
 			const int krows = min(LC_BK, p - k0);
 			if (lane == 0) {
 				mbar_spin(empty + slot, phase ^ 1u);
-				mbar_expect_tx(full + slot, (unsigned)(LT_X_BYTES + krows * nt * 8));
+				mbar_expect_tx(full + slot, (unsigned)(LT_X_BYTES + krows * cbytes));
 				tma_load_2d(xs_base + (size_t)slot * LT_X_BYTES, tmx, k0, (int)r0, full + slot);
 			}
 			__syncwarp();
 			if (lane < krows)
 				bulk_load_1d(cs_base + (size_t)slot * LT_C_BYTES + (size_t)lane * LC_SC * 8,
-				             c + (size_t)(k0 + lane) * c_rs + n0, (unsigned)(nt * 8), full + slot);
+				             c + (size_t)(k0 + lane) * c_rs + n0, (unsigned)cbytes, full + slot);
 			if (++slot == LT_NS) { slot = 0; phase ^= 1u; }
 		}
 		return;
@@ -579,6 +580,13 @@ lincomb_tma_body(const CUtensorMap *tmx, long long n, int p, int q, const double
 				dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
 			}
 		}
+		// Every fragment load of this stage must have been PERFORMED before the slot is handed back.  The
+		// mbarrier arrive alone does not wait for shared-memory loads still in flight, and ptxas schedules
+		// it above the last DMMAs (the only instructions that wait for those loads): without this fence
+		// the refill of the slot overtook the last A-fragment loads of a stage about once per 10^9
+		// loads -- whole output rows wrong, only when the consumers were starved (narrow last column
+		// tile, misaligned x) -- found with scripts/lincomb_race.py.
+		asm volatile("fence.acq_rel.cta;" ::: "memory");
 		__syncwarp();
 		if (lane == 0) mbar_arrive(empty + slot);
 		if (++slot == LT_NS) { slot = 0; phase ^= 1u; }
@@ -627,11 +635,7 @@ lincomb_tma_kernel(const __grid_constant__ CUtensorMap tmx, long long n, int p, 
 static int lincomb_tma_launch(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
                               const double *beta_dev, int incb, double *y, int ldy)
 {
-	// OPT-IN (B200_TMA_DENSE=1): on B200 this kernel produced rare wrong entries inside full solves (one
-	// entry in ~10^10, not reproducible call by call: B200_TMA_VERIFY=1 runs it next to the cp.async kernel
-	// and reports differences) although every isolated shape test passes -- a race not yet found.  The
-	// cp.async kernel stays the product path until it is.
-	static const bool on = getenv("B200_TMA_DENSE") != nullptr || getenv("B200_TMA_VERIFY") != nullptr;
+	static const bool on = getenv("B200_NO_TMA_DENSE") == nullptr;
 	if (!on || n < LC_BM || c_cs != 1 || (c_rs & 1) || (q & 1) || ((uintptr_t)c_dev % 16) || ((uintptr_t)x % 16) || (ldx & 1) ||
 	    n > 0x7fffffffLL)
 		return 2;

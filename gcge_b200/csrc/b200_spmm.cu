@@ -640,6 +640,10 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 				else if (w == 3) dia_run_ct<RB, 3, K, KP, CP>(acc, tile, vrow + sp, nd);
 				else             dia_run_ct<RB, 1, K, KP, CP>(acc, tile, vrow + sp, nd);
 			}
+			// the loads from the tile must have been performed before it is handed back (the arrive does not
+			// wait for loads in flight and ptxas may schedule it above the arithmetic that does; see
+			// lincomb_tma_body in b200_dense.cu, where exactly that corrupted results)
+			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty + slot);          // this warp is done with the tile
 			if (++slot == NS) { slot = 0; phase ^= 1u; }

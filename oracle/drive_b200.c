@@ -84,6 +84,13 @@ int drive_gcg_b200(int tier, int n,
 			"mgs", 80, 2, 2 * DBL_EPSILON,
 			30, 1e-2, 1e-14, "abs", 0,
 			-1, gapMin, 2 * DBL_EPSILON, ops);
+	{
+		/* the solver object is a function-static struct of the reference (src/ops_eig_sol_gcg.c:1569):
+		 * what EigenSolverSetParameters_GCG does not cover keeps the value a previous call's options
+		 * left behind, so put the reference's own defaults (:1585-1596) back before parsing argv */
+		GCGSolver *gs = (GCGSolver *)ops->eigen_solver_workspace;
+		gs->compW_cg_order = 1; gs->compW_cg_shift = 0.0; gs->compW_cg_auto_shift = 0;
+	}
 	EigenSolverSetParametersFromCommandLine_GCG(argc, argv, ops);
 	ops->EigenSolver(A, B, eval, evec, nevGiven, &nevConv, ops);
 	double t1 = ops->GetWtime();
