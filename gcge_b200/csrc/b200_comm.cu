@@ -389,7 +389,7 @@ int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 // a flag there, waits for the flags of all the others in its own memory, adds the nranks
 // contributions in rank order -- the same bits on every rank -- and goes on with the scalar update.
 // Two inbox parities: a rank can run at most one allreduce ahead of the slowest (it needs everybody's
-// flag for the one in between).  A wait that lasts longer than ~4 s records a time-out in a status word
+// flag for the one in between).  A wait that lasts longer than ~35 s records a time-out in a status word
 // (checked by the host at the end of the solve) instead of hanging the GPU.
 namespace {
 struct ArState {
@@ -480,6 +480,6 @@ extern "C" int b200k_ar_check(void)
 	int st = 0;
 	B200_CUDA(cudaMemcpyAsync(&st, g_ar.flags + 2 * B200_AR_MAX_RANKS + 1, sizeof(int), cudaMemcpyDeviceToHost, g_b200.stream));
 	B200_CUDA(cudaStreamSynchronize(g_b200.stream));
-	B200_CHECK(st == 0, "in-kernel allreduce: a rank waited more than 4 s for its peers (the ranks no longer run the same sequence of kernels)");
+	B200_CHECK(st == 0, "in-kernel allreduce: a rank waited more than 35 s for its peers (the ranks no longer run the same sequence of kernels)");
 	return 0;
 }

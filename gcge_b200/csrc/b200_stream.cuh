@@ -152,7 +152,7 @@ __device__ __forceinline__ void stream_allreduce_cta(const B200ArCtx &ar, double
 		volatile unsigned *mine = ar.flags[ar.rank] + par * ar.nranks + threadIdx.x;
 		const long long t0 = clock64();
 		while ((int)(*mine - e) < 0) {
-			if (clock64() - t0 > (1ll << 33)) { *ar.status = 1; break; }      // ~4 s: give up instead of hanging
+			if (clock64() - t0 > (1ll << 36)) { *ar.status = 1; break; }      // ~35 s: give up instead of hanging
 		}
 	}
 	__threadfence_system();
