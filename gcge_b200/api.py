@@ -176,17 +176,16 @@ def measure_dmma_peak() -> float:
     return t.value
 
 
-def read_matrix_market(path: str):
-    """On-disk matrix (MatrixMarket coordinate file) -> problems.CCS, through the library's own reader."""
+def _read_ccs_file(fn_name: str, path):
     from . import problems as P
     L = lib()
-    L.b200_ccs_read_matrix_market.argtypes = [C.c_char_p, c_int_p, c_int_p, C.POINTER(c_int_p), C.POINTER(c_int_p),
-                                              C.POINTER(c_dbl_p)]
+    fn = getattr(L, fn_name)
+    fn.argtypes = [C.c_char_p, c_int_p, c_int_p, C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_dbl_p)]
     L.b200_ccs_free.argtypes = [c_int_p, c_int_p, c_dbl_p]
     L.b200_ccs_free.restype = None
     m, n = C.c_int(0), C.c_int(0)
     jc, ir, da = c_int_p(), c_int_p(), c_dbl_p()
-    _chk(L.b200_ccs_read_matrix_market(str(path).encode(), C.byref(m), C.byref(n), C.byref(jc), C.byref(ir), C.byref(da)))
+    _chk(fn(str(path).encode(), C.byref(m), C.byref(n), C.byref(jc), C.byref(ir), C.byref(da)))
     try:
         j_col = np.ctypeslib.as_array(jc, shape=(n.value + 1,)).copy()
         nnz = int(j_col[-1])
@@ -195,6 +194,16 @@ def read_matrix_market(path: str):
     finally:
         L.b200_ccs_free(jc, ir, da)
     return P.CCS(m.value, n.value, j_col.astype(np.int32), i_row.astype(np.int32), data.astype(np.float64))
+
+
+def read_matrix_market(path):
+    """On-disk matrix (MatrixMarket coordinate file) -> problems.CCS, through the library's own reader."""
+    return _read_ccs_file("b200_ccs_read_matrix_market", path)
+
+
+def read_petsc_binary(path):
+    """On-disk matrix (PETSc binary AIJ, MatView/MatLoad format) -> problems.CCS."""
+    return _read_ccs_file("b200_ccs_read_petsc_binary", path)
 
 
 def partition_plan(ccs, rank: int, nranks: int) -> dict:

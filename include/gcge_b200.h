@@ -73,6 +73,8 @@ int  b200_prof_get_gap(int cls, double *ms);
  * arrays (malloc'ed; release with b200_ccs_free): rows ascending inside every column, symmetric
  * files expanded to both triangles.  Host only. */
 int  b200_ccs_read_matrix_market(const char *path, int *nrows, int *ncols, int **j_col, int **i_row, double **data);
+/* PETSc binary matrix (MatView/MatLoad format, big-endian AIJ): the files the reference's SLEPc driver reads */
+int  b200_ccs_read_petsc_binary(const char *path, int *nrows, int *ncols, int **j_col, int **i_row, double **data);
 void b200_ccs_free(int *j_col, int *i_row, double *data);
 
 /* ---- several GPUs: one process per GPU, 1-D contiguous row blocks -----------

@@ -42,3 +42,33 @@ def test_matrix_market_pattern_and_errors(tmp_path):
     (tmp_path / "oob.mtx").write_text("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n")
     with pytest.raises(RuntimeError):
         api.read_matrix_market(tmp_path / "oob.mtx")
+
+
+def _write_petsc(path, m):
+    """PETSc binary AIJ as MatView writes it: big-endian header, row lengths, column indices, values."""
+    m = sp.csr_matrix(m); m.sort_indices()
+    with open(path, "wb") as f:
+        np.array([1211216, m.shape[0], m.shape[1], m.nnz], dtype=">i4").tofile(f)
+        np.diff(m.indptr).astype(">i4").tofile(f)
+        m.indices.astype(">i4").tofile(f)
+        m.data.astype(">f8").tofile(f)
+
+
+def test_petsc_binary(tmp_path):
+    rng = np.random.default_rng(4)
+    g = sp.random(29, 41, density=0.2, random_state=rng, format="csr")
+    _write_petsc(tmp_path / "g.petsc", g)
+    _same(api.read_petsc_binary(tmp_path / "g.petsc"), g)
+    pen = P.p1_fem_kuhn(6)
+    _write_petsc(tmp_path / "b.petsc", pen.B.to_scipy())
+    got = api.read_petsc_binary(tmp_path / "b.petsc")
+    assert np.array_equal(got.j_col, pen.B.j_col) and np.array_equal(got.i_row, pen.B.i_row)
+    assert np.array_equal(got.data, pen.B.data)
+    (tmp_path / "bad.petsc").write_bytes(b"\x00" * 32)
+    with pytest.raises(RuntimeError):
+        api.read_petsc_binary(tmp_path / "bad.petsc")
+    with open(tmp_path / "trunc.petsc", "wb") as f:
+        np.array([1211216, 3, 3, 5], dtype=">i4").tofile(f)
+        np.array([2, 2, 1], dtype=">i4").tofile(f)
+    with pytest.raises(RuntimeError):
+        api.read_petsc_binary(tmp_path / "trunc.petsc")
