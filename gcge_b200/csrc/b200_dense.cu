@@ -197,6 +197,140 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 	}
 }
 
+// ------------------------------------------------------------------ gram, bulk-copy fed
+// Same tiles and fragment loads as gram_partial_body, but the ring is fed by a producer warp with one
+// 1-D bulk copy per tile row (both operands are read in the 4-rows-by-8-columns fragment pattern, which
+// needs rows padded to 68 doubles: no tensor-map swizzle produces that, so the copies go row by row),
+// and the consumers release a stage through an mbarrier -- no cp.async address arithmetic and no
+// __syncthreads in the main loop.  Needs 16-byte aligned operands and even p, q.
+// OPT-IN (B200_TMA_GRAM=1) until it has been through the race checks the LinearComb kernel needed.
+template <int NQ8>
+__device__ __forceinline__ void
+gram_tma_body(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy, long long rows_per_chunk,
+              double *part)
+{
+	extern __shared__ __align__(16) double gsm[];
+	__shared__ unsigned long long full[GR_STAGES], empty[GR_STAGES];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int p0 = blockIdx.x * GR_BP, q0 = blockIdx.z * GR_BQ;
+	const int pt = min(GR_BP, p - p0), qt = min(GR_BQ, q - q0);
+	const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
+	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
+	const int ntiles = (int)((r_end - r_begin + GR_BK - 1) / GR_BK);
+	// columns beyond pt / qt and the rows of a ragged last tile are never copied: no NaN patterns there
+	for (int i = tid; i < GR_STAGES * GR_STAGE_DBL; i += blockDim.x) gsm[i] = 0.0;
+	if (tid == 0) {
+		for (int s = 0; s < GR_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	__syncthreads();
+
+	if (warp == 8) {
+		// ------------------------------------------------------------------ producer warp: lane = tile row
+		int slot = 0; unsigned phase = 0;
+		for (int tile = 0; tile < ntiles; ++tile) {
+			const long long r0 = r_begin + (long long)tile * GR_BK;
+			const int rows = (int)min((long long)GR_BK, r_end - r0);
+			if (lane == 0) {
+				mbar_spin(empty + slot, phase ^ 1u);
+				mbar_expect_tx(full + slot, (unsigned)(rows * (pt + qt) * 8));
+			}
+			__syncwarp();
+			if (lane < rows) {
+				double *Xs = gsm + (size_t)slot * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
+				bulk_load_1d(Xs + lane * GR_S, x + (size_t)(r0 + lane) * ldx + p0, (unsigned)(pt * 8), full + slot);
+				bulk_load_1d(Ys + lane * GR_S, y + (size_t)(r0 + lane) * ldy + q0, (unsigned)(qt * 8), full + slot);
+			}
+			if (++slot == GR_STAGES) { slot = 0; phase ^= 1u; }
+		}
+		return;
+	}
+	// ---------------------------------------------------------------------- consumer warps
+	const int g = lane >> 2, t = lane & 3;
+	const int pw = warp & 3, kh = warp >> 2;
+	const bool p_live = pw * 16 < pt;
+	double acc[2][NQ8][2];
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+#pragma unroll
+		for (int j = 0; j < NQ8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+	int slot = 0; unsigned phase = 0;
+	for (int tile = 0; tile < ntiles; ++tile) {
+		mbar_spin(full + slot, phase);
+		const int rows = (int)min((long long)GR_BK, r_end - (r_begin + (long long)tile * GR_BK));
+		const double *Xs = gsm + (size_t)slot * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
+		if (p_live) {
+#pragma unroll
+			for (int ks = 0; ks < GR_BK / 2; ks += 4) {
+				const int kr = kh * (GR_BK / 2) + ks + t;
+				// rows of a ragged last tile hold an earlier tile's data: their X entries count as zero
+				const bool ok = kr < rows;
+				const double a0 = ok ? Xs[kr * GR_S + pw * 16 + g] : 0.0;
+				const double a1 = ok ? Xs[kr * GR_S + pw * 16 + 8 + g] : 0.0;
+#pragma unroll
+				for (int j = 0; j < NQ8; ++j) {
+					const double b = Ys[kr * GR_S + j * 8 + g];
+					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
+					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
+				}
+			}
+		}
+		// the loads of this stage must have been performed before the slot is handed back (see lincomb_tma_body)
+		asm volatile("fence.acq_rel.cta;" ::: "memory");
+		__syncwarp();
+		if (lane == 0) mbar_arrive(empty + slot);
+		if (++slot == GR_STAGES) { slot = 0; phase ^= 1u; }
+	}
+	// combine the two row halves through shared memory (every stage has been consumed and refilled for the
+	// last time: the ring is dead); consumer-only barrier, the producer warp is gone
+	asm volatile("bar.sync 1, 256;" ::: "memory");
+	double *red = gsm;
+	if (kh == 1) {
+#pragma unroll
+		for (int i = 0; i < 2; ++i)
+#pragma unroll
+			for (int j = 0; j < NQ8; ++j) {
+				const int cr = pw * 16 + i * 8 + g;
+				red[cr * GR_S + j * 8 + 2 * t]     = acc[i][j][0];
+				red[cr * GR_S + j * 8 + 2 * t + 1] = acc[i][j][1];
+			}
+	}
+	asm volatile("bar.sync 1, 256;" ::: "memory");
+	if (kh == 0) {
+		double *out = part + (size_t)blockIdx.y * p * q;
+#pragma unroll
+		for (int i = 0; i < 2; ++i)
+#pragma unroll
+			for (int j = 0; j < NQ8; ++j) {
+				const int cr = pw * 16 + i * 8 + g;
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const int cc = j * 8 + 2 * t + h;
+					if (cr < pt && cc < qt)
+						out[(size_t)(q0 + cc) * p + (p0 + cr)] = acc[i][j][h] + red[cr * GR_S + cc];
+				}
+			}
+	}
+}
+
+__global__ void __launch_bounds__(288, 2)
+gram_tma_kernel(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy, long long rows_per_chunk,
+                double *part)
+{
+	const int qt = min(GR_BQ, q - (int)blockIdx.z * GR_BQ);
+	switch ((qt + 7) >> 3) {                             // uniform over the CTA
+	case 1: gram_tma_body<1>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 2: gram_tma_body<2>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 3: gram_tma_body<3>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 4: gram_tma_body<4>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 5: gram_tma_body<5>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 6: gram_tma_body<6>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 7: gram_tma_body<7>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	default: gram_tma_body<8>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	}
+}
+
 // C[i + j*ldc] = sum_chunks part[chunk][i + j*p]; mode 'S' mirrors the lower triangle.
 __global__ void gram_reduce_kernel(int p, int q, int chunks, const double *__restrict__ part, double alpha,
                                    double *__restrict__ c, int c_rs, int c_cs, int symmetric)
@@ -343,8 +477,17 @@ int b200k_gram(char mode, long long n, int p, int q, double alpha, const double 
 		// even tile widths; anything else takes the 8-byte path
 		const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) &&
 		                  (p % 2 == 0) && (q % 2 == 0);
-		if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
-		else      gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		static const bool tma_gram = getenv("B200_TMA_GRAM") != nullptr;
+		if (al16 && tma_gram) {
+			static bool attr2 = false;
+			if (!attr2) {
+				B200_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				attr2 = true;
+			}
+			gram_tma_kernel<<<grid, 288, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		}
+		else if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		else           gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
 		B200_KERNEL_CHECK();
 		gram_reduce_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, (int)chunks, part, alpha, dst,
 		                                                                        d_rs, d_cs, (!multi && mode == 'S') ? 1 : 0);
