@@ -179,7 +179,7 @@ int b200k_neighbor_exchange(int nnbr, const int *nbr, const double *send_dev, co
 // it needs an SM, so it runs underneath the persistent SpMM CTAs working on the interior rows --
 // an NCCL send/recv kernel on a side stream would simply queue behind them.
 //
-//   sender s -> receiver r, message e (the e-th exchange of the process; all ranks count alike):
+//   sender s -> receiver r, message e (the e-th message on the link s -> r; both ends count it):
 //     s: wait  s.free[r]    >= e-1      r has unpacked my previous message
 //        copy  x rows -> r.mailbox[slot of s]        (2-D: k*8 bytes wide, pitch ldx*8 -> k*8)
 //        write r.arrived[s] =  e
@@ -200,7 +200,9 @@ struct P2P {
 	unsigned *flags = nullptr;          // [0..1] arrived from below / above, [2..3] free of below / above
 	double *peer_mailbox[2] = {nullptr, nullptr};     // below, above
 	unsigned *peer_flags[2] = {nullptr, nullptr};
-	unsigned epoch = 0;
+	// messages sent to / received from the rank below [0] and above [1]: both ends of a link count the
+	// same stream of messages, whatever mix of matrices (with different halos) the exchanges belong to
+	unsigned sent[2] = {0, 0}, recvd[2] = {0, 0};
 	stream_value32_fn wait32 = nullptr, write32 = nullptr;
 } g_p2p;
 
@@ -213,7 +215,8 @@ void p2p_release()
 	}
 	if (g_p2p.mailbox) cudaFree(g_p2p.mailbox);
 	if (g_p2p.flags) cudaFree(g_p2p.flags);
-	g_p2p.mailbox = nullptr; g_p2p.flags = nullptr; g_p2p.region_bytes = 0; g_p2p.ok = false; g_p2p.epoch = 0;
+	g_p2p.mailbox = nullptr; g_p2p.flags = nullptr; g_p2p.region_bytes = 0; g_p2p.ok = false;
+	g_p2p.sent[0] = g_p2p.sent[1] = g_p2p.recvd[0] = g_p2p.recvd[1] = 0;
 	cudaGetLastError();
 }
 
@@ -314,7 +317,8 @@ int b200k_p2p_register(int rows, int *all_ranks_ok)
 		all_good = (flag == 0.0);
 	}
 	if (!all_good) { p2p_release(); return 0; }
-	g_p2p.region_bytes = need; g_p2p.ok = true; g_p2p.epoch = 0;
+	g_p2p.region_bytes = need; g_p2p.ok = true;
+	g_p2p.sent[0] = g_p2p.sent[1] = g_p2p.recvd[0] = g_p2p.recvd[1] = 0;
 	*all_ranks_ok = 1;
 	return 0;
 }
@@ -350,7 +354,6 @@ int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 	cudaStream_t cs = g_b200.comm_stream;
 	B200_CUDA(cudaEventRecord(g_b200.ev_x_ready, g_b200.stream));
 	B200_CUDA(cudaStreamWaitEvent(cs, g_b200.ev_x_ready, 0));
-	const unsigned e = ++g_p2p.epoch;
 	const size_t width = (size_t)k * sizeof(double);
 	// sends
 	for (int i = 0; i < M->nnbr; ++i) {
@@ -359,6 +362,7 @@ int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 		if (nsend <= 0) continue;
 		// at the neighbour I am the rank above (slot 1) if it is below me, and the other way round
 		const int my_slot_there = 1 - side;
+		const unsigned e = ++g_p2p.sent[side];                          // my e-th message on this link
 		if (e > 1) B200_CU(g_p2p.wait32((CUstream)cs, (CUdeviceptr)(g_p2p.flags + 2 + side), e - 1, CU_STREAM_WAIT_VALUE_GEQ));
 		double *dst = (double *)((char *)g_p2p.peer_mailbox[side] + (size_t)my_slot_there * g_p2p.region_bytes);
 		const double *src = x + (size_t)M->send_rows[M->send_off[i]] * ldx;
@@ -370,6 +374,7 @@ int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k)
 		const int side = (M->nbr[i] < g_b200.rank) ? 0 : 1;
 		const int nrecv = M->recv_off[i + 1] - M->recv_off[i];
 		if (nrecv <= 0) continue;
+		const unsigned e = ++g_p2p.recvd[side];                         // the neighbour's e-th message to me
 		B200_CU(g_p2p.wait32((CUstream)cs, (CUdeviceptr)(g_p2p.flags + side), e, CU_STREAM_WAIT_VALUE_GEQ));
 		const double *src = (const double *)((const char *)g_p2p.mailbox + (size_t)side * g_p2p.region_bytes);
 		double *dst = (side == 0) ? x - (size_t)nrecv * ldx : x + (size_t)M->nrows * ldx;
