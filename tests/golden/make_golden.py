@@ -31,6 +31,14 @@ CASES = [
     ("q1_27pt", {"m": 16}, 20),
     ("laplace3d_7pt", {"m": 30}, 50),
     ("p1_fem_kuhn", {"m": 20}, 50),
+    # the block structure of the headline run (nevMax 400, block_size 40, projected problems up to 480)
+    ("p1_fem_kuhn", {"m": 24}, 200),
+    # SURVEY 8f options (appended: the tests address the cases above by position)
+    ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_compW_cg_order", 2)),
+    ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_initX_orth_method", "bgs", "-gcge_compP_orth_method", "bgs",
+                                    "-gcge_compW_orth_method", "bgs")),
+    ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_compW_cg_auto_shift", 1)),
+    ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_compW_cg_shift", 3.0)),
 ]
 
 
@@ -38,12 +46,17 @@ def main():
     ref.set_threads(1)
     out = {"blas": "OpenBLAS 0.3.15 (opencv_python_headless.libs/libopenblasp-r0-59ffcd50.3.15.so), 1 thread",
            "reference_threads": 1, "cases": []}
-    for name, kw, nev in CASES:
+    for case in CASES:
+        name, kw, nev = case[:3]
+        argv = tuple(case[3]) if len(case) > 3 else ()
         pen = getattr(P, name)(**kw)
-        r = ref.gcg_solve(pen.A, pen.B, nev=nev, want_evec=False)
-        out["cases"].append({"generator": name, "args": kw, "nev": nev, "num_iter": r["num_iter"],
-                             "nev_conv": r["nev_conv"], "eval": [float(f"{v:.17g}") for v in r["eval"][:r["nev_conv"]]]})
-        print(name, kw, nev, r["num_iter"], r["nev_conv"], r["eval"][:3])
+        r = ref.gcg_solve(pen.A, pen.B, nev=nev, want_evec=False, argv=argv)
+        rec = {"generator": name, "args": kw, "nev": nev, "num_iter": r["num_iter"],
+               "nev_conv": r["nev_conv"], "eval": [float(f"{v:.17g}") for v in r["eval"][:r["nev_conv"]]]}
+        if argv:
+            rec["argv"] = [str(a) for a in argv]
+        out["cases"].append(rec)
+        print(name, kw, nev, argv, r["num_iter"], r["nev_conv"], r["eval"][:3])
     (Path(__file__).parent / "gcg_reference.json").write_text(json.dumps(out, indent=1))
 
 

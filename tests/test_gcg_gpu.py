@@ -111,7 +111,7 @@ def test_tierB_through_ops_table_and_live_reference(b200, refmod, drive_b200):
     ("-gcge_compW_cg_auto_shift", 1),                                              # A + sigma B through MatAxpby
     ("-gcge_compW_cg_shift", 3.0),
 ])
-def test_tierA_reference_options_over_ops_b200(b200, refmod, drive_b200, argv):
+def test_tierA_reference_options_over_ops_b200(b200, refmod, drive_b200, argv, golden):
     """SURVEY 8f rows 1-2 at tier A: the reference's ComputeW12 (order-2 Krylov W,
     src/ops_eig_sol_gcg.c:697-923), BinaryGramSchmidt / OrthSelfEVP (src/ops_orth.c:122-201,415-640)
     and the shifted inner solve (MatAxpby slot, :594-625) run UNCHANGED over OPS_B200_Set; same
@@ -125,9 +125,12 @@ def test_tierA_reference_options_over_ops_b200(b200, refmod, drive_b200, argv):
     assert abs(a["num_iter"] - r["num_iter"]) <= 1, (a["num_iter"], r["num_iter"])
     k = min(a["nev_conv"], r["nev_conv"])
     assert rel(a["eval"][:k], r["eval"][:k]) < 1e-10
+    case = _golden_case(golden, 12, 10, argv)            # and the recorded run (tests/golden)
+    assert abs(a["num_iter"] - case["num_iter"]) <= 1
+    assert rel(a["eval"][:10], np.array(case["eval"][:10])) < 1e-10
 
 
-def test_device_gcg_order2_krylov_W(b200, refmod):
+def test_device_gcg_order2_krylov_W(b200, refmod, golden):
     """Tier B ComputeW12 (b200_gcg.c: compute_w12) against the live reference with
     -gcge_compW_cg_order 2: eigenvalues 1e-10, iteration count within 2."""
     pen = P.p1_fem_kuhn(12)
@@ -136,6 +139,9 @@ def test_device_gcg_order2_krylov_W(b200, refmod):
     base = b200.gcg_solve(A, B, nev=10)
     assert o["nev_conv"] >= 10
     assert rel(o["eval"][:10], base["eval"][:10]) < 1e-9
+    case = _golden_case(golden, 12, 10, ("-gcge_compW_cg_order", 2))
+    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    assert rel(o["eval"][:10], np.array(case["eval"][:10])) < 1e-10
     if refmod is not None:
         r = refmod.gcg_solve(pen.A, pen.B, nev=10, want_evec=False, argv=("-gcge_compW_cg_order", 2))
         assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
@@ -157,7 +163,15 @@ def test_device_gcg_from_matrix_market_files(b200, tmp_path):
     assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"][:8], o2["eval"][:8])
 
 
-def test_device_gcg_headline_block_structure(b200, refmod):
+def _golden_case(golden, m, nev, argv=()):
+    want = [str(a) for a in argv]
+    for c in golden["cases"]:
+        if c["generator"] == "p1_fem_kuhn" and c["args"] == {"m": m} and c["nev"] == nev and c.get("argv", []) == want:
+            return c
+    raise KeyError((m, nev, argv))
+
+
+def test_device_gcg_headline_block_structure(b200, refmod, golden):
     """nev = 200 (nevMax 400, block_size 40, projected problems of order up to 480) on a small lattice:
     the shapes of the headline run -- contraction lengths far beyond the kernels' tile rings, several
     column tiles, locked columns shifting the block offsets -- which the nev = 10 cases never reach.
@@ -168,6 +182,10 @@ def test_device_gcg_headline_block_structure(b200, refmod):
     assert o["nev_conv"] >= 200 and o["num_iter"] < 60, (o["nev_conv"], o["num_iter"])
     ev = o["eval"][:200]
     assert np.all(np.diff(ev) > -1e-9 * ev[-1]) and ev[0] > 25.0
+    case = _golden_case(golden, 24, 200)                 # the reference's recorded run of the same pencil
+    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    k = min(o["nev_conv"], case["nev_conv"])
+    assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
     if refmod is not None:
         r = refmod.gcg_solve(pen.A, pen.B, nev=200, want_evec=False)
         assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
