@@ -74,6 +74,7 @@ class GCGParams:
     cg_tol_type: str = "abs"
     cg_shift: float = 0.0
     cg_auto_shift: int = 0
+    cg_order: int = 1                # 2: ComputeW12 (reference src/ops_eig_sol_gcg.c:697-923, -gcge_compW_cg_order 2)
     # variants of the device implementation (False/"column" == the reference's algorithm)
     orth_self: str = "column"        # "column" (reference OrthSelf) | "panel" (Gram + Cholesky recurrence)
 
@@ -462,6 +463,38 @@ class GCG:
         s.endW = mgs(s.V, s.startW, s.endW, s.B, s.p.compW_orth, s.p.orth_self)   # :644-663
         s.sizeW = s.endW - s.startW
 
+    # -- reference :697-923: W = [W1 | W2], the inner solve for the first half of the unconverged columns
+    #    and the same systems solved again from W1 as the initial guess
+    def compute_w12(self, offset):
+        s = self
+        ev = s.ss_eval
+        sigma = 0.0
+        if s.p.cg_auto_shift == 1:                                          # :707-713
+            if s.sizeC < 3:
+                d = 3 * (ev[1] - ev[0])
+            else:
+                d = ev[s.sizeC] - ev[s.sizeC - 3]
+            sigma = -ev[s.sizeC] + (d if d > 1 else 1)
+        sigma += s.p.cg_shift
+        cols = []
+        for (o1, o2) in offset:
+            cols.extend(range(o1, o2))
+        cols = cols[:len(cols) // 2]                                        # total_length/2, :740-772
+        k = len(cols)
+        s.startW = s.endP
+        s.V[:, s.startW:s.startW + k] = s.ritz[:, cols]
+        b = _matdot(s.B, s.V[:, cols]) * (ev[cols] + sigma)
+        xw = s.V[:, s.startW:s.startW + k].copy(order="F")
+        n1, _ = block_pcg(s.A, b, xw, s.p.cg_max_iter, s.p.cg_rate, s.p.cg_tol, s.p.cg_tol_type, shift=sigma, B=s.B)
+        s.V[:, s.startW:s.startW + k] = xw
+        xw2 = xw.copy(order="F")                                            # second solve starts from the first, :800-804
+        n2, _ = block_pcg(s.A, b, xw2, s.p.cg_max_iter, s.p.cg_rate, s.p.cg_tol, s.p.cg_tol_type, shift=sigma, B=s.B)
+        s.V[:, s.startW + k:s.startW + 2 * k] = xw2
+        s.cg_iters.append(n1 + n2)
+        s.endW = s.startW + 2 * k
+        s.endW = mgs(s.V, s.startW, s.endW, s.B, s.p.compW_orth, s.p.orth_self)
+        s.sizeW = s.endW - s.startW
+
     def solve(self, seed_already_set=False):
         s, p = self, self.p
         n = s.n
@@ -517,7 +550,10 @@ class GCG:
             else:
                 s.compute_p(s.offsetP)
             s.V[:, s.startN:s.endX] = s.ritz[:, s.startN:s.endX]          # ComputeX, reference :458-471
-            s.compute_w(offsetW)
+            if p.cg_order != 1:
+                s.compute_w12(offsetW)                                      # reference :1451-1456
+            else:
+                s.compute_w(offsetW)
             s.offsetP = offsetW
             s.rayleigh_ritz(nev_conv)
             s.ritz_vec_update()

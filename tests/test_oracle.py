@@ -117,6 +117,21 @@ def test_port_reference_algorithm_vs_golden(golden, idx):
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
 
 
+@pytest.mark.parametrize("argv,kw", [(("-gcge_compW_cg_order", "2"), {"cg_order": 2}),
+                                     (("-gcge_compW_cg_auto_shift", "1"), {"cg_auto_shift": 1}),
+                                     (("-gcge_compW_cg_shift", "3.0"), {"cg_shift": 3.0})])
+def test_port_options_vs_golden(golden, argv, kw):
+    """SURVEY 8f options in the port (ComputeW12, automatic and fixed shift of the inner solve) against
+    the reference's recorded runs with the same command-line options."""
+    case = [c for c in golden["cases"] if c.get("argv") == list(argv)][0]
+    pen = _gen(case)
+    o = G.gcg_solve(pen.A.to_scipy().tocsr(), pen.B.to_scipy().tocsr(), nev=case["nev"], orth_self="column", **kw)
+    assert o["nev_conv"] >= case["nev"]
+    assert abs(o["num_iter"] - case["num_iter"]) <= 1, (o["num_iter"], case["num_iter"])
+    k = min(o["nev_conv"], case["nev_conv"])
+    assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
+
+
 @pytest.mark.parametrize("idx", [0, 1, 2, 3, 4, 5, 6])
 def test_port_device_variant_vs_golden(golden, idx):
     """The variant the device code implements (BCGS2 + Gram/Cholesky panel) against the
