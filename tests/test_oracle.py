@@ -132,6 +132,18 @@ def test_port_options_vs_golden(golden, argv, kw):
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
 
 
+def test_port_device_variant_headline_block_structure(golden):
+    """The device variant of the port at nev = 200 (nevMax 400, block_size 40, projected problems of order
+    up to 480 -- the block structure of the headline benchmark) against the reference's recorded run."""
+    case = [c for c in golden["cases"] if c["nev"] == 200][0]
+    pen = _gen(case)
+    o = G.gcg_solve(pen.A.to_scipy().tocsr(), pen.B.to_scipy().tocsr(), nev=200, orth_self="bcgs2")
+    assert o["nev_conv"] >= 200
+    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    k = min(o["nev_conv"], case["nev_conv"])
+    assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
+
+
 @pytest.mark.parametrize("idx", [0, 1, 2, 3, 4, 5, 6])
 def test_port_device_variant_vs_golden(golden, idx):
     """The variant the device code implements (BCGS2 + Gram/Cholesky panel) against the
