@@ -821,8 +821,26 @@ __global__ void colscale_kernel(long long n, int q, int rows_per_cta, const doub
 	}
 }
 
+static int lincomb_rows(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
+                        const double *beta_dev, int incb, double *y, int ldy);
+
+// Row tiles are gridDim.y of the kernels (at most 65535): blocks with more rows go in several launches.
 int b200k_lincomb(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
                   const double *beta_dev, int incb, double *y, int ldy)
+{
+	const long long max_rows = 65535LL * LC_BM;
+	if (n <= max_rows) return lincomb_rows(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
+	for (long long r0 = 0; r0 < n; r0 += max_rows) {
+		const long long nr = (n - r0 < max_rows) ? n - r0 : max_rows;
+		if (lincomb_rows(nr, p, q, x ? x + (size_t)r0 * ldx : nullptr, ldx, c_dev, c_rs, c_cs, beta_dev, incb,
+		                 y + (size_t)r0 * ldy, ldy))
+			return 1;
+	}
+	return 0;
+}
+
+static int lincomb_rows(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
+                        const double *beta_dev, int incb, double *y, int ldy)
 {
 	if (n <= 0 || q <= 0) return 0;
 	cudaStream_t st = g_b200.stream;
