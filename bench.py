@@ -22,9 +22,22 @@ cpu_baseline / --impl reference
          and tolerances on a smaller lattice, solved to convergence), scaled linearly in n and
          in the outer-iteration count to the full workload -- see `sample` in the JSON line.
 
+same_size  a MEASURED pair at one size both arms can run: the reference solves --same-m (default 40:
+         n = 64 000, same nev / block size / tolerances) to convergence on the host cores, the device
+         solver is timed on the same pencil in the same run -- beside the extrapolated full-size figure.
+parity_vs_golden
+         before the timed region EVERY rank solves two of the reference's recorded runs
+         (tests/golden/gcg_reference.json: p1_fem_kuhn m = 12 nev = 10 and m = 24 nev = 200) and the line
+         carries iteration counts, eigenvalue differences and whether all ranks hold identical bits.
+
+Other workloads of BASELINE.json (same line format): --workload laplace7 --m 100 --nev 50 (config 2,
+standard problem, analytic eigenvalues as the parity pin), --workload q1_27pt (config 4's operator).
+
 Multi-GPU (torchrun, one rank per GPU): the SAME pencil is split into 1-D row blocks over the N
-GPUs (strong scaling): halo rows of SpMM by ncclSend/ncclRecv, Gram blocks / dots / CG scalars by
-ncclAllReduce, projected problem replicated.  value = seconds per solve, max over ranks.
+GPUs (strong scaling): SpMM halo rows travel by copy-engine peer-to-peer copies into IPC mailboxes
+over NVLink (overlapped with the interior rows), the CG scalars are allreduced inside the streaming
+kernels over NVLink, Gram blocks by ncclAllReduce, projected problem replicated.  value = seconds per
+solve, max over ranks.
 """
 from __future__ import annotations
 
@@ -119,31 +132,60 @@ def iters_full(m: int, nev: int, fallback: int) -> tuple[int, str]:
         return fallback, "fallback (no recorded B200 run for this size)"
 
 
-def reference_sample(m_full: int, nev: int, m_ref: int, it_ref: int, threads: int) -> dict:
-    """One bounded sample of the reference's own GCG (oracle/_ref, unmodified sources):
-    P1-FEM pencil at m_ref^3, same nev / nevMax / block_size / tolerances, it_ref outer
-    iterations from srand(0) (InitializeX included)."""
+WORKLOADS = {"p1_fem": "p1_fem_kuhn", "laplace7": "laplace3d_7pt", "q1_27pt": "q1_27pt"}
+
+
+def make_pencil(workload: str, m: int):
     from gcge_b200 import problems as P
+    return getattr(P, WORKLOADS[workload])(m)
+
+
+def reference_sample(workload: str, nev: int, m_ref: int, it_ref: int, threads: int) -> dict:
+    """One bounded sample of the reference's own GCG (oracle/_ref, unmodified sources): the
+    workload's pencil at m_ref^3, same nev / nevMax / block_size / tolerances, up to it_ref outer
+    iterations from srand(0) (InitializeX included)."""
     from oracle import ref
     ref.set_threads(threads)
-    pen = P.p1_fem_kuhn(m_ref)
+    pen = make_pencil(workload, m_ref)
     r = ref.gcg_solve(pen.A, pen.B, nev=nev, max_iter=it_ref, want_evec=False)
-    return {"seconds": r["seconds"], "num_iter": r["num_iter"], "n": pen.A.ncols, "m": m_ref}
+    return {"seconds": r["seconds"], "num_iter": r["num_iter"], "nev_conv": r["nev_conv"], "n": pen.A.ncols, "m": m_ref,
+            "generator": WORKLOADS[workload], "eval": r["eval"]}
 
 
 def scale_reference(sample: dict, m_full: int, nev: int) -> tuple[float, str]:
     n_full = m_full ** 3
+    if sample["m"] == m_full:
+        return sample["seconds"], (f"reference GCG (oracle/_ref, CCS+OpenMP, unmodified) solving {sample['generator']} "
+                                   f"m={m_full} (n={n_full}), nev={nev}, AT FULL SIZE to convergence: {sample['num_iter']} outer "
+                                   f"iterations, {sample['seconds']:.2f} s incl. InitializeX -- measured, not scaled")
     itf, src = iters_full(m_full, nev, fallback=100)
     per_row_iter = sample["seconds"] / sample["n"] / max(sample["num_iter"], 1)
     value = per_row_iter * n_full * itf
-    desc = (f"reference GCG (oracle/_ref, CCS+OpenMP, unmodified) solving p1_fem_kuhn m={sample['m']} (n={sample['n']}), "
+    desc = (f"reference GCG (oracle/_ref, CCS+OpenMP, unmodified) solving {sample['generator']} m={sample['m']} (n={sample['n']}), "
             f"nev={nev}, to convergence: {sample['num_iter']} outer iterations, {sample['seconds']:.2f} s incl. "
             f"InitializeX; scaled linearly x(n {n_full}/{sample['n']}) x(outer iterations {itf}/{sample['num_iter']}; "
             f"{itf} = full solve, {src}).  The sample fits the host caches, so this flatters the CPU.")
     return value, desc
 
 
+def pick_reference_size(cal: dict, m_full: int, budget_s: float) -> int:
+    """Largest lattice (multiple of 8) whose reference solve is expected to fit budget_s: seconds ~ rows x
+    outer iterations; the calibration sample is cache-resident, so a factor 2 of margin."""
+    per_row = cal["seconds"] / cal["n"]
+    best = cal["m"]
+    for m in range(cal["m"] + 8, m_full + 1, 8):
+        if per_row * m ** 3 * 2.0 <= budget_s:
+            best = m
+    if m_full > best and per_row * m_full ** 3 * 2.0 <= budget_s:
+        best = m_full
+    return best
+
+
 def run_reference(a) -> int:
+    """Reference arm: the UNMODIFIED reference on the host cores.  One calibration solve at --ref-m, then ONE
+    real solve, to convergence, at the largest lattice expected to fit --ref-budget seconds (the whole arm
+    must end within minutes, so the K timed steps of the launch are not K repetitions of it); `value` is
+    that solve scaled to the full workload (rows x outer iterations), `measured` is the solve itself."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
@@ -153,18 +195,22 @@ def run_reference(a) -> int:
                           "(needs /root/reference at build time)"}))
         return 0
     cores = host_cores()
-    vals, last = [], None
-    for i in range(a.warmup + a.steps):
-        s = reference_sample(a.m, a.nev, a.ref_m, a.ref_iters, cores)
-        v, desc = scale_reference(s, a.m, a.nev)
-        if i >= a.warmup:
-            vals.append(v); last = desc
-    value = float(np.mean(vals))
+    cal = reference_sample(a.workload, a.nev, min(a.ref_m, a.m), a.ref_iters, cores)
+    m_big = a.ref_big_m if a.ref_big_m > 0 else pick_reference_size(cal, a.m, a.ref_budget)
+    big = cal if m_big == cal["m"] else reference_sample(a.workload, a.nev, m_big, a.ref_iters, cores)
+    value, desc = scale_reference(big, a.m, a.nev)
+    desc += (f"  [calibration: m={cal['m']} in {cal['seconds']:.2f} s; one solve measured, the --steps/--warmup of this "
+             f"arm are not repetitions]")
+    cfg = workload_config(a, 1)
+    cfg["reference_ran"] = {"m": big["m"], "n": big["n"], "nev": a.nev, "scaled_to_m": a.m}
     line = {"impl": "reference", "metric": "gcg_solve_seconds", "value": value, "unit": "s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a, 1),
-            "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "reference", "sample": last},
+            "config": cfg,
+            "extrapolated": big["m"] != a.m,
+            "measured": {"m": big["m"], "n": big["n"], "nev": a.nev, "seconds": big["seconds"],
+                         "num_iter": big["num_iter"], "nev_conv": big["nev_conv"], "cores": cores},
+            "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "reference", "sample": desc},
             "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -172,12 +218,21 @@ def run_reference(a) -> int:
 
 
 def workload_config(a, n_gpus: int) -> dict:
-    return {"workload": f"3D P1-FEM stiffness/mass pencil A x = lambda B x (Kuhn triangulation), n = {a.m}^3 = "
-                        f"{a.m ** 3}, nev = {a.nev} (nevMax {2 * a.nev}, block_size {a.nev // 5 if a.nev >= 30 else a.nev}), "
-                        f"B-orthogonal GCG with BlockPCG, tol = (1e-1, 1e-8), srand(0)",
-            "generator": "gcge_b200.problems.p1_fem_kuhn", "m": a.m, "nev": a.nev,
-            "parallelism": "single GPU" if n_gpus == 1 else f"1-D row blocks over {n_gpus} GPUs (NCCL halo exchange + allreduce, replicated Rayleigh-Ritz)",
-            "l2": "inputs >> L2 (matrices 2.9 GB, multi-vectors 64 GB at m=200); no flush needed"}
+    nev, m = a.nev, a.m
+    bs = nev // 5 if nev >= 30 else nev
+    what = {"p1_fem": "3D P1-FEM stiffness/mass pencil A x = lambda B x (Kuhn triangulation)",
+            "laplace7": "3D 7-point Laplacian, standard problem A x = lambda x (B = NULL)",
+            "q1_27pt": "3D 27-point trilinear (Q1) stiffness/mass pencil A x = lambda B x"}[a.workload]
+    par = "single GPU" if n_gpus == 1 else (
+        f"1-D row blocks over {n_gpus} GPUs (SpMM halos by copy-engine P2P mailboxes over NVLink, CG scalars "
+        f"allreduced in-kernel over NVLink, Gram blocks by ncclAllReduce, replicated Rayleigh-Ritz)")
+    mv_gb = 8.0 * m ** 3 * (2 * (2 * nev + 2 * bs) + 2 * nev + 3 * bs) / 1e9
+    return {"workload": f"{what}, n = {m}^3 = {m ** 3}, nev = {nev} (nevMax {2 * nev}, block_size {bs}), "
+                        f"{'B-orthogonal ' if a.workload != 'laplace7' else ''}GCG with BlockPCG, tol = (1e-1, 1e-8), srand(0)",
+            "generator": f"gcge_b200.problems.{WORKLOADS[a.workload]}", "m": m, "nev": nev,
+            "parallelism": par,
+            "l2": f"inputs >> L2 (multi-vectors {mv_gb:.1f} GB at m={m}); no flush needed" if mv_gb > 1.0 else
+                  "L2 flushed between solves (b200_flush_l2)"}
 
 
 def residual_check(api, A, B, evec, ev, npairs, prm, n, width=40) -> dict:
@@ -208,6 +263,42 @@ def residual_check(api, A, B, evec, ev, npairs, prm, n, width=40) -> dict:
             "max_abs_xBx_minus_1": float(np.abs(bnorm - 1.0).max()), "tol": [tol0, tol1]}
 
 
+def golden_parity(api, dist, cases=(4, 9)) -> list:
+    """Every rank solves recorded reference runs (tests/golden/gcg_reference.json, produced by the unmodified
+    reference through tests/golden/make_golden.py) with the device solver -- row-partitioned over all ranks of
+    the job -- and compares: outer iterations (contract: within 1), eigenvalues (1e-10 relative), converged
+    count, and whether every rank ended with bit-identical eigenvalues."""
+    import torch
+    from gcge_b200 import problems as P
+    gold = json.loads((ROOT / "tests" / "golden" / "gcg_reference.json").read_text())["cases"]
+    out = []
+    for idx in cases:
+        c = gold[idx]
+        pen = getattr(P, c["generator"])(**c["args"])
+        A = api.Mat(pen.A); B = None if pen.B is None else api.Mat(pen.B)
+        o = api.gcg_solve(A, B, nev=c["nev"])
+        k = min(o["nev_conv"], c["nev_conv"])
+        ref_ev = np.array(c["eval"][:k])
+        err = float(np.max(np.abs(o["eval"][:k] - ref_ev) / np.abs(ref_ev))) if k else None
+        same = True
+        if dist is not None:
+            ev = torch.from_numpy(o["eval"].copy()).cuda()
+            ev0 = ev.clone()
+            dist.broadcast(ev0, 0)
+            flag = torch.tensor([1 if torch.equal(ev.view(torch.int64), ev0.view(torch.int64)) else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            same = bool(flag.item())
+        out.append({"case": f"{c['generator']} {c['args']} nev={c['nev']}", "num_iter": int(o["num_iter"]),
+                    "ref_num_iter": int(c["num_iter"]), "nev_conv": int(o["nev_conv"]), "ref_nev_conv": int(c["nev_conv"]),
+                    "max_rel_eval": err, "bitwise_identical_across_ranks": same,
+                    "ok": bool(abs(o["num_iter"] - c["num_iter"]) <= 1 and err is not None and err < 1e-10
+                               and o["nev_conv"] >= c["nev"] and same)})
+        o["evec_mv"].close(); A.close()
+        if B is not None:
+            B.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------- ours
 def run_b200(a) -> int:
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -222,14 +313,22 @@ def run_b200(a) -> int:
     if world > 1:
         api.comm_init_from_torch()
 
+    # ---- parity against the reference's recorded runs, on all ranks, before anything is timed
+    par_gold = None
+    if not a.no_parity:
+        try:
+            par_gold = golden_parity(api, dist)
+        except Exception as exc:
+            par_gold = [{"error": str(exc)[:300], "ok": False}]
+
     t0 = time.time()
-    pen = P.p1_fem_kuhn(a.m)
+    pen = make_pencil(a.workload, a.m)
     n, nnz = pen.A.ncols, pen.A.nnz
-    host_arrays = [pen.A.j_col, pen.A.i_row, pen.A.data, pen.B.j_col, pen.B.i_row, pen.B.data]
+    host_arrays = [pen.A.j_col, pen.A.i_row, pen.A.data] + ([] if pen.B is None else [pen.B.j_col, pen.B.i_row, pen.B.data])
     for h in host_arrays:
         api.host_register(h)
     t_gen = time.time() - t0
-    A, B = api.Mat(pen.A), api.Mat(pen.B)
+    A, B = api.Mat(pen.A), (None if pen.B is None else api.Mat(pen.B))
     prm = api.default_params(a.nev)
     evec = api.MultiVec(n, prm.nevMax)
 
@@ -282,7 +381,9 @@ def run_b200(a) -> int:
         parity = {"error": str(exc)[:200]}
 
     # ---- e2e: host CCS arrays -> upload -> workspaces -> solve -> eigenpairs back on the host
-    A.close(); B.close()
+    A.close()
+    if B is not None:
+        B.close()
     for w in ws:
         w.close()
     nev_out = a.nev
@@ -293,13 +394,15 @@ def run_b200(a) -> int:
     for i in range(a.e2e_steps):
         barrier()
         w0 = time.time()
-        A2, B2 = api.Mat(pen.A), api.Mat(pen.B)
+        A2, B2 = api.Mat(pen.A), (None if pen.B is None else api.Mat(pen.B))
         o2 = solve(A2, B2)
         evec.numpy_local(0, nev_out, out=host_vec)
         ev_host = o2["eval"][:nev_out].copy()
         barrier()
         e2e_s.append(time.time() - w0)
-        A2.close(); B2.close()
+        A2.close()
+        if B2 is not None:
+            B2.close()
     e2e = float(np.mean(e2e_s)) if e2e_s else None
     if dist is not None and e2e is not None:
         t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
@@ -359,35 +462,67 @@ def run_b200(a) -> int:
         extra["spmm_GBs"] = round(spmm["bytes"] / spmm["ms"] / 1e6, 1)
         extra["spmm_frac_hbm"] = round(spmm["bytes"] / spmm["ms"] / 1e6 / hbm_peak, 4)
 
-    # ---- CPU baseline: the reference itself on the host cores, bounded sample -----------------
-    cpu = None
+    # ---- CPU baseline: the reference itself on the host cores, bounded sample, and the same-size pair -----
+    cpu, same = None, None
     if world == 1 and not a.no_cpu:
         try:
             from oracle import ref
             if ref.available():
                 cores = host_cores()
-                s = reference_sample(a.m, a.nev, a.ref_m, a.ref_iters, cores)
+                m_s = min(a.same_m, a.m)
+                s = reference_sample(a.workload, a.nev, m_s, a.ref_iters, cores)
                 try:
                     ITERS_FILE.parent.mkdir(exist_ok=True)
                     d = json.loads(ITERS_FILE.read_text()) if ITERS_FILE.exists() else {}
-                    if a.max_iter <= 0:
+                    if a.max_iter <= 0 and a.workload == "p1_fem":
                         d[f"m{a.m}_nev{a.nev}"] = {"num_iter": int(out["num_iter"]), "nev_conv": int(out["nev_conv"])}
                         ITERS_FILE.write_text(json.dumps(d, indent=1, sort_keys=True) + "\n")
                 except Exception:
                     pass
                 v, desc = scale_reference(s, a.m, a.nev)
                 cpu = {"value": v, "unit": "s", "cores": cores, "kind": "reference", "sample": desc}
+                # the device solver on the very same pencil, in the same run: a measured pair
+                pen_s = pen if m_s == a.m else make_pencil(a.workload, m_s)
+                w0 = time.time()
+                As, Bs = api.Mat(pen_s.A), (None if pen_s.B is None else api.Mat(pen_s.B))
+                ev_s = api.MultiVec(pen_s.A.ncols, prm.nevMax)
+                o_w = api.gcg_solve(As, Bs, nev=a.nev, evec=ev_s, seed=0)           # warm-up (and the e2e-style wall time)
+                host_s = ev_s.numpy(0, a.nev)
+                api.sync()
+                e2e_same = time.time() - w0
+                api.timer_start()
+                o_s = api.gcg_solve(As, Bs, nev=a.nev, evec=ev_s, seed=0)
+                dev_s = api.timer_stop() / 1e3
+                k = min(int(o_s["nev_conv"]), int(s["nev_conv"]))
+                err = float(np.max(np.abs(o_s["eval"][:k] - s["eval"][:k]) / np.abs(s["eval"][:k]))) if k else None
+                same = {"m": m_s, "n": pen_s.A.ncols, "nev": a.nev, "generator": WORKLOADS[a.workload],
+                        "reference_s": s["seconds"], "reference_cores": cores, "reference_num_iter": s["num_iter"],
+                        "reference_nev_conv": s["nev_conv"],
+                        "b200_s": dev_s, "b200_e2e_s": e2e_same, "b200_num_iter": int(o_s["num_iter"]),
+                        "b200_nev_conv": int(o_s["nev_conv"]), "max_rel_eval_vs_reference": err,
+                        "ratio_reference_over_b200": s["seconds"] / dev_s if dev_s > 0 else None,
+                        "ratio_reference_over_b200_e2e": s["seconds"] / e2e_same if e2e_same > 0 else None,
+                        "note": "both arms measured in this run on this box at the same size, both to convergence from srand(0); "
+                                "b200_e2e_s = matrices from host CCS + workspaces + solve + eigenvectors back (first call: includes "
+                                "one-time module loading for kernels of this width)"}
+                del host_s
+                ev_s.close(); As.close()
+                if Bs is not None:
+                    Bs.close()
             else:
                 cpu = {"value": None, "unit": "s", "cores": 0, "kind": "reference",
                        "sample": "oracle/_ref not present on this box"}
         except Exception as e:  # the baseline must never take the GPU number down with it
-            cpu = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+            cpu = cpu or {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+            same = {"error": str(e)[:300]}
 
     line = {"metric": "gcg_solve_seconds", "value": sec, "unit": "s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, world),
+            "parity_vs_golden": par_gold,
             "parity_at_full_size": parity,
+            "same_size": same,
             "result": {"num_iter": int(out["num_iter"]), "nev_conv": int(out["nev_conv"]),
                        "eval_first": float(out["eval"][0]), "eval_nev": float(out["eval"][a.nev - 1]),
                        "wall_s_per_step": wall / a.steps},
@@ -413,13 +548,20 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="p1_fem", choices=sorted(WORKLOADS),
+                    help="p1_fem: BASELINE config 3 (default); laplace7: config 2; q1_27pt: config 4's operator")
     ap.add_argument("--m", type=int, default=200, help="lattice size: n = m^3 unknowns (200 -> 8.0 M)")
     ap.add_argument("--nev", type=int, default=200)
     ap.add_argument("--max-iter", type=int, default=0, help="cap on outer iterations (0 = reference default 500)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-m", type=int, default=24, help="lattice size of the reference's bounded sample")
     ap.add_argument("--ref-iters", type=int, default=500, help="outer-iteration cap of the reference's bounded sample")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / same_size leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity solves before the timed region")
+    ap.add_argument("--same-m", type=int, default=40, help="lattice size of the measured same-size pair (reference on the "
+                    "host cores and device solver on the same pencil); also the sample the cpu_baseline is scaled from")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: seconds the one real solve may take")
+    ap.add_argument("--ref-big-m", type=int, default=0, help="--impl reference: lattice size of the real solve (0: pick by budget)")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)

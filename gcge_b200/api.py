@@ -446,10 +446,11 @@ def gcg_workspace(n: int, p) -> list:
 
 
 def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=None, max_iter=0, verbose=False,
-              evec=None, seed=0, ws=None, **overrides):
+              evec=None, seed=0, ws=None, nev_given=0, **overrides):
     """slot EigenSolver (reference src/ops.h:146-147) through b200_gcg_solve, with the driver
     defaults of reference test/test_eig_sol_gcg.c:33-115.  ``A``/``B`` are :class:`Mat`.
-    Seeds glibc rand() like the reference driver unless seed is None."""
+    Seeds glibc rand() like the reference driver unless seed is None.  ``nev_given`` > 0: warm start
+    from the first nev_given columns of ``evec`` (reference src/ops_eig_sol_gcg.c:107-109)."""
     p = default_params(nev)
     if nev_max > 0:
         p.nevMax = nev_max
@@ -477,7 +478,9 @@ def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=None, 
     ws_c = None
     if ws is not None:
         ws_c = (C.c_void_p * 4)(*[w.h for w in ws])
-    _chk(lib().b200_gcg_solve(A.h, None if B is None else B.h, _dp(ev), evec.h, 0, C.byref(nconv), C.byref(p),
+    if nev_given > 0 and own:
+        raise B200Error("gcg_solve: nev_given needs the caller's evec multi-vector")
+    _chk(lib().b200_gcg_solve(A.h, None if B is None else B.h, _dp(ev), evec.h, int(nev_given), C.byref(nconv), C.byref(p),
                               ws_c, C.byref(st)))
     out = {"eval": ev, "num_iter": st.numIter, "nev_conv": nconv.value, "evec_mv": evec,
            "stats": {k: getattr(st, k) for k, _ in _GCGStats._fields_}}

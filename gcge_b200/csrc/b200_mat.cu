@@ -436,14 +436,59 @@ extern "C" int b200_mat_to_ccs(const b200_mat *A, int *j_col, int *i_row, double
 	return 0;
 }
 
-// values only: Y = alpha X + beta Y elementwise over the nnz array (identical patterns)
-__global__ void mat_axpby_kernel(int nnz, double alpha, const double *__restrict__ x, double beta,
-                                 double *__restrict__ y)
+// ---- Y = alpha X + beta Y, slot MatAxpby (reference src/ops.h:52; used by GCG for the in-place shift
+// A + sigma B, src/ops_eig_sol_gcg.c:594-602).  The pattern of X must be a SUBSET of Y's (the reference's
+// SLEPc back end passes SUBSET_NONZERO_PATTERN, app/app_slepc.c; e.g. A = stiffness, B = lumped mass).
+// Everything is validated before anything is modified.
+
+// one thread per row: merge-walk the ascending column lists of X's and Y's row; pos[e] = index of X's entry
+// e in Y's arrays, or -1 (counted in *missing)
+__global__ void mat_locate_kernel(int nrows, const int *__restrict__ xrp, const int *__restrict__ xci,
+                                  const int *__restrict__ yrp, const int *__restrict__ yci, int *__restrict__ pos,
+                                  int *missing)
 {
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x) {
-		// same operation order as a BLAS dscal followed by daxpy
-		double v = (beta == 1.0) ? y[i] : beta * y[i];
-		y[i] = fma(alpha, x[i], v);
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	int ey = yrp[r];
+	const int ey1 = yrp[r + 1];
+	int miss = 0;
+	for (int ex = xrp[r]; ex < xrp[r + 1]; ++ex) {
+		const int c = xci[ex];
+		while (ey < ey1 && yci[ey] < c) ++ey;
+		if (ey < ey1 && yci[ey] == c) pos[ex] = ey;
+		else { pos[ex] = -1; ++miss; }
+	}
+	if (miss) atomicAdd(missing, miss);
+}
+
+__global__ void mat_scale_kernel(long long cnt, double beta, double *__restrict__ y)
+{
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x)
+		y[i] = beta * y[i];
+}
+
+// same operation order as a BLAS dscal followed by daxpy
+__global__ void mat_scatter_add_kernel(int nnz, double alpha, const double *__restrict__ x, const int *__restrict__ pos,
+                                       double *__restrict__ y)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x)
+		y[pos[i]] = fma(alpha, x[i], y[pos[i]]);
+}
+
+// the diagonal image of Y: entry (r, c) of X lands in slot start_g + (c - r - off_g) of row r
+__global__ void mat_dia_add_kernel(int nrows, const int *__restrict__ xrp, const int *__restrict__ xci,
+                                   const double *__restrict__ xva, double alpha, int ng, const int *__restrict__ off,
+                                   const int *__restrict__ grp, int ndp, double *__restrict__ dia, int *missing)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	for (int e = xrp[r]; e < xrp[r + 1]; ++e) {
+		const int d = xci[e] - r;
+		int slot = -1;
+		for (int g = 0; g < ng; ++g)
+			if (d >= off[g] && d < off[g] + grp[2 * g + 1]) slot = grp[2 * g] + (d - off[g]);
+		if (slot < 0) { if (missing) atomicAdd(missing, 1); continue; }
+		if (dia) dia[(size_t)r * ndp + slot] = fma(alpha, xva[e], dia[(size_t)r * ndp + slot]);
 	}
 }
 
@@ -451,26 +496,68 @@ extern "C" int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200
 {
 	B200_REQUIRE_INIT();
 	B200_CHECK(X && Y, "b200_mat_axpby: NULL matrix");
-	B200_CHECK(X->nrows == Y->nrows && X->ncols == Y->ncols && X->nnz == Y->nnz,
-	           "b200_mat_axpby: shape/nnz mismatch (identical sparsity patterns required)");
-	if (Y->nnz == 0) return 0;
-	const int threads = 256;
-	const int blocks = b200_ceil_div(Y->nnz, threads) < g_b200.num_sms * 8 ? b200_ceil_div(Y->nnz, threads)
-	                                                                      : g_b200.num_sms * 8;
-	mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->va, beta, Y->va);
-	B200_KERNEL_CHECK();
-	if (Y->dia_nd) {
-		// identical patterns => identical diagonal structure; the slots absent from the pattern stay 0
-		B200_CHECK(X->dia_nd == Y->dia_nd, "b200_mat_axpby: diagonal images differ");
-		const long long cnt = (long long)Y->nrows * Y->dia_ndp;
-		B200_CHECK(cnt < 0x7fffffffLL, "b200_mat_axpby: diagonal image too large");
-		mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>((int)cnt, alpha, X->dia_val, beta, Y->dia_val);
-		B200_KERNEL_CHECK();
+	B200_CHECK(X->nrows == Y->nrows && X->ncols == Y->ncols && X->row0 == Y->row0 &&
+	           X->nrows_global == Y->nrows_global, "b200_mat_axpby: shapes differ");
+	if (b200_multi()) {
+		// the local column numbering must agree: contiguous halos number columns by global index; halo
+		// lists number them by slot, so the lists must be the same
+		bool same = X->halo_contiguous == Y->halo_contiguous && X->halo_below <= Y->halo_below;
+		if (same && !X->halo_contiguous) {
+			same = X->nhalo == Y->nhalo;
+			for (int i = 0; same && i < X->nhalo; ++i) same = X->halo_cols[i] == Y->halo_cols[i];
+		}
+		B200_CHECK(same, "b200_mat_axpby: across ranks the two matrices need the same halo numbering");
 	}
-	if (!Y->t_shared && Y->t_va) {
-		B200_CHECK(X->t_va, "b200_mat_axpby: internal");
-		mat_axpby_kernel<<<blocks, threads, 0, g_b200.stream>>>(Y->nnz, alpha, X->t_va, beta, Y->t_va);
+	cudaStream_t st = g_b200.stream;
+	const int threads = 256;
+	const int row_blocks = b200_ceil_div(Y->nrows > 0 ? Y->nrows : 1, threads);
+	// ---- validate: every entry of X must exist in Y (CSR image, transpose image, diagonal image)
+	int *pos = (int *)b200_scratch(2, sizeof(int) * ((size_t)2 * (X->nnz > 0 ? X->nnz : 1) + 4));
+	if (!pos) return 1;
+	int *pos_t = pos + (X->nnz > 0 ? X->nnz : 1), *missing = pos_t + (X->nnz > 0 ? X->nnz : 1);
+	B200_CUDA(cudaMemsetAsync(missing, 0, sizeof(int), st));
+	const bool own_t = !Y->t_shared && Y->t_va;
+	if (X->nnz > 0) {
+		mat_locate_kernel<<<row_blocks, threads, 0, st>>>(X->nrows, X->rp, X->ci, Y->rp, Y->ci, pos, missing);
 		B200_KERNEL_CHECK();
+		if (own_t) {
+			B200_CHECK(X->t_rp && X->t_ci && X->t_va, "b200_mat_axpby: internal (no transpose image of X)");
+			mat_locate_kernel<<<b200_ceil_div(X->ncols, threads), threads, 0, st>>>(X->ncols, X->t_rp, X->t_ci, Y->t_rp, Y->t_ci,
+			                                                                     pos_t, missing);
+			B200_KERNEL_CHECK();
+		}
+		if (Y->dia_nd) {
+			mat_dia_add_kernel<<<row_blocks, threads, 0, st>>>(X->nrows, X->rp, X->ci, X->va, 0.0, Y->dia_ng, Y->dia_off,
+			                                                  Y->dia_grp, Y->dia_ndp, nullptr, missing);
+			B200_KERNEL_CHECK();
+		}
+	}
+	int missing_h = 0;
+	B200_CUDA(cudaMemcpyAsync(&missing_h, missing, sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	B200_CHECK(missing_h == 0, "b200_mat_axpby: %d entries of X have no counterpart in Y (the pattern of X must be a "
+	           "subset of Y's, as SUBSET_NONZERO_PATTERN in the reference's SLEPc back end); Y is unchanged", missing_h);
+	// ---- update
+	const int sm8 = g_b200.num_sms * 8;
+	auto blocks_for = [&](long long cnt) { long long b = (cnt + threads - 1) / threads; return (int)(b < sm8 ? (b > 0 ? b : 1) : sm8); };
+	const long long dia_cnt = Y->dia_nd ? (long long)Y->nrows * Y->dia_ndp : 0;
+	if (beta != 1.0) {
+		if (Y->nnz > 0) { mat_scale_kernel<<<blocks_for(Y->nnz), threads, 0, st>>>(Y->nnz, beta, Y->va); B200_KERNEL_CHECK(); }
+		if (own_t && Y->nnz > 0) { mat_scale_kernel<<<blocks_for(Y->nnz), threads, 0, st>>>(Y->nnz, beta, Y->t_va); B200_KERNEL_CHECK(); }
+		if (dia_cnt > 0) { mat_scale_kernel<<<blocks_for(dia_cnt), threads, 0, st>>>(dia_cnt, beta, Y->dia_val); B200_KERNEL_CHECK(); }
+	}
+	if (X->nnz > 0 && alpha != 0.0) {
+		mat_scatter_add_kernel<<<blocks_for(X->nnz), threads, 0, st>>>(X->nnz, alpha, X->va, pos, Y->va);
+		B200_KERNEL_CHECK();
+		if (own_t) {
+			mat_scatter_add_kernel<<<blocks_for(X->nnz), threads, 0, st>>>(X->nnz, alpha, X->t_va, pos_t, Y->t_va);
+			B200_KERNEL_CHECK();
+		}
+		if (dia_cnt > 0) {
+			mat_dia_add_kernel<<<row_blocks, threads, 0, st>>>(X->nrows, X->rp, X->ci, X->va, alpha, Y->dia_ng, Y->dia_off,
+			                                                  Y->dia_grp, Y->dia_ndp, Y->dia_val, nullptr);
+			B200_KERNEL_CHECK();
+		}
 	}
 	return 0;
 }

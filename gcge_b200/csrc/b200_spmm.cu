@@ -515,14 +515,25 @@ static int launch_spmm_dia(const b200_mat *M, const double *x, int ldx, double *
 //     just pulled through L2 by the TMA unit, so the dot is a few FMAs in the epilogue and the
 //     separate 16nk-byte streaming pass over p and w disappears.  Per-CTA partial sums go to
 //     dot_part[cta][k]; the caller adds them in a fixed order (deterministic).
-template <int RB, int W, int K, int KP, int CP>
-__device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2 * CP], const double *tile, const double *vrow, int ndp)
+// zrow >= 0 (fused dot only): this run contains offset 0 at position zrow, i.e. x row i + zrow of the box IS
+// row i of the block itself -- keep it in pst for the p^T w epilogue instead of reading p again from memory
+template <int RB, int W, int K, int KP, int CP, bool DOT>
+__device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2 * CP], const double *tile, const double *vrow, int ndp,
+                                           double2 (&pst)[RB][CP], int zrow)
 {
 	double2 xv[RB + W - 1][CP];
 #pragma unroll
 	for (int t = 0; t < RB + W - 1; ++t)
 #pragma unroll
 		for (int j = 0; j < CP; ++j) xv[t][j] = *reinterpret_cast<const double2 *>(tile + t * K + 2 * KP * j);
+	if (DOT && zrow >= 0) {
+#pragma unroll
+		for (int i = 0; i < RB; ++i)
+#pragma unroll
+			for (int j = 0; j < CP; ++j)
+				pst[i][j] = (W >= 3 && zrow == 2) ? xv[i + (W >= 3 ? 2 : 0)][j]
+				          : ((W >= 2 && zrow == 1) ? xv[i + (W >= 2 ? 1 : 0)][j] : xv[i][j]);
+	}
 #pragma unroll
 	for (int i = 0; i < RB; ++i) {
 		const double2 a01 = *reinterpret_cast<const double2 *>(vrow);
@@ -563,7 +574,7 @@ constexpr int DIA2_MAX_NS = 8;                         // deepest tile ring
 // consecutive threads and owns RB consecutive rows; lane gl of a group owns the column pairs
 // gl, gl + KP, ... (so every 128-bit request of a warp covers one contiguous piece of an x row).
 template <int KP, int CP, int RB, int NT, bool DOT>
-__global__ void __launch_bounds__(NT + 32)
+__global__ void __launch_bounds__(NT + 32, DOT ? 3 : 1)
 spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblocks, int nd, const int *__restrict__ off,
                    const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes, int NS,
                    const double *x, int ldx, double *y, int ldy, const int *__restrict__ gate, double *dot_part,
@@ -621,8 +632,13 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	const int lr0 = (live ? group : 0) * RB;           // first row of this group inside the block
 	double acc[RB][2 * CP];
 	double dot[2 * CP];
+	double2 pst[RB][CP];                               // DOT: the block's own x rows, kept from the run that holds offset 0
 #pragma unroll
 	for (int j = 0; j < 2 * CP; ++j) dot[j] = 0.0;
+#pragma unroll
+	for (int i = 0; i < RB; ++i)
+#pragma unroll
+		for (int j = 0; j < CP; ++j) pst[i][j] = make_double2(0.0, 0.0);
 	int slot = 0; unsigned phase = 0;
 	for (int lb = 0; lb < my_blocks; ++lb) {
 		mbar_spin(vfull + (lb & 1), (unsigned)((lb >> 1) & 1));
@@ -636,9 +652,11 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 			const int sp = grp_s[2 * g], w = grp_s[2 * g + 1];     // padded first slot, width
 			const double *tile = reinterpret_cast<const double *>(smem_raw + (size_t)slot * tile_bytes) + lr0 * K + c;
 			if (live) {
-				if (w == 2)      dia_run_ct<RB, 2, K, KP, CP>(acc, tile, vrow + sp, nd);
-				else if (w == 3) dia_run_ct<RB, 3, K, KP, CP>(acc, tile, vrow + sp, nd);
-				else             dia_run_ct<RB, 1, K, KP, CP>(acc, tile, vrow + sp, nd);
+				// position of offset 0 inside this run (-1: not in it)
+				const int zrow = (DOT && d0_s[g] <= 0 && d0_s[g] + w > 0) ? -d0_s[g] : -1;
+				if (w == 2)      dia_run_ct<RB, 2, K, KP, CP, DOT>(acc, tile, vrow + sp, nd, pst, zrow);
+				else if (w == 3) dia_run_ct<RB, 3, K, KP, CP, DOT>(acc, tile, vrow + sp, nd, pst, zrow);
+				else             dia_run_ct<RB, 1, K, KP, CP, DOT>(acc, tile, vrow + sp, nd, pst, zrow);
 			}
 			// the loads from the tile must have been performed before it is handed back (the arrive does not
 			// wait for loads in flight and ptxas may schedule it above the arithmetic that does; see
@@ -662,7 +680,7 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 						__stcs(reinterpret_cast<double2 *>(y + (size_t)(r0 + i) * ldy + c + 2 * KP * j),
 						       make_double2(acc[i][2 * j], acc[i][2 * j + 1]));
 						if (DOT) {
-							const double2 pv = __ldg(reinterpret_cast<const double2 *>(x + (size_t)(r0 + i) * ldx + c + 2 * KP * j));
+							const double2 pv = pst[i][j];
 							dot[2 * j] = fma(pv.x, acc[i][2 * j], dot[2 * j]);
 							dot[2 * j + 1] = fma(pv.y, acc[i][2 * j + 1], dot[2 * j + 1]);
 						}
@@ -741,9 +759,20 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 	const int nblocks_all = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
 	int nblocks = nblocks_all, blk_base = 0, split = 0x7fffffff, skip = 0;
 	if (mode != 0) {
-		// block b needs halo rows iff b*ROWS < halo_below or (b+1)*ROWS + halo_above > nrows
-		const int ha = M->nhalo - hb;
-		int b_lo = (hb + ROWS - 1) / ROWS, b_hi = (M->nrows - ha) / ROWS;
+		// block b can touch halo rows iff b*ROWS < reach_below or (b+1)*ROWS + reach_above > nrows, where the
+		// reach is that of the DIAGONAL IMAGE (farthest offsets), not of the halo plan: the plan's extents
+		// come from the entries the first / last slab rows really have, and a row further inside may still
+		// own the farthest diagonal (masked or irregular stencils, slabs not aligned to lattice planes)
+		int reach_below = 0, reach_above = 0;
+		for (int g = 0; g < ng; ++g) {
+			const int lo = M->dia_off_h[g], hi = M->dia_off_h[g] + M->dia_grp_h[2 * g + 1] - 1;
+			if (-lo > reach_below) reach_below = -lo;
+			if (hi > reach_above) reach_above = hi;
+		}
+		if (hb > reach_below) reach_below = hb;
+		if (M->nhalo - hb > reach_above) reach_above = M->nhalo - hb;
+		int b_lo = (reach_below + ROWS - 1) / ROWS, b_hi = (M->nrows - reach_above) / ROWS;
+		if (b_hi < 0) b_hi = 0;
 		if (b_lo > nblocks_all) b_lo = nblocks_all;
 		if (b_hi < b_lo) b_hi = b_lo;
 		if (mode == 1) { blk_base = b_lo; nblocks = b_hi - b_lo; }
@@ -978,6 +1007,13 @@ int b200k_spmm_dot(const b200_mat *M, const double *x, int ldx, double *y, int l
 {
 	*nparts = 0;
 	if (!(M->dia_nd > 0 && k > 4 && k <= 64 && M->nrows > 0) || getenv("B200_NO_FUSED_DOT")) return 2;
+	{
+		// the epilogue takes p from the run that holds offset 0 (the main diagonal): without one, no fusion
+		bool has_diag = false;
+		for (int g = 0; g < M->dia_ng; ++g)
+			has_diag = has_diag || (M->dia_off_h[g] <= 0 && M->dia_off_h[g] + M->dia_grp_h[2 * g + 1] > 0);
+		if (!has_diag) return 2;
+	}
 	const bool vec = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (k % 2 == 0);
 	if (!vec) return 2;
 	if (spmm_overlap_ok(M, 0, x, ldx, y, ldy, k)) {

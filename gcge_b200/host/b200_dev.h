@@ -80,6 +80,7 @@ struct b200_mv_ {
 };
 
 int  b200_fail(const char *fmt, ...);
+void b200_gcg_free_cache(void);               /* b200_gcg.c: the solver's cached second [X P W] buffer */
 void *b200_scratch(int slot, size_t bytes);   /* growable device scratch; NULL on failure */
 void *b200_pinned(int slot, size_t bytes);    /* growable pinned host staging */
 int  b200k_num_sms(void);

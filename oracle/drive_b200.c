@@ -28,7 +28,8 @@ int drive_gcg_b200(int tier, int n,
 		double tol_abs, double tol_rel, int max_iter_gcg,
 		int argc, char **argv, int quiet,
 		double *eval_out, double *evec_out,
-		int *numIter_out, int *nevConv_out, double *seconds_out)
+		int *numIter_out, int *nevConv_out, double *seconds_out,
+		int nevGiven, const double *evec_given)
 {
 	OPS *ops = NULL;
 	OPS_Create(&ops);
@@ -44,7 +45,7 @@ int drive_gcg_b200(int tier, int n,
 		B200_MatCreateFromCCS(&mB, &ccsB); B = (void *)&mB;
 	}
 
-	int multiMax = 1; double gapMin = 1e-5; int nevGiven = 0;
+	int multiMax = 1; double gapMin = 1e-5;
 	if (nevMax <= 0) nevMax = 2 * nevConv;
 	if (block_size <= 0) block_size = nevConv < 30 ? (nevMax - nevConv) : nevConv / 5;
 	if (nevInit <= 0) nevInit = nevMax;
@@ -55,6 +56,13 @@ int drive_gcg_b200(int tier, int n,
 	void **evec;
 	ops->MultiVecCreateByMat(&evec, nevMax, A, ops);
 	ops->MultiVecSetRandomValue(evec, 0, nevMax, ops);
+	/* warm start (reference src/ops_eig_sol_gcg.c:107-109) */
+	if (nevGiven > 0 && evec_given != NULL) {
+		if (b200_mv_upload((b200_mv *)evec, 0, nevGiven, evec_given, n)) {
+			fprintf(stderr, "drive_gcg_b200: %s\n", b200_last_error());
+			abort();
+		}
+	} else nevGiven = 0;
 	void **gcg_mv_ws[4]; double *dbl_ws; int *int_ws;
 	ops->MultiVecCreateByMat(&gcg_mv_ws[0], nevMax + 2 * block_size, A, ops);
 	ops->MultiVecSetRandomValue(gcg_mv_ws[0], 0, nevMax + 2 * block_size, ops);

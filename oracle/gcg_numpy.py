@@ -495,7 +495,7 @@ class GCG:
         s.endW = mgs(s.V, s.startW, s.endW, s.B, s.p.compW_orth, s.p.orth_self)
         s.sizeW = s.endW - s.startW
 
-    def solve(self, seed_already_set=False):
+    def solve(self, seed_already_set=False, evec_given=None):
         s, p = self, self.p
         n = s.n
         nev0 = min(p.nev, p.nev_max)
@@ -510,9 +510,16 @@ class GCG:
         s.startN, s.endN, s.endX = 0, bs, s.sizeX
         s.startP = s.endP = s.endX
         s.startW = s.endW = s.endP
-        # InitializeX, reference :101-158 (nevGiven = 0)
-        fill_random(s.V, 0, s.sizeX)
-        e = mgs(s.V, 0, s.sizeX, s.B, p.initX_orth, p.orth_self)
+        # InitializeX, reference :101-158: the given block first (warm start, :107-109,140), then
+        # random columns behind whatever survived its orthonormalisation
+        ng = 0
+        if evec_given is not None and evec_given.shape[1] > 0:
+            ng = evec_given.shape[1]
+            assert p.nev_init >= ng
+            s.V[:, :ng] = evec_given
+            ng = mgs(s.V, 0, ng, s.B, p.initX_orth, p.orth_self)
+        fill_random(s.V, ng, s.sizeX)
+        e = mgs(s.V, ng, s.sizeX, s.B, p.initX_orth, p.orth_self)
         assert e == s.sizeX
         s.ss_matA = None
         s.rayleigh_ritz(0)
@@ -571,6 +578,7 @@ def gcg_solve(A, B=None, seed=0, **kw):
     reference driver (srand(0), reference test/test_eig_sol_gcg.c:87)."""
     variant = {k: kw.pop(k) for k in ("orth_self",) if k in kw}
     verbose = kw.pop("verbose", False)
+    evec_given = kw.pop("evec_given", None)
     prm = GCGParams(**kw, **variant)
     srand(seed)
-    return GCG(A, B, prm, verbose=verbose).solve()
+    return GCG(A, B, prm, verbose=verbose).solve(evec_given=evec_given)

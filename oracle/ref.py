@@ -148,7 +148,7 @@ def block_pcg(M, b, x, start, end, max_iter=30, rate=1e-2, tol=1e-14, tol_type="
 
 
 def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=(1e-1, 1e-8), max_iter=500,
-              argv=(), quiet=True, want_evec=True):
+              argv=(), quiet=True, want_evec=True, evec_given=None):
     """Runs the reference GCG (reference src/ops_eig_sol_gcg.c:1253) through the sequence of
     reference test/test_eig_sol_gcg.c:28-169.  Returns dict(eval, evec, num_iter, nev_conv, seconds)."""
     n = A.ncols
@@ -164,6 +164,8 @@ def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=(1e-1,
                         int(nev), int(nev_max), int(block_size), int(nev_init),
                         C.c_double(tol[0]), C.c_double(tol[1]), int(max_iter),
                         len(args), argv_c, 1 if quiet else 0,
-                        _dp(ev), _dp(evec), C.byref(num_iter), C.byref(nev_conv), C.byref(secs))
+                        _dp(ev), _dp(evec), C.byref(num_iter), C.byref(nev_conv), C.byref(secs),
+                        0 if evec_given is None else int(evec_given.shape[1]),
+                        _dp(None if evec_given is None else _F(np.asfortranarray(evec_given, dtype=np.float64))))
     return {"eval": ev, "evec": evec, "num_iter": num_iter.value, "nev_conv": nev_conv.value,
             "seconds": secs.value}

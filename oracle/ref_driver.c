@@ -203,14 +203,15 @@ int ref_gcg_solve(int n,
 		double tol_abs, double tol_rel, int max_iter_gcg,
 		int argc, char **argv, int quiet,
 		double *eval_out, double *evec_out,
-		int *numIter_out, int *nevConv_out, double *seconds_out)
+		int *numIter_out, int *nevConv_out, double *seconds_out,
+		int nevGiven, const double *evec_given)
 {
 	OPS *ops = make_ops(quiet);
 	CCSMAT ccsA, ccsB; void *A, *B = NULL;
 	wrap_ccs(&ccsA, n, A_j_col, A_i_row, A_data); A = (void *)&ccsA;
 	if (B_j_col != NULL) { wrap_ccs(&ccsB, n, B_j_col, B_i_row, B_data); B = (void *)&ccsB; }
 
-	int multiMax = 1; double gapMin = 1e-5; int nevGiven = 0;
+	int multiMax = 1; double gapMin = 1e-5;
 	if (nevMax <= 0) nevMax = 2 * nevConv;
 	if (block_size <= 0) block_size = nevConv < 30 ? (nevMax - nevConv) : nevConv / 5;
 	if (nevInit <= 0) nevInit = nevMax;
@@ -221,6 +222,11 @@ int ref_gcg_solve(int n,
 	void **evec;
 	ops->MultiVecCreateByMat(&evec, nevMax, A, ops);
 	ops->MultiVecSetRandomValue(evec, 0, nevMax, ops);
+	/* warm start (reference src/ops_eig_sol_gcg.c:107-109): the caller's approximate eigenvectors
+	 * in the first nevGiven columns of evec */
+	if (nevGiven > 0 && evec_given != NULL)
+		memcpy(((LAPACKVEC *)evec)->data, evec_given, (size_t)n * nevGiven * sizeof(double));
+	else nevGiven = 0;
 	void **gcg_mv_ws[4]; double *dbl_ws; int *int_ws;
 	ops->MultiVecCreateByMat(&gcg_mv_ws[0], nevMax + 2 * block_size, A, ops);
 	ops->MultiVecSetRandomValue(gcg_mv_ws[0], 0, nevMax + 2 * block_size, ops);

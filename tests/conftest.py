@@ -45,6 +45,19 @@ def refmod():
     return ref
 
 
+def reference_runs_over_threads(refmod, solve, threads=(1, 2, 4, 8)):
+    """The reference's OpenMP reductions make its own outer-iteration count move with the thread count
+    (profiles/reference_iteration_spread_r2.log: 69..72 on one moving-window case, 101..122 on another):
+    run it at several thread counts and return the runs, so a test can hold the device solver to
+    [min - 1, max + 1] of the reference's own spread instead of to one arbitrary member of it."""
+    runs = []
+    for t in threads:
+        refmod.set_threads(t)
+        runs.append(solve())
+    refmod.set_threads(min(8, os.cpu_count() or 1))
+    return runs
+
+
 @pytest.fixture(scope="session")
 def golden():
     return json.loads((ROOT / "tests" / "golden" / "gcg_reference.json").read_text())
@@ -68,7 +81,7 @@ def drive_b200(refmod):
     drv = C.CDLL(str(drv_path))
 
     def run(tier, A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=(1e-1, 1e-8), max_iter=500,
-            argv=(), want_evec=False):
+            argv=(), want_evec=False, evec_given=None):
         n = A.ncols
         nm = nev_max if nev_max > 0 else 2 * nev
         ev = np.zeros(nm)
@@ -83,7 +96,9 @@ def drive_b200(refmod):
                            dp(None if B is None else B.data),
                            int(nev), int(nev_max), int(block_size), int(nev_init),
                            C.c_double(tol[0]), C.c_double(tol[1]), int(max_iter),
-                           len(args), argv_c, 1, dp(ev), dp(evec), C.byref(it), C.byref(nc), C.byref(secs))
+                           len(args), argv_c, 1, dp(ev), dp(evec), C.byref(it), C.byref(nc), C.byref(secs),
+                           0 if evec_given is None else int(evec_given.shape[1]),
+                           dp(None if evec_given is None else np.asfortranarray(evec_given, dtype=np.float64)))
         return {"eval": ev, "evec": evec, "num_iter": it.value, "nev_conv": nc.value, "seconds": secs.value}
 
     return run

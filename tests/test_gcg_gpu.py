@@ -7,9 +7,15 @@ device-resident GCG (b200_gcg_solve)."""
 import numpy as np
 import pytest
 
+from conftest import reference_runs_over_threads
 from gcge_b200 import problems as P
 
 pytestmark = pytest.mark.gpu
+
+# outer-iteration parity of the device GCG (tier B) with the reference: the north_star contract
+#  is +-1; scripts/parity_deltas.py prints the per-case differences
+# (profiles/parity_deltas_r2.log)
+ITER_TOL = 1
 
 
 def rel(a, b):
@@ -47,14 +53,14 @@ def cluster_angles(pen, ev, v1, v2, gap=1e-5):
     return worst
 
 
-@pytest.mark.parametrize("idx", [0, 2, 4, 3, 5, 6])
+@pytest.mark.parametrize("idx", [0, 1, 2, 4, 3, 5, 6, 7, 8])
 def test_device_gcg_vs_golden(b200, golden, idx):
     case = golden["cases"][idx]
     pen = gen(case)
     A = b200.Mat(pen.A); B = None if pen.B is None else b200.Mat(pen.B)
     o = b200.gcg_solve(A, B, nev=case["nev"])
     assert o["nev_conv"] >= case["nev"]
-    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    assert abs(o["num_iter"] - case["num_iter"]) <= ITER_TOL, (o["num_iter"], case["num_iter"])
     k = min(o["nev_conv"], case["nev_conv"])
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
     vec = o["evec_mv"].numpy(0, k)
@@ -97,7 +103,7 @@ def test_tierB_through_ops_table_and_live_reference(b200, refmod, drive_b200):
     r = refmod.gcg_solve(pen.A, pen.B, nev=nev)
     b = drive_b200(1, pen.A, pen.B, nev=nev, want_evec=True)
     assert b["nev_conv"] >= nev
-    assert abs(b["num_iter"] - r["num_iter"]) <= 2, (b["num_iter"], r["num_iter"])
+    assert abs(b["num_iter"] - r["num_iter"]) <= ITER_TOL, (b["num_iter"], r["num_iter"])
     k = min(b["nev_conv"], r["nev_conv"])
     assert rel(b["eval"][:k], r["eval"][:k]) < 1e-10
     ok, res = residual_test(pen, b["eval"][:k], b["evec"][:, :k])
@@ -132,7 +138,7 @@ def test_tierA_reference_options_over_ops_b200(b200, refmod, drive_b200, argv, g
 
 def test_device_gcg_order2_krylov_W(b200, refmod, golden):
     """Tier B ComputeW12 (b200_gcg.c: compute_w12) against the live reference with
-    -gcge_compW_cg_order 2: eigenvalues 1e-10, iteration count within 2."""
+    -gcge_compW_cg_order 2: eigenvalues 1e-10, iteration count within 1."""
     pen = P.p1_fem_kuhn(12)
     A = b200.Mat(pen.A); B = b200.Mat(pen.B)
     o = b200.gcg_solve(A, B, nev=10, compW_cg_order=2)
@@ -140,11 +146,11 @@ def test_device_gcg_order2_krylov_W(b200, refmod, golden):
     assert o["nev_conv"] >= 10
     assert rel(o["eval"][:10], base["eval"][:10]) < 1e-9
     case = _golden_case(golden, 12, 10, ("-gcge_compW_cg_order", 2))
-    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    assert abs(o["num_iter"] - case["num_iter"]) <= ITER_TOL, (o["num_iter"], case["num_iter"])
     assert rel(o["eval"][:10], np.array(case["eval"][:10])) < 1e-10
     if refmod is not None:
         r = refmod.gcg_solve(pen.A, pen.B, nev=10, want_evec=False, argv=("-gcge_compW_cg_order", 2))
-        assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
+        assert abs(o["num_iter"] - r["num_iter"]) <= ITER_TOL, (o["num_iter"], r["num_iter"])
         k = min(o["nev_conv"], r["nev_conv"])
         assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
 
@@ -175,7 +181,7 @@ def test_device_gcg_headline_block_structure(b200, refmod, golden):
     """nev = 200 (nevMax 400, block_size 40, projected problems of order up to 480) on a small lattice:
     the shapes of the headline run -- contraction lengths far beyond the kernels' tile rings, several
     column tiles, locked columns shifting the block offsets -- which the nev = 10 cases never reach.
-    Against the live reference: iteration count within 2, eigenvalues 1e-10."""
+    Against the live reference: iteration count within 1, eigenvalues 1e-10."""
     pen = P.p1_fem_kuhn(24)
     A = b200.Mat(pen.A); B = b200.Mat(pen.B)
     o = b200.gcg_solve(A, B, nev=200)
@@ -183,19 +189,20 @@ def test_device_gcg_headline_block_structure(b200, refmod, golden):
     ev = o["eval"][:200]
     assert np.all(np.diff(ev) > -1e-9 * ev[-1]) and ev[0] > 25.0
     case = _golden_case(golden, 24, 200)                 # the reference's recorded run of the same pencil
-    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    assert abs(o["num_iter"] - case["num_iter"]) <= ITER_TOL, (o["num_iter"], case["num_iter"])
     k = min(o["nev_conv"], case["nev_conv"])
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
     if refmod is not None:
         r = refmod.gcg_solve(pen.A, pen.B, nev=200, want_evec=False)
-        assert abs(o["num_iter"] - r["num_iter"]) <= 2, (o["num_iter"], r["num_iter"])
+        assert abs(o["num_iter"] - r["num_iter"]) <= ITER_TOL, (o["num_iter"], r["num_iter"])
         k = min(o["nev_conv"], r["nev_conv"])
         assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
 
 
-def test_device_gcg_moving_window_and_shift(b200):
+def test_device_gcg_moving_window_and_shift(b200, refmod):
     """nevInit < nevMax (reference src/ops_eig_sol_gcg.c:1400-1428) and the shifted inner
-    solve (compW_cg_shift, reference :482-492): same eigenvalues as the plain run."""
+    solve (compW_cg_shift, reference :482-492): same eigenvalues as the plain run, and -- with the
+    live reference on the box -- as the reference run with the same -nevMax / -nevInit."""
     pen = P.p1_fem_kuhn(12)
     A = b200.Mat(pen.A); B = b200.Mat(pen.B)
     base = b200.gcg_solve(A, B, nev=30)
@@ -205,3 +212,80 @@ def test_device_gcg_moving_window_and_shift(b200):
     sh = b200.gcg_solve(A, B, nev=10, compW_cg_shift=5.0)
     assert sh["nev_conv"] >= 10
     assert rel(sh["eval"][:10], base["eval"][:10]) < 1e-9
+    if refmod is not None:
+        r = refmod.gcg_solve(pen.A, pen.B, nev=10, want_evec=False, argv=("-gcge_compW_cg_shift", 5.0))
+        assert abs(sh["num_iter"] - r["num_iter"]) <= ITER_TOL, (sh["num_iter"], r["num_iter"])
+        assert rel(sh["eval"][:10], r["eval"][:10]) < 1e-10
+
+
+@pytest.mark.parametrize("gen_args,nev,nev_max,nev_init", [
+    (("p1_fem_kuhn", {"m": 14}), 40, 64, 24),       # block_size 8: several growth steps of the window
+    (("p1_fem_kuhn", {"m": 12}), 30, 48, 18),       # block_size 6
+])
+def test_device_gcg_moving_window_vs_live_reference(b200, refmod, gen_args, nev, nev_max, nev_init):
+    """Moving window (reference src/ops_eig_sol_gcg.c:1281-1283,1400-1428): X starts with
+    nevInit < nevMax columns and grows by P and W every time the window has converged.  Same
+    -nevMax / -nevInit to the live reference: eigenvalues 1e-10, residual test, and the iteration count
+    within 1 of the reference's own spread over OpenMP thread counts (its reductions reorder; these long
+    runs move by up to 3 iterations between 1, 2, 4 and 8 threads)."""
+    if refmod is None:
+        pytest.skip("oracle/_ref not present on this box")
+    pen = getattr(P, gen_args[0])(**gen_args[1])
+    runs = reference_runs_over_threads(
+        refmod, lambda: refmod.gcg_solve(pen.A, pen.B, nev=nev, nev_max=nev_max, nev_init=nev_init, want_evec=False))
+    its = [r["num_iter"] for r in runs]
+    r = runs[0]
+    A = b200.Mat(pen.A); B = None if pen.B is None else b200.Mat(pen.B)
+    o = b200.gcg_solve(A, B, nev=nev, nev_max=nev_max, nev_init=nev_init)
+    assert o["nev_conv"] >= nev and r["nev_conv"] >= nev
+    assert min(its) - ITER_TOL <= o["num_iter"] <= max(its) + ITER_TOL, (o["num_iter"], its)
+    k = min(o["nev_conv"], r["nev_conv"])
+    assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+    ok, res = residual_test(pen, o["eval"][:k], o["evec_mv"].numpy(0, k))
+    assert ok, res
+
+
+def _warm_start_block(pen, nev, noise, seed=3):
+    """approximate eigenvectors: the reference's converged ones plus relative noise"""
+    import scipy.sparse.linalg as sla
+    A = pen.A.to_scipy().tocsc(); Bm = None if pen.B is None else pen.B.to_scipy().tocsc()
+    w, v = sla.eigsh(A, k=nev, M=Bm, sigma=0.0, which="LM")
+    order = np.argsort(w)
+    v = v[:, order]
+    rng = np.random.default_rng(seed)
+    v = v + noise * np.abs(v).max() * rng.standard_normal(v.shape)
+    return np.asfortranarray(v)
+
+
+@pytest.mark.parametrize("nev_given,noise", [(10, 1e-3), (6, 1e-6), (14, 1e-2)])
+def test_device_gcg_warm_start_vs_live_reference(b200, refmod, drive_b200, nev_given, noise):
+    """Warm start (reference src/ops_eig_sol_gcg.c:107-109,140): the first nevGiven
+    columns of evec hold approximate eigenvectors; InitializeX copies them into V, B-orthonormalises
+    them and fills the rest of X with random columns.  Same given block to the live reference, to the
+    device GCG (tier B) and to the reference's GCG over OPS_B200_Set (tier A): iteration counts
+    within 1, eigenvalues 1e-10, and fewer iterations than the cold start."""
+    if refmod is None:
+        pytest.skip("oracle/_ref not present on this box")
+    pen = P.p1_fem_kuhn(12)
+    nev = 10
+    given = _warm_start_block(pen, nev_given, noise)
+    cold = refmod.gcg_solve(pen.A, pen.B, nev=nev, want_evec=False)
+    r = refmod.gcg_solve(pen.A, pen.B, nev=nev, want_evec=False, evec_given=given)
+    assert r["nev_conv"] >= nev and r["num_iter"] <= cold["num_iter"]
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    prm = b200.default_params(nev)
+    evec = b200.MultiVec(pen.A.ncols, prm.nevMax)
+    evec.upload(given, 0)
+    o = b200.gcg_solve(A, B, nev=nev, evec=evec, nev_given=nev_given)
+    assert o["nev_conv"] >= nev
+    assert abs(o["num_iter"] - r["num_iter"]) <= ITER_TOL, (o["num_iter"], r["num_iter"])
+    k = min(o["nev_conv"], r["nev_conv"])
+    assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+    ok, res = residual_test(pen, o["eval"][:k], evec.numpy(0, k))
+    assert ok, res
+    if drive_b200 is not None:
+        for tier in (0, 1):
+            a = drive_b200(tier, pen.A, pen.B, nev=nev, evec_given=given)
+            assert a["nev_conv"] >= nev
+            assert abs(a["num_iter"] - r["num_iter"]) <= ITER_TOL, (tier, a["num_iter"], r["num_iter"])
+            assert rel(a["eval"][:k], r["eval"][:k]) < 1e-10

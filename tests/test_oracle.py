@@ -139,23 +139,22 @@ def test_port_device_variant_headline_block_structure(golden):
     pen = _gen(case)
     o = G.gcg_solve(pen.A.to_scipy().tocsr(), pen.B.to_scipy().tocsr(), nev=200, orth_self="bcgs2")
     assert o["nev_conv"] >= 200
-    assert abs(o["num_iter"] - case["num_iter"]) <= 2, (o["num_iter"], case["num_iter"])
+    assert abs(o["num_iter"] - case["num_iter"]) <= 1, (o["num_iter"], case["num_iter"])
     k = min(o["nev_conv"], case["nev_conv"])
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
 
 
-@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_port_device_variant_vs_golden(golden, idx):
     """The variant the device code implements (BCGS2 + Gram/Cholesky panel) against the
-    reference's recorded results: eigenvalues 1e-10, iteration count within 2 (the reference
-    itself moves by that much with the eigenvector basis LAPACK picks inside degenerate
-    clusters -- DESIGN.md)."""
+    reference's recorded results, incl. the nev = 30 / 50 block structures (cases 1, 7, 8): eigenvalues
+    1e-10, iteration count within 1 -- the north_star contract."""
     case = golden["cases"][idx]
     pen = _gen(case)
     o = G.gcg_solve(pen.A.to_scipy().tocsr(), None if pen.B is None else pen.B.to_scipy().tocsr(),
                     nev=case["nev"], orth_self="bcgs2")
     assert o["nev_conv"] >= case["nev"]
-    assert abs(o["num_iter"] - case["num_iter"]) <= 2
+    assert abs(o["num_iter"] - case["num_iter"]) <= 1, (o["num_iter"], case["num_iter"])
     k = min(o["nev_conv"], case["nev_conv"])
     assert rel(o["eval"][:k], np.array(case["eval"][:k])) < 1e-10
 
@@ -177,6 +176,47 @@ def test_port_against_live_reference(refmod):
     r = refmod.gcg_solve(pen.A, pen.B, nev=8, want_evec=False)
     o = G.gcg_solve(pen.A.to_scipy().tocsr(), pen.B.to_scipy().tocsr(), nev=8, orth_self="bcgs2")
     assert abs(o["num_iter"] - r["num_iter"]) <= 1
+    k = min(o["nev_conv"], r["nev_conv"])
+    assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+@pytest.mark.parametrize("nev_given,noise", [(10, 1e-3), (6, 1e-6)])
+def test_port_warm_start_against_live_reference(refmod, nev_given, noise):
+    """Warm start (reference src/ops_eig_sol_gcg.c:107-109,140) in the port, pinned against the reference
+    itself with the same given block in the first nevGiven columns of evec."""
+    if refmod is None:
+        pytest.skip("oracle/_ref not present")
+    import scipy.sparse.linalg as sla
+    pen = P.p1_fem_kuhn(10)
+    A, B = pen.A.to_scipy().tocsc(), pen.B.to_scipy().tocsc()
+    w, v = sla.eigsh(A, k=nev_given, M=B, sigma=0.0, which="LM")
+    v = v[:, np.argsort(w)]
+    given = np.asfortranarray(v + noise * np.abs(v).max() * np.random.default_rng(3).standard_normal(v.shape))
+    r = refmod.gcg_solve(pen.A, pen.B, nev=8, want_evec=False, evec_given=given)
+    o = G.gcg_solve(A.tocsr(), B.tocsr(), nev=8, orth_self="bcgs2", evec_given=given)
+    assert o["nev_conv"] >= 8 and r["nev_conv"] >= 8
+    assert abs(o["num_iter"] - r["num_iter"]) <= 1, (o["num_iter"], r["num_iter"])
+    k = min(o["nev_conv"], r["nev_conv"])
+    assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+@pytest.mark.parametrize("nev,nev_max,nev_init", [(30, 48, 18)])
+def test_port_moving_window_against_live_reference(refmod, nev, nev_max, nev_init):
+    """nevInit < nevMax (reference src/ops_eig_sol_gcg.c:1281-1283,1400-1428) in the port against the reference
+    with the same -nevMax / -nevInit."""
+    if refmod is None:
+        pytest.skip("oracle/_ref not present")
+    pen = P.p1_fem_kuhn(12)
+    from conftest import reference_runs_over_threads
+    runs = reference_runs_over_threads(
+        refmod, lambda: refmod.gcg_solve(pen.A, pen.B, nev=nev, nev_max=nev_max, nev_init=nev_init, want_evec=False))
+    its = [q["num_iter"] for q in runs]
+    r = runs[0]
+    o = G.gcg_solve(pen.A.to_scipy().tocsr(), pen.B.to_scipy().tocsr(), nev=nev, nev_max=nev_max, nev_init=nev_init,
+                    block_size=nev // 5, orth_self="bcgs2")
+    assert o["nev_conv"] >= nev and r["nev_conv"] >= nev
+    # the reference's own count moves with its OpenMP thread count on this long run (69..72)
+    assert min(its) - 1 <= o["num_iter"] <= max(its) + 1, (o["num_iter"], its)
     k = min(o["nev_conv"], r["nev_conv"])
     assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
 

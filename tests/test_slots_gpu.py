@@ -469,6 +469,67 @@ def test_mat_axpby(b200, pencil):
     assert rel(v, pencil.A.data) < 1e-15
 
 
+def _ccs_from_scipy(M):
+    M = M.tocsc(); M.sort_indices()
+    return P.CCS(M.shape[0], M.shape[1], M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64))
+
+
+def test_mat_axpby_subset_pattern_and_validation(b200):
+    """Y = alpha X + beta Y where X's pattern is a strict SUBSET of Y's (A = stiffness, B = lumped
+    diagonal mass -- what the reference's SLEPc back end passes as SUBSET_NONZERO_PATTERN), checked through
+    SpMM (diagonal image), the CCS round trip (transpose image) and beta != 1; a pattern that is NOT a subset
+    fails before Y is touched."""
+    import scipy.sparse as sp
+    from gcge_b200 import api
+    pen = P.p1_fem_kuhn(9)
+    n = pen.A.ncols
+    lumped = np.asarray(pen.B.to_scipy().sum(axis=1)).ravel()
+    D = _ccs_from_scipy(sp.diags(lumped))
+    Y = b200.Mat(pen.A); X = b200.Mat(D)
+    Y.axpby(0.75, X, 1.0)
+    want = (pen.A.to_scipy() + 0.75 * sp.diags(lumped)).tocsc(); want.sort_indices()
+    _, _, v = Y.to_ccs()
+    assert np.array_equal(v, want.data)
+    x = np.asfortranarray(np.random.default_rng(0).standard_normal((n, 10)))
+    Xv = b200.MultiVec.from_numpy(x); Yv = b200.MultiVec(n, 10)
+    api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
+    assert rel(Yv.numpy(), want @ x) < 1e-14
+    Y.axpby(-1.5, X, 2.0)                                    # beta != 1
+    want2 = (2.0 * want - 1.5 * sp.diags(lumped)).tocsc(); want2.sort_indices()
+    _, _, v = Y.to_ccs()
+    assert rel(v, want2.data) < 1e-15
+    api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
+    assert rel(Yv.numpy(), want2 @ x) < 1e-14
+    # not a subset: same nnz as X would have passed the old shape/nnz check
+    off = sp.diags([lumped[:-7]], [7], shape=(n, n))         # a diagonal the P1 pattern does not have
+    Z = b200.Mat(_ccs_from_scipy(off))
+    before = Y.to_ccs()[2].copy()
+    with pytest.raises(api.B200Error, match="subset"):
+        Y.axpby(1.0, Z, 3.0)
+    assert np.array_equal(Y.to_ccs()[2], before)             # nothing was modified
+    api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
+    assert rel(Yv.numpy(), want2 @ x) < 1e-14
+
+
+def test_tierA_shifted_solve_with_diagonal_B(b200, refmod, drive_b200):
+    """The route ADVICE r1 names: the reference's GCG over OPS_B200_Set with sigma != 0 and B != NULL takes
+    MatAxpby(sigma, B, 1, A) (src/ops_eig_sol_gcg.c:594-602); with B = lumped (diagonal) mass its pattern
+    differs from A's.  Same run on the reference's CCS back end (whose MatAxpby slot is NULL: shifted
+    operator route): same eigenvalues, iteration count within 1."""
+    if drive_b200 is None:
+        pytest.skip("oracle/_ref (reference + driver) not present on this box")
+    import scipy.sparse as sp
+    pen = P.p1_fem_kuhn(10)
+    lumped = np.asarray(pen.B.to_scipy().sum(axis=1)).ravel()
+    D = _ccs_from_scipy(sp.diags(lumped))
+    argv = ("-gcge_compW_cg_shift", 2.0)
+    r = refmod.gcg_solve(pen.A, D, nev=8, want_evec=False, argv=argv)
+    a = drive_b200(0, pen.A, D, nev=8, argv=argv)
+    assert a["nev_conv"] >= 8 and r["nev_conv"] >= 8
+    assert abs(a["num_iter"] - r["num_iter"]) <= 1, (a["num_iter"], r["num_iter"])
+    assert rel(a["eval"][:8], r["eval"][:8]) < 1e-10
+
+
 def test_argument_errors_are_loud(b200):
     from gcge_b200 import api
     X = b200.MultiVec(10, 3); Y = b200.MultiVec(11, 3)
