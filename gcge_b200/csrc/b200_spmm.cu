@@ -573,8 +573,8 @@ constexpr int DIA2_MAX_NS = 8;                         // deepest tile ring
 // k = 2 KP CP columns; NT consumer threads (NT / 32 warps) + one producer warp; a row group is KP
 // consecutive threads and owns RB consecutive rows; lane gl of a group owns the column pairs
 // gl, gl + KP, ... (so every 128-bit request of a warp covers one contiguous piece of an x row).
-template <int KP, int CP, int RB, int NT, bool DOT>
-__global__ void __launch_bounds__(NT + 32, DOT ? 3 : 1)
+template <int KP, int CP, int RB, int NT, bool DOT, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB)
 spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nblocks, int nd, const int *__restrict__ off,
                    const double *__restrict__ val, int ng, const int *__restrict__ grp, int hb, int tile_bytes, int NS,
                    const double *x, int ldx, double *y, int ldy, const int *__restrict__ gate, double *dot_part,
@@ -717,7 +717,8 @@ static int env_int(const char *name, int dflt)
 
 // returns 0 launched, 1 error, 2 not applicable; *nparts = number of per-CTA dot partials written
 // mode 0: every row block; 1: interior blocks (no halo row needed); 2: the boundary blocks
-template <int KP, int CP, int RB, int NT, bool DOT>
+// MINB: CTAs per SM the kernel is compiled for (register cap) and its tile ring is sized for
+template <int KP, int CP, int RB, int NT, bool DOT, int MINB>
 static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
                               double *dot_part, int dot_cap, int *nparts, int mode)
 {
@@ -731,7 +732,7 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 	// ring depth: the deepest that still lets `want_ctas` CTAs share an SM (measured at k = 40: three
 	// CTAs with 3 tiles each 0.201 ms, two with 6 tiles 0.205 ms, one with 8 tiles 0.29 ms, four with
 	// 2 tiles 0.32 ms)
-	static const int want_ctas = env_int("B200_SPMM_CTAS", 3), ns_env = env_int("B200_SPMM_NS", 0);
+	static const int want_ctas = env_int("B200_SPMM_CTAS", MINB), ns_env = env_int("B200_SPMM_NS", 0);
 	const size_t budget = (size_t)(224 * 1024) / (want_ctas > 0 ? want_ctas : 1) - 2048;
 	int NS = ns_env > 0 ? ns_env : (budget > val_smem ? (int)((budget - val_smem) / tile_bytes) : 0);
 	if (NS > DIA2_MAX_NS) NS = DIA2_MAX_NS;
@@ -753,7 +754,7 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 	if (r != CUDA_SUCCESS) return 2;
 	static bool attr_set = false;
 	if (!attr_set) {
-		B200_CUDA(cudaFuncSetAttribute(spmm_dia_ws_kernel<KP, CP, RB, NT, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		B200_CUDA(cudaFuncSetAttribute(spmm_dia_ws_kernel<KP, CP, RB, NT, DOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr_set = true;
 	}
 	const int nblocks_all = (int)(((long long)M->nrows + ROWS - 1) / ROWS);
@@ -786,7 +787,7 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 		if (grid > dot_cap) return 2;
 		*nparts = grid;
 	}
-	spmm_dia_ws_kernel<KP, CP, RB, NT, DOT><<<grid, NT + 32, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off,
+	spmm_dia_ws_kernel<KP, CP, RB, NT, DOT, MINB><<<grid, NT + 32, smem, g_b200.stream>>>(tm, M->nrows, nblocks, nd, M->dia_off,
 		M->dia_val, ng, M->dia_grp, hb, tile_bytes, NS, x, ldx, y, ldy, gate, dot_part, blk_base, split, skip);
 	B200_KERNEL_CHECK();
 	return 0;
@@ -804,8 +805,12 @@ static int launch_spmm_dia_ws_kp(const b200_mat *M, const double *x, int ldx, do
                                  double *dot_part, int dot_cap, int *nparts, int mode)
 {
 	constexpr int RB = Dia2Cfg<KP, NT>::RB;
-	if (dot_part) return launch_spmm_dia_ws<KP, CP, RB, NT, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
-	return launch_spmm_dia_ws<KP, CP, RB, NT, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
+	// the fused-dot variant keeps the block's own x rows in registers (96 instead of 56): two CTAs per SM with a
+	// ring twice as deep.  Measured in the BlockPCG loop at n = 8 M, k = 40 (profiles/spmm_dot_variants_r2.log):
+	// 2.06 ms; capped at 72 registers for three CTAs (spills) 2.32 ms; p re-read with __ldg (round 1) 2.01-2.10 ms;
+	// plain kernel 1.93 ms + a separate 0.73 ms dot pass
+	if (dot_part) return launch_spmm_dia_ws<KP, CP, RB, NT, true, 2>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
+	return launch_spmm_dia_ws<KP, CP, RB, NT, false, 3>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
 }
 
 static bool dia_ws_has(int k)

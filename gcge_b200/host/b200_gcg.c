@@ -36,6 +36,7 @@ typedef struct {
 	const b200_mat *A, *B;
 	const b200_gcg_params *p;
 	b200_mv *V, *V2, *ritz, *ws[3];     /* V: the current [X | P | W]; V2: where the next X and P are built */
+	b200_mv *V_alloc;                   /* the buffer this solve allocated (V and V2 trade places) */
 	int own_ws;
 	long long n;
 	/* reference file-scope state, src/ops_eig_sol_gcg.c:44-54 */
@@ -398,7 +399,7 @@ static void gcg_release(gcg_t *g)
 	b200k_free(g->idx_d);
 	free(g->eval_h); free(g->res_h); free(g->offP); free(g->offW);
 	if (g->own_ws) {
-		b200_mv_destroy(g->V);
+		b200_mv_destroy(g->V_alloc);
 		for (int i = 0; i < 3; ++i) b200_mv_destroy(g->ws[i]);
 	}
 }
@@ -512,6 +513,7 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
 	} else {
 		g.own_ws = 1;
 		if (b200_mv_create(A->nrows_global, sizeVmax, &g.V)) return 1;
+		g.V_alloc = g.V;
 		for (int i = 0; i < 3; ++i) if (b200_mv_create(A->nrows_global, bs, &g.ws[i])) goto done;
 	}
 	g.V2 = gcg_second_buffer(g.V);

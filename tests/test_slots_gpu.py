@@ -488,8 +488,12 @@ def test_mat_axpby_subset_pattern_and_validation(b200):
     Y = b200.Mat(pen.A); X = b200.Mat(D)
     Y.axpby(0.75, X, 1.0)
     want = (pen.A.to_scipy() + 0.75 * sp.diags(lumped)).tocsc(); want.sort_indices()
-    _, _, v = Y.to_ccs()
-    assert np.array_equal(v, want.data)
+    jc, ir, v = Y.to_ccs()
+    assert np.array_equal(jc, pen.A.j_col) and np.array_equal(ir, pen.A.i_row)      # Y keeps its own pattern
+    cols = np.repeat(np.arange(n), np.diff(pen.A.j_col))
+    on_diag = pen.A.i_row == cols
+    want_v = pen.A.data.copy(); want_v[on_diag] += 0.75 * lumped
+    assert rel(v, want_v) < 1e-15
     x = np.asfortranarray(np.random.default_rng(0).standard_normal((n, 10)))
     Xv = b200.MultiVec.from_numpy(x); Yv = b200.MultiVec(n, 10)
     api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
@@ -497,7 +501,8 @@ def test_mat_axpby_subset_pattern_and_validation(b200):
     Y.axpby(-1.5, X, 2.0)                                    # beta != 1
     want2 = (2.0 * want - 1.5 * sp.diags(lumped)).tocsc(); want2.sort_indices()
     _, _, v = Y.to_ccs()
-    assert rel(v, want2.data) < 1e-15
+    want_v = 2.0 * want_v; want_v[on_diag] -= 1.5 * lumped
+    assert rel(v, want_v) < 1e-15
     api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
     assert rel(Yv.numpy(), want2 @ x) < 1e-14
     # not a subset: same nnz as X would have passed the old shape/nnz check
