@@ -60,6 +60,11 @@ int b200k_p2p_register(int rows, int *all_ranks_ok);
 int b200k_p2p_usable(const b200_mat *M, int k);
 int b200k_p2p_halo_exchange(const b200_mat *M, double *x, int ldx, int k);
 
+// lattice SpMM (b200_spmm_lat.cu): recognition at matrix creation; multiply: 0 launched, 1 error, 2 not applicable
+int b200k_lat_detect(b200_mat *A);
+int b200k_spmm_lat(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate,
+                   double *dot_part, int dot_cap, int *nparts, int mode);
+
 extern b200_ctx g_b200;
 static inline bool b200_multi() { return g_b200.nranks > 1; }
 

@@ -319,6 +319,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 		// fast path: the whole construction on the device (b200_matbuild.cu); 2 = not applicable
 		const int rc = b200k_mat_build_device(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A);
 		if (rc == 0) {
+			if (b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
 			if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
 			*out = A; return 0;
 		}
@@ -360,7 +361,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	B200_CUDA(cudaStreamSynchronize(st));
 	const int rc_dia = dia_build(A, rp, ci, va, nranks);
 	free(rp); free(ci); free(va);
-	if (rc_dia) { b200_mat_destroy(A); return 1; }
+	if (rc_dia || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
 	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
 	*out = A;
 	return 0;
@@ -387,6 +388,15 @@ extern "C" int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nn
 	if (nrows) *nrows = A->nrows_global;
 	if (ncols) *ncols = A->ncols_global;
 	if (nnz) *nnz = A->nnz_global;
+	return 0;
+}
+
+extern "C" int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2)
+{
+	B200_CHECK(A, "b200_mat_storage: NULL matrix");
+	if (dia_nd) *dia_nd = A->dia_nd;
+	if (lat_s1) *lat_s1 = A->lat_s1;
+	if (lat_s2) *lat_s2 = A->lat_s2;
 	return 0;
 }
 

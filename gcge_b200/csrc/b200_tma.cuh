@@ -32,6 +32,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
 	             ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+                                            unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+	             ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy): data read once per kernel should leave L2 first
+__device__ __forceinline__ void tma_load_4d_hint(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+                                                 unsigned long long *bar, unsigned long long policy)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+	             ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -60,6 +60,10 @@ struct b200_mat_ {
 	int dia_off_h[32], dia_grp_h[64];
 	int *dia_off, *dia_grp;           /* device copies */
 	double *dia_val;                  /* device [rows padded][dia_ndp] */
+	/* Lattice structure read off the diagonal image (b200_spmm_lat.cu: b200k_lat_detect): row = i + lat_s1 (j +
+	 * (lat_s2 / lat_s1) k), every entry couples lattice neighbours (|di|, |dj|, |dk| <= 1), nothing crosses a
+	 * lattice face, slabs are whole planes.  0: not a lattice (the 1-D diagonal kernel or the CSR kernels run). */
+	int lat_s1, lat_s2;
 };
 
 /* host-side partition plan, usable without a device (tests): fills a zeroed b200_mat with

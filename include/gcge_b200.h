@@ -124,8 +124,12 @@ int b200_mat_to_ccs(const b200_mat *A, int *j_col, int *i_row, double *data);
  * whole matrix (== the CCS arrays of its transpose) bit for bit */
 int b200_mat_local_range(const b200_mat *A, int *row0, int *nrows_local, int *nnz_local, int *nhalo);
 int b200_mat_local_csr(const b200_mat *A, int *rp, int *ci, double *va);
-/* Y = alpha X + beta Y on identical sparsity patterns; slot MatAxpby, reference src/ops.h:52 */
+/* Y = alpha X + beta Y; the pattern of X must be a subset of Y's (checked before Y is touched); slot MatAxpby,
+ * reference src/ops.h:52, used for the in-place shift A + sigma B, src/ops_eig_sol_gcg.c:594-602 */
 int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200_mat *Y);
+/* which SpMM storage the matrix got (diagnosis / tests): number of diagonals of its diagonal image (0: CSR
+ * kernels only) and the lattice strides recognised in it (0, 0: none; else row = i + s1 (j + (s2/s1) k)) */
+int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2);
 
 /* ---- multi-vector life cycle: reference app/app_ccs.c:40-49 (MultiVecCreateByMat),
  *      app/app_lapack.c:230-286 (create/destroy) ------------------------------ */

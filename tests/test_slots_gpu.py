@@ -232,6 +232,74 @@ def test_spmm_bitexact_both_storage_paths(b200, name, k):
         assert not got[:, :yo].any() and not got[:, yo + k:].any()
 
 
+def _lattice_matrix(mx, my, mz, kind, seed=0, periodic=False):
+    """Variable-coefficient operator on an mx x my x mz lattice (row = i + mx (j + my k)): the pattern of a
+    7-point, 27-point or P1-Kuhn (15-point) stencil, every entry its own random value -- unlike the constant
+    stencils of gcge_b200.problems this catches a value that lands on the wrong row or diagonal."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    if kind == "7pt":
+        offs = [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    elif kind == "27pt":
+        offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    else:
+        offs = P._KUHN_OFFS
+    i, j, k = np.meshgrid(np.arange(mx), np.arange(my), np.arange(mz), indexing="ij")
+    i, j, k = (a.transpose(2, 1, 0).reshape(-1) for a in (i, j, k))          # row-major in (k, j, i)
+    row = i + mx * (j + my * k)
+    rows, cols = [], []
+    for (di, dj, dk) in offs:
+        ii, jj2, kk = i + di, j + dj, k + dk
+        if periodic:
+            ok = np.ones(len(row), bool); ii %= mx; jj2 %= my; kk %= mz
+        else:
+            ok = (ii >= 0) & (ii < mx) & (jj2 >= 0) & (jj2 < my) & (kk >= 0) & (kk < mz)
+        rows.append(row[ok]); cols.append((ii + mx * (jj2 + my * kk))[ok])
+    rows = np.concatenate(rows); cols = np.concatenate(cols)
+    m = sp.csc_matrix((rng.standard_normal(len(rows)), (rows, cols)), shape=(mx * my * mz,) * 2)
+    m.sum_duplicates(); m.sort_indices()
+    return P.CCS(m.shape[0], m.shape[1], m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.astype(np.float64))
+
+
+@pytest.mark.parametrize("kind,dims", [("7pt", (13, 7, 5)), ("27pt", (12, 9, 4)), ("p1", (21, 6, 7)), ("p1", (40, 40, 6)),
+                                       ("27pt", (8, 8, 3)), ("7pt", (50, 11, 9))])
+@pytest.mark.parametrize("k", [8, 10, 20, 40, 64])
+def test_spmm_lattice_kernel_bitexact(b200, kind, dims, k, monkeypatch):
+    """The plane-marching lattice kernel (b200_spmm_lat.cu) on non-cubic lattices with variable coefficients,
+    partial tiles in i and j, short k extents: recognised as a lattice, identical bits to the reference's CCS
+    scatter (plain-C oracle), at aligned and unaligned column offsets of a wider block."""
+    from gcge_b200 import api
+    M = _lattice_matrix(*dims, kind, seed=k)
+    A = b200.Mat(M)
+    st = A.storage()
+    assert st["lat_s1"] == dims[0] and st["lat_s2"] == dims[0] * dims[1], st
+    n = M.ncols
+    x = np.asfortranarray(np.random.default_rng(k + 1).standard_normal((n, k + 4)))
+    X = b200.MultiVec.from_numpy(x)
+    for xo, yo in ((0, 0), (2, 4), (1, 2)):
+        Y = b200.MultiVec(n, k + 6)
+        api.mat_dot_multivec(A, X, Y, (xo, yo), (xo + k, yo + k))
+        got = Y.numpy()
+        want = oracle_spmm(M, np.asfortranarray(x[:, xo:xo + k]))
+        assert np.array_equal(got[:, yo:yo + k], want), (kind, dims, k, xo, yo)
+        assert not got[:, :yo].any() and not got[:, yo + k:].any()
+
+
+def test_spmm_lattice_recognition_rejects_wrap_around(b200):
+    """A periodic operator has the same diagonals (plus the wrap diagonals) but couples across the lattice faces:
+    it must NOT be taken for a Dirichlet lattice (the tiles would read zero-filled rows outside the lattice),
+    and the result through the other kernels is still the reference's."""
+    from gcge_b200 import api
+    M = _lattice_matrix(10, 8, 6, "7pt", periodic=True)
+    A = b200.Mat(M)
+    assert A.storage()["lat_s1"] == 0
+    n = M.ncols
+    x = np.asfortranarray(np.random.default_rng(3).standard_normal((n, 16)))
+    Y = b200.MultiVec(n, 16)
+    api.mat_dot_multivec(A, b200.MultiVec.from_numpy(x), Y, (0, 0), (16, 16))
+    assert np.array_equal(Y.numpy(), oracle_spmm(M, x))
+
+
 def test_axpby_semantics(b200, refmod):
     """MultiVecAxpby (reference app/app_lapack.c:334-395; call shapes of
     reference test/test_multi_vec.c:103-116)."""
