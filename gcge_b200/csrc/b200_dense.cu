@@ -197,52 +197,62 @@ gram_partial_kernel(long long n, int p, int q, const double *x, int ldx, const d
 	}
 }
 
-// ------------------------------------------------------------------ gram, bulk-copy fed
-// Same tiles and fragment loads as gram_partial_body, but the ring is fed by a producer warp with one
-// 1-D bulk copy per tile row (both operands are read in the 4-rows-by-8-columns fragment pattern, which
-// needs rows padded to 68 doubles: no tensor-map swizzle produces that, so the copies go row by row),
-// and the consumers release a stage through an mbarrier -- no cp.async address arithmetic and no
-// __syncthreads in the main loop.  Needs 16-byte aligned operands and even p, q.
-// OPT-IN (B200_TMA_GRAM=1) until it has been through the race checks the LinearComb kernel needed.
+// ------------------------------------------------------------------ gram, TMA-fed
+// Same CTA tile (64 X columns x up to 64 Y columns over a chunk of rows), warp roles (4 column slices x 2 row
+// halves) and DMMA fragments as gram_partial_body, but the ring is fed by a producer thread with tensor-map
+// copies, like lincomb_tma_body: per stage of G2_BK rows, the X tile arrives as 4 boxes and the Y tile as
+// ceil(qt / 16) boxes of 16 columns (128 bytes per row) with the 128-byte swizzle -- 7 copies per stage at
+// q = 40 where the cp.async version spends 85 % of its instructions on copy addresses, predicates and stage
+// barriers (ncu profiles/ncu_r1f_*: tensor pipe 65 % busy), and where a first bulk-copy version needed one copy
+// per tile ROW (64 per stage) and was producer-bound.  Both operands are read in the 4-rows-by-8-columns
+// fragment pattern; in a swizzled box the 16-byte chunk index of a row is XOR-ed with row % 8, so rows with
+// row % 8 < 4 keep a slice's 8 columns in one 64-byte half of the bank round and the others in the other
+// half: a k-step therefore takes the rows {0, 4, 1, 5} (then {2, 6, 3, 7}) of an 8-row group -- two rows per
+// half, two wavefronts per fragment load, the minimum.  Any permutation of the rows of a stage is as good as
+// any other for a sum over rows, as long as the X and Y fragments use the same one.
+// Needs 16-byte aligned operands (even column offsets and leading dimensions).
+constexpr int G2_BK = 32;                              // multi-vector rows per stage (== GR_BK: chunks are multiples of it)
+constexpr int G2_BOX = G2_BK * 128;                    // bytes of one 16-column box
+constexpr int G2_MAX_NS = 4;
+
 template <int NQ8>
 __device__ __forceinline__ void
-gram_tma_body(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy, long long rows_per_chunk,
-              double *part)
+gram_tma2_body(const CUtensorMap *tmx, const CUtensorMap *tmy, long long n, int p, int q, long long rows_per_chunk,
+               int NS, double *part)
 {
-	extern __shared__ __align__(16) double gsm[];
-	__shared__ unsigned long long full[GR_STAGES], empty[GR_STAGES];
+	extern __shared__ __align__(1024) unsigned char g2sm[];
+	__shared__ unsigned long long full[G2_MAX_NS], empty[G2_MAX_NS];
+	constexpr int NQB = (NQ8 + 1) / 2;                 // Y boxes
+	constexpr int STAGE = (4 + NQB) * G2_BOX;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int p0 = blockIdx.x * GR_BP, q0 = blockIdx.z * GR_BQ;
 	const int pt = min(GR_BP, p - p0), qt = min(GR_BQ, q - q0);
 	const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
 	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	const int ntiles = (int)((r_end - r_begin + GR_BK - 1) / GR_BK);
-	// columns beyond pt / qt and the rows of a ragged last tile are never copied: no NaN patterns there
-	for (int i = tid; i < GR_STAGES * GR_STAGE_DBL; i += blockDim.x) gsm[i] = 0.0;
+	const int ntiles = (int)((r_end - r_begin + G2_BK - 1) / G2_BK);
 	if (tid == 0) {
-		for (int s = 0; s < GR_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+		for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	__syncthreads();
 
 	if (warp == 8) {
-		// ------------------------------------------------------------------ producer warp: lane = tile row
-		int slot = 0; unsigned phase = 0;
-		for (int tile = 0; tile < ntiles; ++tile) {
-			const long long r0 = r_begin + (long long)tile * GR_BK;
-			const int rows = (int)min((long long)GR_BK, r_end - r0);
-			if (lane == 0) {
+		// ------------------------------------------------------------------ producer
+		if (lane == 0) {
+			int slot = 0; unsigned phase = 0;
+			for (int tile = 0; tile < ntiles; ++tile) {
+				const int r0 = (int)(r_begin + (long long)tile * G2_BK);
+				unsigned char *st = g2sm + (size_t)slot * STAGE;
 				mbar_spin(empty + slot, phase ^ 1u);
-				mbar_expect_tx(full + slot, (unsigned)(rows * (pt + qt) * 8));
+				mbar_expect_tx(full + slot, (unsigned)STAGE);
+				// boxes beyond the last column / row of an operand arrive as zeros
+#pragma unroll
+				for (int b = 0; b < 4; ++b) tma_load_2d(st + b * G2_BOX, tmx, p0 + 16 * b, r0, full + slot);
+#pragma unroll
+				for (int b = 0; b < NQB; ++b) tma_load_2d(st + (4 + b) * G2_BOX, tmy, q0 + 16 * b, r0, full + slot);
+				if (++slot == NS) { slot = 0; phase ^= 1u; }
 			}
-			__syncwarp();
-			if (lane < rows) {
-				double *Xs = gsm + (size_t)slot * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
-				bulk_load_1d(Xs + lane * GR_S, x + (size_t)(r0 + lane) * ldx + p0, (unsigned)(pt * 8), full + slot);
-				bulk_load_1d(Ys + lane * GR_S, y + (size_t)(r0 + lane) * ldy + q0, (unsigned)(qt * 8), full + slot);
-			}
-			if (++slot == GR_STAGES) { slot = 0; phase ^= 1u; }
 		}
 		return;
 	}
@@ -255,37 +265,39 @@ gram_tma_body(long long n, int p, int q, const double *x, int ldx, const double 
 	for (int i = 0; i < 2; ++i)
 #pragma unroll
 		for (int j = 0; j < NQ8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+	// row of the stage this lane reads in k-step s: kh*16 + 8*(s >> 1) + 2*(s & 1) + {0, 4, 1, 5}[t]
+	const int rperm = (t & 1) * 4 + (t >> 1);
 	int slot = 0; unsigned phase = 0;
 	for (int tile = 0; tile < ntiles; ++tile) {
 		mbar_spin(full + slot, phase);
-		const int rows = (int)min((long long)GR_BK, r_end - (r_begin + (long long)tile * GR_BK));
-		const double *Xs = gsm + (size_t)slot * GR_STAGE_DBL, *Ys = Xs + GR_BK * GR_S;
+		const double *st = reinterpret_cast<const double *>(g2sm + (size_t)slot * STAGE);
+		const double *Xb = st + pw * (G2_BOX / 8);
 		if (p_live) {
 #pragma unroll
-			for (int ks = 0; ks < GR_BK / 2; ks += 4) {
-				const int kr = kh * (GR_BK / 2) + ks + t;
-				// rows of a ragged last tile hold an earlier tile's data: their X entries count as zero
-				const bool ok = kr < rows;
-				const double a0 = ok ? Xs[kr * GR_S + pw * 16 + g] : 0.0;
-				const double a1 = ok ? Xs[kr * GR_S + pw * 16 + 8 + g] : 0.0;
+			for (int s = 0; s < 4; ++s) {
+				const int r = kh * 16 + 8 * (s >> 1) + 2 * (s & 1) + rperm;
+				const int sw = (2 * (s & 1) + rperm) & 7;                       // r % 8
+				const int lo = r * 16 + ((((g >> 1)) ^ sw) << 1) + (g & 1);      // column g of a box
+				const int hi = r * 16 + (((4 + (g >> 1)) ^ sw) << 1) + (g & 1);  // column 8 + g
+				const double a0 = Xb[lo], a1 = Xb[hi];
 #pragma unroll
 				for (int j = 0; j < NQ8; ++j) {
-					const double b = Ys[kr * GR_S + j * 8 + g];
+					const double b = st[(4 + (j >> 1)) * (G2_BOX / 8) + ((j & 1) ? hi : lo)];
 					dmma_8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
 					dmma_8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
 				}
 			}
 		}
-		// the loads of this stage must have been performed before the slot is handed back (see lincomb_tma_body)
+		// the fragment loads of this stage must have been performed before the slot is handed back (see lincomb_tma_body)
 		asm volatile("fence.acq_rel.cta;" ::: "memory");
 		__syncwarp();
 		if (lane == 0) mbar_arrive(empty + slot);
-		if (++slot == GR_STAGES) { slot = 0; phase ^= 1u; }
+		if (++slot == NS) { slot = 0; phase ^= 1u; }
 	}
-	// combine the two row halves through shared memory (every stage has been consumed and refilled for the
-	// last time: the ring is dead); consumer-only barrier, the producer warp is gone
+	// combine the two row halves through shared memory (the ring is dead: every stage was consumed); consumer-only
+	// barrier, the producer warp is gone
 	asm volatile("bar.sync 1, 256;" ::: "memory");
-	double *red = gsm;
+	double *red = reinterpret_cast<double *>(g2sm);
 	if (kh == 1) {
 #pragma unroll
 		for (int i = 0; i < 2; ++i)
@@ -314,21 +326,64 @@ gram_tma_body(long long n, int p, int q, const double *x, int ldx, const double 
 	}
 }
 
+// lower != 0 ('S' with x == y on one rank): tiles strictly above the diagonal are skipped, the reduction mirrors
 __global__ void __launch_bounds__(288, 2)
-gram_tma_kernel(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy, long long rows_per_chunk,
-                double *part)
+gram_tma2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, long long n, int p, int q,
+                 long long rows_per_chunk, int NS, int lower, double *part)
 {
+	if (lower && blockIdx.z > blockIdx.x) return;
 	const int qt = min(GR_BQ, q - (int)blockIdx.z * GR_BQ);
 	switch ((qt + 7) >> 3) {                             // uniform over the CTA
-	case 1: gram_tma_body<1>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 2: gram_tma_body<2>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 3: gram_tma_body<3>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 4: gram_tma_body<4>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 5: gram_tma_body<5>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 6: gram_tma_body<6>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	case 7: gram_tma_body<7>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
-	default: gram_tma_body<8>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part); break;
+	case 1: gram_tma2_body<1>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 2: gram_tma2_body<2>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 3: gram_tma2_body<3>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 4: gram_tma2_body<4>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 5: gram_tma2_body<5>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 6: gram_tma2_body<6>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	case 7: gram_tma2_body<7>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
+	default: gram_tma2_body<8>(&tmx, &tmy, n, p, q, rows_per_chunk, NS, part); break;
 	}
+}
+
+// 0 launched, 1 error, 2 not applicable
+static int gram_tma2_launch(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
+                            long long rows_per_chunk, dim3 grid, int lower, double *part)
+{
+	static const bool on = getenv("B200_NO_TMA_DENSE") == nullptr;
+	if (!on || n < G2_BK || n > 0x7fffffffLL || ((uintptr_t)x % 16) || ((uintptr_t)y % 16) || (ldx & 1) || (ldy & 1)) return 2;
+	tmap_encode_fn enc = tmap_encoder();
+	if (!enc) return 2;
+	CUtensorMap tmx, tmy;
+	const cuuint32_t box[2] = {16, (cuuint32_t)G2_BK};
+	const cuuint32_t estr[2] = {1, 1};
+	{
+		const cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
+		const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 8};
+		if (enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return 2;
+	}
+	{
+		const cuuint64_t gdim[2] = {(cuuint64_t)q, (cuuint64_t)n};
+		const cuuint64_t gstr[1] = {(cuuint64_t)ldy * 8};
+		if (enc(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(y), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return 2;
+	}
+	// ring depth: four stages while two CTAs still share an SM (<= 48 Y columns per tile), else three
+	const int nqb = ((q < GR_BQ ? q : GR_BQ) + 15) / 16;
+	const int NS = nqb <= 3 ? 4 : 3;
+	size_t smem = (size_t)NS * (4 + nqb) * G2_BOX;
+	const size_t red_bytes = sizeof(double) * GR_BP * GR_S;
+	if (smem < red_bytes) smem = red_bytes;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(cudaFuncSetAttribute(gram_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8 * G2_BOX));
+		attr_set = true;
+	}
+	gram_tma2_kernel<<<grid, 288, smem, g_b200.stream>>>(tmx, tmy, n, p, q, rows_per_chunk, NS, lower, part);
+	B200_KERNEL_CHECK();
+	return 0;
 }
 
 // C[i + j*ldc] = sum_chunks part[chunk][i + j*p]; mode 'S' mirrors the lower triangle.
@@ -477,18 +532,18 @@ int b200k_gram(char mode, long long n, int p, int q, double alpha, const double 
 		// even tile widths; anything else takes the 8-byte path
 		const bool al16 = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) &&
 		                  (p % 2 == 0) && (q % 2 == 0);
-		static const bool tma_gram = getenv("B200_TMA_GRAM") != nullptr;
-		if (al16 && tma_gram) {
-			static bool attr2 = false;
-			if (!attr2) {
-				B200_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-				attr2 = true;
-			}
-			gram_tma_kernel<<<grid, 288, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+		// 'S' with one operand on one rank: only the tiles on and below the diagonal are computed
+		const int lower = (!multi && mode == 'S' && x == y && ldx == ldy && p == q) ? 1 : 0;
+		int rc_tma = 2;
+		if (al16) {
+			rc_tma = gram_tma2_launch(n, p, q, x, ldx, y, ldy, rows_per_chunk, grid, lower, part);
+			if (rc_tma == 1) return 1;
 		}
-		else if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
-		else           gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
-		B200_KERNEL_CHECK();
+		if (rc_tma == 2) {
+			if (al16) gram_partial_kernel<true><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+			else      gram_partial_kernel<false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, y, ldy, rows_per_chunk, part);
+			B200_KERNEL_CHECK();
+		}
 		gram_reduce_kernel<<<b200_ceil_div((long long)p * q, 256), 256, 0, st>>>(p, q, (int)chunks, part, alpha, dst,
 		                                                                        d_rs, d_cs, (!multi && mode == 'S') ? 1 : 0);
 		B200_KERNEL_CHECK();

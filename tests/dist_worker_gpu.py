@@ -68,6 +68,47 @@ for k in (1, 6, 10, 40, 70):
     want = oracle_spmm(pen.A, np.asfortranarray(x[:, 1:1 + k]))
     check(np.array_equal(got, want), f"SpMM k={k} differs from the oracle")
 
+# ---- lattice kernel on plane-aligned slabs: variable coefficients, halo planes from the neighbours ------------
+from test_slots_gpu import _lattice_matrix         # noqa: E402
+for kind, dims in (("p1", (12, 9, 4 * world)), ("27pt", (10, 6, 3 * world)), ("7pt", (16, 5, 5 * world))):
+    M = _lattice_matrix(*dims, kind, seed=7)
+    Am = api.Mat(M)
+    st = Am.storage()
+    check(st["lat_s1"] == dims[0] and st["lat_s2"] == dims[0] * dims[1], f"lattice not recognised on a slab: {st}")
+    nl = M.ncols
+    for k in (10, 40):
+        xl = np.asfortranarray(np.random.default_rng(k).standard_normal((nl, k + 2)))
+        Xl = api.MultiVec.from_numpy(xl); Yl = api.MultiVec(nl, k)
+        for rep in range(2):                          # second pass: stale halo rows of the first must be replaced
+            if rep:
+                xl = np.asfortranarray(np.random.default_rng(100 + k).standard_normal((nl, k + 2))); Xl.upload(xl)
+            api.mat_dot_multivec(Am, Xl, Yl, (2, 0), (2 + k, k))
+            got = gather_rows(Yl, 0, k, nl)
+            check(np.array_equal(got, oracle_spmm(M, np.asfortranarray(xl[:, 2:2 + k]))), f"lattice SpMM {kind} k={k} rep={rep}")
+
+# ---- the first slab rows lack the farthest sub-diagonal, so the halo plan's extent (from the entries
+# those rows have) is SHORTER than the reach of the diagonal image; rows further inside still need halo rows and
+# must not be multiplied before the halo has arrived ------------------------------------------------------------
+import scipy.sparse as sp                             # noqa: E402
+mm = 16
+full = P.laplace3d_7pt(mm).A.to_scipy().tolil()
+nn = mm ** 3
+for q in range(1, world):
+    r0 = (nn * q) // world
+    for r in range(r0, r0 + 100):                     # rows r0 .. r0+99 lose their (r, r - m^2) entry
+        if r - mm * mm >= 0:
+            full[r, r - mm * mm] = 0.0
+fullc = full.tocsc(); fullc.eliminate_zeros(); fullc.sort_indices()
+Mh = P.CCS(nn, nn, fullc.indptr.astype(np.int32), fullc.indices.astype(np.int32), fullc.data.astype(np.float64))
+Ah = api.Mat(Mh)
+for k in (40,):
+    Xh = api.MultiVec(nn, k); Yh = api.MultiVec(nn, k)
+    for rep in range(3):
+        xh = np.asfortranarray(np.random.default_rng(50 + rep).standard_normal((nn, k)))
+        Xh.upload(xh)
+        api.mat_dot_multivec(Ah, Xh, Yh, (0, 0), (k, k))
+        check(np.array_equal(gather_rows(Yh, 0, k, nn), oracle_spmm(Mh, xh)), f"masked-halo SpMM rep={rep}")
+
 # ---- Gram / dots: globally reduced, identical on every rank -----------------------------------
 x = np.asfortranarray(np.random.default_rng(1).standard_normal((n, 24)))
 y = np.asfortranarray(np.random.default_rng(2).standard_normal((n, 10)))
