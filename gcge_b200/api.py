@@ -48,7 +48,8 @@ class GCGParams(C.Structure):
                 ("compW_orth_zero_tol", C.c_double),
                 ("compW_cg_max_iter", C.c_int), ("compW_cg_rate", C.c_double), ("compW_cg_tol", C.c_double),
                 ("compW_cg_tol_type", C.c_int), ("compW_cg_auto_shift", C.c_int), ("compW_cg_shift", C.c_double),
-                ("compRR_tol", C.c_double), ("compW_cg_order", C.c_int), ("verbose", C.c_int)]
+                ("compRR_tol", C.c_double), ("compW_cg_order", C.c_int), ("verbose", C.c_int),
+                ("initX_orth_method", C.c_int), ("compP_orth_method", C.c_int), ("compW_orth_method", C.c_int)]
 
 
 class _GCGStats(C.Structure):
@@ -404,6 +405,21 @@ def orth(x, start_x, end_x, B=None, ws=None, block_size=-1, max_reorth=2,
         ws = MultiVec(x.nrows, min(max(end_x - start_x, 1), 128))
     e = C.c_int(end_x)
     _chk(lib().b200_mv_orth(x.h, start_x, C.byref(e), None if B is None else B.h, C.byref(prm), ws.h))
+    if own:
+        ws.close()
+    return e.value
+
+
+def orth_bgs(x, start_x, end_x, B=None, ws=None, block_size=-1, max_reorth=2,
+             orth_zero_tol=2 * np.finfo(float).eps, reorth_tol=50 * np.finfo(float).eps):
+    """slot MultiVecOrth with BinaryGramSchmidt / OrthSelfEVP (reference src/ops_orth.c:122-201,415-640); returns the new end."""
+    prm = _OrthParams(block_size, max_reorth, orth_zero_tol, reorth_tol)
+    own = ws is None
+    if own:
+        ws = MultiVec(x.nrows, max(end_x - start_x, 1))
+    e = C.c_int(end_x)
+    lib().b200_mv_orth_bgs.argtypes = lib().b200_mv_orth.argtypes
+    _chk(lib().b200_mv_orth_bgs(x.h, start_x, C.byref(e), None if B is None else B.h, C.byref(prm), ws.h))
     if own:
         ws.close()
     return e.value

@@ -223,6 +223,21 @@ void OPS_B200_Set(struct OPS_ *ops)
 	ops->MultiVecQtAP             = B200_MultiVecQtAP;
 }
 
+int B200_SetOptionsFromCommandLine(int argc, char *argv[], struct OPS_ *ops)
+{
+	int nset = 0;
+	for (int i = 0; i < b200_option_count(); ++i) {
+		char opt[80];
+		int value = 0;
+		snprintf(opt, sizeof(opt), "-b200_%s", b200_option_name(i));
+		if (ops->GetOptionFromCommandLine(opt, 'i', &value, argc, argv, ops)) {
+			B200_DO(b200_option_set(b200_option_name(i), value));
+			++nset;
+		}
+	}
+	return nset;
+}
+
 /* ==== tier B: fused device providers behind the three L3 slots ===================== */
 
 static int tol_type_code(const char *t) { return (t && 0 == strcmp(t, "rel")) ? 1 : 0; }
@@ -302,6 +317,9 @@ static void GCG_B200(void *A, void *B, double *eval, void **evec, int nevGiven, 
 	p.compW_cg_auto_shift = s->compW_cg_auto_shift; p.compW_cg_shift = s->compW_cg_shift;
 	p.compRR_tol = s->compRR_tol;
 	p.compW_cg_order = s->compW_cg_order;
+	p.initX_orth_method = (0 == strcmp("bgs", s->initX_orth_method)) ? 1 : 0;     /* reference :1757-1785 */
+	p.compP_orth_method = (0 == strcmp("bgs", s->compP_orth_method)) ? 1 : 0;
+	p.compW_orth_method = (0 == strcmp("bgs", s->compW_orth_method)) ? 1 : 0;
 	p.verbose = 1;
 	b200_mv *ws[4];
 	for (int i = 0; i < 4; ++i) ws[i] = MV(s->mv_ws[i]);

@@ -28,6 +28,11 @@ void B200_MatDestroy(B200MAT *mat);
  * host lapack_ops exactly like OPS_CCS_Set (reference app/app_ccs.c:215-217). */
 void OPS_B200_Set(struct OPS_ *ops);
 
+/* -b200_<name> <int> on the command line -> the library's run-time switches (b200_option_set), read through the
+ * table's own GetOptionFromCommandLine like every other option of the reference (src/ops_multi_vec.c:58-95,
+ * src/ops_eig_sol_gcg.c:1737); call next to EigenSolverSetParametersFromCommandLine_GCG.  Returns the number set. */
+int B200_SetOptionsFromCommandLine(int argc, char *argv[], struct OPS_ *ops);
+
 /* Tier B: install the fused device providers in the three L3 slots.  Signatures mirror
  * the reference setups (reference src/ops_lin_sol.h:41-45, src/ops_orth.h:36-41,
  * src/ops_eig_sol_gcg.h:54-60); workspace arguments the device code does not need are

@@ -94,11 +94,11 @@ extern "C" int b200_comm_init(int rank, int nranks, const char *id128)
 	nccl_uid u; memcpy(u.internal, id128, 128);
 	B200_NCCL(g_nccl.CommInitRank(&g_comm, nranks, u, rank));
 	g_b200.rank = rank; g_b200.nranks = nranks;
-	if (!getenv("B200_NO_P2P") && ar_setup()) return 1;
+	if (!b200_opt(B200_OPT_NO_P2P) && ar_setup()) return 1;
 	// side stream for the SpMM halo exchange (copy engines over NVLink, see p2p_* below), so that it
 	// overlaps the interior rows of the multiply
 	g_b200.comm_stream = nullptr;
-	if (!getenv("B200_NO_OVERLAP")) {
+	if (!b200_opt(B200_OPT_NO_OVERLAP)) {
 		B200_CUDA(cudaStreamCreateWithFlags(&g_b200.comm_stream, cudaStreamNonBlocking));
 		B200_CUDA(cudaEventCreateWithFlags(&g_b200.ev_x_ready, cudaEventDisableTiming));
 		B200_CUDA(cudaEventCreateWithFlags(&g_b200.ev_halo_done, cudaEventDisableTiming));
@@ -240,7 +240,7 @@ bool p2p_resolve_driver()
 int b200k_p2p_register(int rows, int *all_ranks_ok)
 {
 	*all_ranks_ok = 0;
-	if (g_b200.nranks <= 1 || !g_comm || !g_b200.comm_stream || getenv("B200_NO_P2P")) return 0;
+	if (g_b200.nranks <= 1 || !g_comm || !g_b200.comm_stream || b200_opt(B200_OPT_NO_P2P)) return 0;
 	cudaStream_t st = g_b200.stream;
 	// global maximum of the rows needed
 	double *dmax = (double *)b200_scratch(8, 256);
@@ -468,7 +468,7 @@ int ar_setup()
 B200ArCtx b200k_ar_ctx()
 {
 	B200ArCtx c; memset(&c, 0, sizeof(c));
-	if (!g_ar.ok || getenv("B200_NO_KERNEL_ALLREDUCE")) return c;
+	if (!g_ar.ok || b200_opt(B200_OPT_NO_KERNEL_ALLREDUCE)) return c;
 	c.nranks = g_b200.nranks; c.rank = g_b200.rank;
 	for (int q = 0; q < g_b200.nranks; ++q) {
 		c.inbox[q] = (q == g_b200.rank) ? g_ar.inbox : (double *)g_ar.peer_inbox[q];

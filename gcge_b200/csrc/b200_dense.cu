@@ -17,7 +17,6 @@
 // two-wavefront (conflict-free) 64-bit access.
 #include "b200_internal.h"
 #include "b200_tma.cuh"
-#include <vector>
 #include <cmath>
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
@@ -349,8 +348,7 @@ gram_tma2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 static int gram_tma2_launch(long long n, int p, int q, const double *x, int ldx, const double *y, int ldy,
                             long long rows_per_chunk, dim3 grid, int lower, double *part)
 {
-	static const bool on = getenv("B200_NO_TMA_DENSE") == nullptr;
-	if (!on || n < G2_BK || n > 0x7fffffffLL || ((uintptr_t)x % 16) || ((uintptr_t)y % 16) || (ldx & 1) || (ldy & 1)) return 2;
+	if (b200_opt(B200_OPT_NO_TMA_DENSE) || n < G2_BK || n > 0x7fffffffLL || ((uintptr_t)x % 16) || ((uintptr_t)y % 16) || (ldx & 1) || (ldy & 1)) return 2;
 	tmap_encode_fn enc = tmap_encoder();
 	if (!enc) return 2;
 	CUtensorMap tmx, tmy;
@@ -833,8 +831,7 @@ lincomb_tma_kernel(const __grid_constant__ CUtensorMap tmx, long long n, int p, 
 static int lincomb_tma_launch(long long n, int p, int q, const double *x, int ldx, const double *c_dev, int c_rs, int c_cs,
                               const double *beta_dev, int incb, double *y, int ldy)
 {
-	static const bool on = getenv("B200_NO_TMA_DENSE") == nullptr;
-	if (!on || n < LC_BM || c_cs != 1 || (c_rs & 1) || (q & 1) || ((uintptr_t)c_dev % 16) || ((uintptr_t)x % 16) || (ldx & 1) ||
+	if (b200_opt(B200_OPT_NO_TMA_DENSE) || n < LC_BM || c_cs != 1 || (c_rs & 1) || (q & 1) || ((uintptr_t)c_dev % 16) || ((uintptr_t)x % 16) || (ldx & 1) ||
 	    n > 0x7fffffffLL)
 		return 2;
 	tmap_encode_fn enc = tmap_encoder();
@@ -912,18 +909,9 @@ static int lincomb_rows(long long n, int p, int q, const double *x, int ldx, con
 		B200_KERNEL_CHECK();
 		return 0;
 	}
-	static const bool verify = getenv("B200_TMA_VERIFY") != nullptr;
-	double *ytmp = nullptr;
-	if (!verify) {
+	{
 		const int rc = lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, y, ldy);
 		if (rc != 2) return rc;
-	} else {
-		// diagnostic: run the TMA kernel on a copy of y, then the reference kernel on y, compare
-		B200_CUDA(cudaMalloc(&ytmp, sizeof(double) * (size_t)n * q));
-		B200_CUDA(cudaMemcpy2DAsync(ytmp, sizeof(double) * q, y, sizeof(double) * ldy, sizeof(double) * q, (size_t)n, cudaMemcpyDeviceToDevice, st));
-		const int rc = lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, ytmp, q);
-		if (rc == 1) return 1;
-		if (rc == 2) { cudaFree(ytmp); ytmp = nullptr; }
 	}
 	dim3 grid(b200_ceil_div(q, LC_BN), (unsigned)((n + LC_BM - 1) / LC_BM));
 	const size_t smem = sizeof(double) * (size_t)LC_STAGES * LC_STAGE_DBL;
@@ -944,38 +932,6 @@ static int lincomb_rows(long long n, int p, int q, const double *x, int ldx, con
 		else      lincomb_kernel<false, false><<<grid, 256, smem, st>>>(n, p, q, x, ldx, c_dev, c_rs, c_cs, nullptr, 0, y, ldy);
 	}
 	B200_KERNEL_CHECK();
-	if (ytmp) {
-		std::vector<double> a((size_t)n * q), b((size_t)n * q);
-		B200_CUDA(cudaMemcpy2DAsync(a.data(), sizeof(double) * q, y, sizeof(double) * ldy, sizeof(double) * q, (size_t)n, cudaMemcpyDeviceToHost, st));
-		B200_CUDA(cudaMemcpyAsync(b.data(), ytmp, sizeof(double) * (size_t)n * q, cudaMemcpyDeviceToHost, st));
-		B200_CUDA(cudaStreamSynchronize(st));
-		double md = 0, mx = 0; size_t at = 0;
-		for (size_t i = 0; i < a.size(); ++i) {
-			const double d = fabs(a[i] - b[i]);
-			if (d > md || d != d) { md = d; at = i; }
-			if (fabs(a[i]) > mx) mx = fabs(a[i]);
-		}
-		static int calls = 0; ++calls;
-		if (md > 1e-10 * (mx > 0 ? mx : 1) || md != md)
-			fprintf(stderr, "TMA-VERIFY call %d MISMATCH n=%lld p=%d q=%d ldx=%d c_rs=%d ldy=%d beta=%d incb=%d x%%16=%d c%%16=%d y%%16=%d maxdiff=%g maxabs=%g at row %zu col %zu ref=%g tma=%g\n",
-			        calls, n, p, q, ldx, c_rs, ldy, beta_dev != nullptr, incb, (int)((uintptr_t)x % 16), (int)((uintptr_t)c_dev % 16),
-			        (int)((uintptr_t)y % 16), md, mx, at / q, at % q, a[at], b[at]);
-		if (md > 1e-10 * (mx > 0 ? mx : 1) || md != md) {
-			// is it reproducible?  run the TMA kernel again and count the differing entries of both runs
-			std::vector<double> b2((size_t)n * q);
-			lincomb_tma_launch(n, p, q, x, ldx, c_dev, c_rs, c_cs, beta_dev, incb, ytmp, q);
-			cudaMemcpyAsync(b2.data(), ytmp, sizeof(double) * (size_t)n * q, cudaMemcpyDeviceToHost, st);
-			cudaStreamSynchronize(st);
-			size_t nb1 = 0, nb2 = 0, nsame = 0; int shown = 0;
-			for (size_t i = 0; i < a.size(); ++i) {
-				const bool bad1 = fabs(a[i] - b[i]) > 1e-10 * mx, bad2 = fabs(a[i] - b2[i]) > 1e-10 * mx;
-				nb1 += bad1; nb2 += bad2; nsame += (bad1 && bad2 && b[i] == b2[i]);
-				if (bad1 && shown < 12) { fprintf(stderr, "   bad (%zu,%zu) ref=%.10g tma=%.10g tma2=%.10g\n", i / q, i % q, a[i], b[i], b2[i]); ++shown; }
-			}
-			fprintf(stderr, "   mismatching entries: run1 %zu, run2 %zu, identical wrong values in both %zu\n", nb1, nb2, nsame);
-		}
-		cudaFree(ytmp);
-	}
 	return 0;
 }
 

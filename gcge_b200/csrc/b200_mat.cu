@@ -226,7 +226,7 @@ static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va
 {
 	const int nloc = A->nrows;
 	A->dia_nd = 0;
-	if (nloc <= 0 || A->nnz <= 0 || getenv("B200_NO_DIA")) return 0;
+	if (nloc <= 0 || A->nnz <= 0 || b200_opt(B200_OPT_NO_DIA)) return 0;
 	if (nranks > 1 && !A->halo_contiguous) return 0;
 	const long long lo = A->row0;
 	auto gcol = [&](int c) -> long long {
@@ -296,6 +296,21 @@ void b200_note_halo_capacity(long long n_global, int nhalo)
 }
 
 // collective: size the halo mailboxes of the copy-engine exchange for this matrix (b200_comm.cu)
+// collective: A is symmetric only if every rank's slab is (a rank that saw an unsymmetric slab would otherwise
+// refuse a transposed multiply while the others enter its halo exchange)
+static int symmetric_across_ranks(b200_mat *A)
+{
+	double *flag = (double *)b200_scratch(3, 64);
+	if (!flag) return 1;
+	const double mine = A->symmetric ? 1.0 : 0.0;
+	if (b200k_h2d(flag, &mine, sizeof(double))) return 1;
+	if (b200k_allreduce_sum(flag, 1)) return 1;
+	double sum = 0.0;
+	if (b200k_d2h(&sum, flag, sizeof(double))) return 1;
+	A->symmetric = (sum > g_b200.nranks - 0.5) ? 1 : 0;
+	return 0;
+}
+
 static int p2p_register_for(b200_mat *A)
 {
 	int rows = 0;
@@ -320,7 +335,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 		const int rc = b200k_mat_build_device(nrows, ncols, j_col, i_row, data, g_b200.rank, nranks, A);
 		if (rc == 0) {
 			if (b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
-			if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
+			if (nranks > 1 && (symmetric_across_ranks(A) || p2p_register_for(A))) { b200_mat_destroy(A); return 1; }
 			*out = A; return 0;
 		}
 		if (rc == 1) { free(A); return 1; }
@@ -362,7 +377,7 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	const int rc_dia = dia_build(A, rp, ci, va, nranks);
 	free(rp); free(ci); free(va);
 	if (rc_dia || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
-	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
+	if (nranks > 1 && (symmetric_across_ranks(A) || p2p_register_for(A))) { b200_mat_destroy(A); return 1; }
 	*out = A;
 	return 0;
 }

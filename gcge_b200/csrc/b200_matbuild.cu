@@ -202,7 +202,7 @@ void b200_note_halo_capacity(long long n_global, int nhalo);
 int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_row, const double *data, int rank,
                            int nranks, b200_mat *A)
 {
-	if (getenv("B200_HOST_BUILD")) return 2;
+	if (b200_opt(B200_OPT_HOST_BUILD)) return 2;
 	if (!j_col || nrows <= 0 || ncols <= 0) return 2;
 	if (nranks > 1 && nrows != ncols) return 2;
 	const int nnz = j_col[ncols];
@@ -322,7 +322,7 @@ int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_
 		mb_symmetry_kernel<<<grid_for(nloc), 256, 0, st>>>(nloc, lo, rp, ci, va, shift, d_jc, d_ir, d_da, fl);
 		B200_KERNEL_CHECK();
 	}
-	const bool try_dia = !getenv("B200_NO_DIA");
+	const bool try_dia = !b200_opt(B200_OPT_NO_DIA);
 	if (try_dia) {
 		mb_offsets_kernel<<<grid_for(nloc), 256, 0, st>>>(nloc, rp, ci, table, fl);
 		B200_KERNEL_CHECK();

@@ -5,7 +5,7 @@
 // to G = X^T B X is a right-looking Cholesky factorisation; it yields the k x k map T with
 // X_orth = X T, so the panel is read once for G and once for the update.  The drop rule is
 // the reference's: r_k < orth_zero_tol => the last live column is swapped in and the block
-// shrinks (src/ops_orth.c:64-73).  One CTA; k <= 128.
+// shrinks (src/ops_orth.c:64-73).  One CTA; k <= 112 (G and T live in shared memory).
 #include "b200_internal.h"
 
 __global__ void __launch_bounds__(256)
@@ -84,7 +84,7 @@ chol_drop_kernel(int k, double *g, double zero_tol, double *t, int *n_live_out, 
 extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev,
                                const double *scale_in, double *scale_out)
 {
-	B200_CHECK(k >= 1 && k <= 128, "orth panel: %d columns (1..128 supported)", k);
+	B200_CHECK(k >= 1 && k <= 112, "orth panel: %d columns (1..112 supported)", k);
 	B200Prof prof(B200_PROF_PANEL, 16.0 * k * k, 2.0 * k * k * k / 3.0);
 	const size_t smem = sizeof(double) * ((size_t)2 * k * (k + 1) + 2 * k);
 	static bool attr_set = false;
@@ -93,6 +93,49 @@ extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_
 		attr_set = true;
 	}
 	chol_drop_kernel<<<1, 256, smem, g_b200.stream>>>(k, g_dev, zero_tol, t_dev, n_live_dev, scale_in, scale_out);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// *out = max |v[i]|, i < count (a coefficient block of the orthogonalisation: at most a few 10^4 entries): one CTA
+__global__ void __launch_bounds__(256)
+absmax_kernel(long long count, const double *__restrict__ v, double *out)
+{
+	__shared__ double red[256];
+	double m = 0.0;
+	for (long long i = threadIdx.x; i < count; i += 256) m = fmax(m, fabs(v[i]));
+	red[threadIdx.x] = m;
+	__syncthreads();
+	for (int s = 128; s > 0; s >>= 1) {
+		if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *out = red[0];
+}
+
+extern "C" int b200k_absmax(long long count, const double *v_dev, double *out_dev)
+{
+	absmax_kernel<<<1, 256, 0, g_b200.stream>>>(count, v_dev, out_dev);
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// OrthSelfEVP coefficient block (reference src/ops_orth.c:183-192): t[i*nk + j] = z[i*n + lin_dep + j] / sqrt(w[lin_dep + j]),
+// nk = n - lin_dep; z row-major with eigenvector j in column j
+__global__ void evp_coef_kernel(int n, int lin_dep, const double *__restrict__ w, const double *__restrict__ z, double *__restrict__ t)
+{
+	const int nk = n - lin_dep;
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n * nk) return;
+	const int i = idx / nk, j = idx - i * nk;
+	t[idx] = z[(size_t)i * n + lin_dep + j] * (1.0 / sqrt(w[lin_dep + j]));
+}
+
+extern "C" int b200k_evp_coef(int n, int lin_dep, const double *w_dev, const double *z_dev, double *t_dev)
+{
+	const int nk = n - lin_dep;
+	if (nk <= 0) return 0;
+	evp_coef_kernel<<<b200_ceil_div((long long)n * nk, 256), 256, 0, g_b200.stream>>>(n, lin_dep, w_dev, z_dev, t_dev);
 	B200_KERNEL_CHECK();
 	return 0;
 }

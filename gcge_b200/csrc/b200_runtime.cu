@@ -22,6 +22,8 @@ extern "C" int b200_device_count(void)
 	return n;
 }
 
+static void options_from_environment(void);
+
 extern "C" int b200_init(int device)
 {
 	if (g_b200.initialised && (device < 0 || device == g_b200.device)) return 0;
@@ -40,6 +42,7 @@ extern "C" int b200_init(int device)
 	B200_CUDA(cudaGetDeviceProperties(&prop, device));
 	B200_CHECK(prop.major >= 10, "b200_init: device %d is sm_%d%d; this library is built for sm_100a only",
 	           device, prop.major, prop.minor);
+	options_from_environment();
 	if (g_b200.initialised) b200_finalize();
 	g_b200.device = device;
 	g_b200.num_sms = prop.multiProcessorCount;
@@ -48,6 +51,53 @@ extern "C" int b200_init(int device)
 	g_b200.initialised = 1;
 	return 0;
 }
+
+// ---- run-time switches -------------------------------------------------------------------------------------
+int g_b200_opt[B200_OPT_COUNT];
+static const char *const g_opt_names[B200_OPT_COUNT] = {
+	"no_dia", "no_lat", "spmm_old_dia", "no_fused_dot", "no_tma_dense", "host_build", "no_overlap", "no_p2p",
+	"no_kernel_allreduce", "syev_prof", "bpcg_trace", "spmm_ctas", "spmm_ns", "lat_ti", "lat_tj", "lat_ns",
+	"lat_even_pitch", "lat_no_vpad", "lat_verbose"};
+
+// B200_<NAME> in the environment: a number is taken as is, anything else (incl. an empty value) means 1
+static void options_from_environment(void)
+{
+	static bool done = false;
+	if (done) return;
+	done = true;
+	for (int i = 0; i < B200_OPT_COUNT; ++i) {
+		char env[64] = "B200_";
+		size_t n = strlen(env);
+		for (const char *c = g_opt_names[i]; *c && n + 1 < sizeof(env); ++c) env[n++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+		env[n] = 0;
+		const char *v = getenv(env);
+		if (!v) continue;
+		char *end = nullptr;
+		const long x = strtol(v, &end, 10);
+		g_b200_opt[i] = (end != v && *end == 0) ? (int)x : 1;
+	}
+}
+
+extern "C" int b200_option_count(void) { return B200_OPT_COUNT; }
+extern "C" const char *b200_option_name(int i) { return (i >= 0 && i < B200_OPT_COUNT) ? g_opt_names[i] : nullptr; }
+
+extern "C" int b200_option_set(const char *name, int value)
+{
+	options_from_environment();
+	for (int i = 0; i < B200_OPT_COUNT; ++i)
+		if (name && 0 == strcmp(name, g_opt_names[i])) { g_b200_opt[i] = value; return 0; }
+	return b200_fail("b200_option_set: unknown option '%s'", name ? name : "(null)");
+}
+
+extern "C" int b200_option_get(const char *name, int *value)
+{
+	options_from_environment();
+	for (int i = 0; i < B200_OPT_COUNT; ++i)
+		if (name && 0 == strcmp(name, g_opt_names[i])) { if (value) *value = g_b200_opt[i]; return 0; }
+	return b200_fail("b200_option_get: unknown option '%s'", name ? name : "(null)");
+}
+
+extern "C" int b200k_opt(int id) { options_from_environment(); return (id >= 0 && id < B200_OPT_COUNT) ? g_b200_opt[id] : 0; }
 
 extern "C" void b200_finalize(void)
 {

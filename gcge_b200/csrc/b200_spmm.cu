@@ -659,12 +659,6 @@ spmm_dia_ws_kernel(const __grid_constant__ CUtensorMap tmx, int nrows, int nbloc
 	}
 }
 
-static int env_int(const char *name, int dflt)
-{
-	const char *e = getenv(name);
-	return (e && *e) ? atoi(e) : dflt;
-}
-
 // returns 0 launched, 1 error, 2 not applicable; *nparts = number of per-CTA dot partials written
 // mode 0: every row block; 1: interior blocks (no halo row needed); 2: the boundary blocks
 // MINB: CTAs per SM the kernel is compiled for (register cap) and its tile ring is sized for
@@ -682,7 +676,7 @@ static int launch_spmm_dia_ws(const b200_mat *M, const double *x, int ldx, doubl
 	// ring depth: the deepest that still lets `want_ctas` CTAs share an SM (measured at k = 40: three
 	// CTAs with 3 tiles each 0.201 ms, two with 6 tiles 0.205 ms, one with 8 tiles 0.29 ms, four with
 	// 2 tiles 0.32 ms)
-	static const int want_ctas = env_int("B200_SPMM_CTAS", MINB), ns_env = env_int("B200_SPMM_NS", 0);
+	const int want_ctas = b200_opt(B200_OPT_SPMM_CTAS) > 0 ? b200_opt(B200_OPT_SPMM_CTAS) : MINB, ns_env = b200_opt(B200_OPT_SPMM_NS);
 	const size_t budget = (size_t)(224 * 1024) / (want_ctas > 0 ? want_ctas : 1) - 2048;
 	int NS = ns_env > 0 ? ns_env : (budget > val_smem ? (int)((budget - val_smem) / tile_bytes) : 0);
 	if (NS > DIA2_MAX_NS) NS = DIA2_MAX_NS;
@@ -767,7 +761,7 @@ static bool dia_ws_has(int k)
 {
 	switch (k) {
 	case 8: case 10: case 12: case 16: case 20: case 24: case 30: case 32: case 40: case 48: case 50: case 56: case 60: case 64:
-		return getenv("B200_SPMM_OLD_DIA") == nullptr;
+		return !b200_opt(B200_OPT_SPMM_OLD_DIA);
 	default: return false;
 	}
 }
@@ -779,7 +773,7 @@ static bool dia_ws_has(int k)
 static int spmm_dia_ws_dispatch(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate,
                                 double *dot_part, int dot_cap, int *nparts, int mode = 0)
 {
-	if (getenv("B200_SPMM_OLD_DIA")) return 2;
+	if (b200_opt(B200_OPT_SPMM_OLD_DIA)) return 2;
 	{
 		// lattice operators: plane tiles marching along k (b200_spmm_lat.cu); same bits, fewer shared-memory bytes
 		const int rc = b200k_spmm_lat(M, x, ldx, y, ldy, k, gate, dot_part, dot_cap, nparts, mode);
@@ -966,7 +960,7 @@ int b200k_spmm_dot(const b200_mat *M, const double *x, int ldx, double *y, int l
                    double *dot_part, int dot_cap, int *nparts)
 {
 	*nparts = 0;
-	if (!(M->dia_nd > 0 && k > 4 && k <= 64 && M->nrows > 0) || getenv("B200_NO_FUSED_DOT")) return 2;
+	if (!(M->dia_nd > 0 && k > 4 && k <= 64 && M->nrows > 0) || b200_opt(B200_OPT_NO_FUSED_DOT)) return 2;
 	{
 		// the epilogue takes p from the run that holds offset 0 (the main diagonal): without one, no fusion
 		bool has_diag = false;

@@ -240,7 +240,7 @@ static bool lat_decompose(const b200_mat *A, long long s1, long long s2, LatRun 
 int b200k_lat_detect(b200_mat *A)
 {
 	A->lat_s1 = 0; A->lat_s2 = 0;
-	if (A->dia_nd <= 0 || A->nrows <= 0 || getenv("B200_NO_LAT")) return 0;
+	if (A->dia_nd <= 0 || A->nrows <= 0 || b200_opt(B200_OPT_NO_LAT)) return 0;
 	const long long n = A->nrows_global;
 	// the central run must hold offset 0; s1 comes from the first run above it, s2 from the runs beyond
 	int zc = -1;
@@ -283,7 +283,7 @@ int b200k_lat_detect(b200_mat *A)
 // even pitch 22 every group boundary inside a quarter-warp is a two-way conflict, +24 % wavefronts on the x reads).
 static int lat_pitch(int TI, int K)
 {
-	static const int force = getenv("B200_LAT_EVEN_PITCH") ? 1 : 0;
+	const int force = b200_opt(B200_OPT_LAT_EVEN_PITCH);
 	int pitch = TI + 2;
 	if (!force && (K * 8) % 128 != 0 && pitch % 2 == 0) ++pitch;
 	return pitch;
@@ -296,14 +296,8 @@ static int lat_pitch(int TI, int K)
 // rows 4 apart 64 bytes apart; the tensor-map box is simply wider than the image and the padding arrives as zeros.
 static int lat_vpitch(int ndp)
 {
-	static const int off = getenv("B200_LAT_NO_VPAD") ? 1 : 0;
+	const int off = b200_opt(B200_OPT_LAT_NO_VPAD);
 	return (!off && ndp % 4 == 0) ? ndp + 2 : ndp;
-}
-
-static int lat_env(const char *name, int dflt)
-{
-	const char *e = getenv(name);
-	return (e && *e) ? atoi(e) : dflt;
 }
 
 // returns 0 launched, 1 error, 2 not applicable; mode 0: all planes, 1: interior planes (no halo plane needed),
@@ -322,7 +316,7 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 	if (!lat_decompose(M, s1, s2, P.run, &P.zero_run, &P.zero_pos)) return 2;
 	if (DOT && P.zero_run < 0) return 2;
 	// ---- tile: TI x TJ rows of a plane, ring depth; estimated shared-memory cycles per matrix row decide
-	static const int env_ti = lat_env("B200_LAT_TI", 0), env_tj = lat_env("B200_LAT_TJ", 0), env_ns = lat_env("B200_LAT_NS", 0);
+	const int env_ti = b200_opt(B200_OPT_LAT_TI), env_tj = b200_opt(B200_OPT_LAT_TJ), env_ns = b200_opt(B200_OPT_LAT_NS);
 	const size_t smem_cap = 227 * 1024 - 1024;
 	int sum_reads = 0, n3 = 0;
 	for (int g = 0; g < P.ng; ++g) { sum_reads += LAT_RB + P.run[g].w - 1; n3 += P.run[g].w == 3; }
@@ -367,8 +361,7 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 		P.run[g].rowoff = dj1 * P.pitch + di1;
 	}
 	const size_t smem = (size_t)P.NS * P.slice_stride + (size_t)P.NV * P.val_stride;
-	static const bool verbose = getenv("B200_LAT_VERBOSE") != nullptr;
-	if (verbose)
+	if (b200_opt(B200_OPT_LAT_VERBOSE))
 		fprintf(stderr, "spmm_lat k=%d dot=%d lattice %d x %d x %d: tile TI=%d TJ=%d pitch=%d ring %d + %d, %zu bytes smem, est %.1f wavefronts/row\n",
 		        K, (int)DOT, s1, my, np, P.TI, P.TJ, P.pitch, P.NS, P.NV, smem, best);
 	// ---- tensor maps: x as (K, s1, my, planes) with a halo plane in front / behind where a slab neighbour exists

@@ -193,7 +193,7 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 	// where the time goes (block 0's view, clock64 ticks): [0] phase 1, [1] barrier, [2] phase 2, [3] barrier
 	long long cyc[6] = {0, 0, 0, 0, 0, 0}, t_prev = clock64();     // [4], [5]: tile load / rotations inside phase 1
 	auto lap = [&](int slot) { const long long t = clock64(); cyc[slot] += t - t_prev; t_prev = t; };
-	int sweep = 0;
+	int sweep = 0, converged = 0;
 	for (; sweep < max_sweeps; ++sweep) {
 		for (int R = 0; R < NB - 1; ++R) {
 			// ---- phase 1: pivot matrices
@@ -304,7 +304,7 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 		grid.sync();
 		if (blockIdx.x == 0 && tid == 0) *rot_count = 0;
 		grid.sync();
-		if (rotated == 0) { ++sweep; break; }
+		if (rotated == 0) { ++sweep; converged = 1; break; }
 	}
 	// rank the diagonal (padding excluded) and emit
 	const int gtid = blockIdx.x * blockDim.x + tid, gsz = gridDim.x * blockDim.x;
@@ -324,7 +324,8 @@ syev_block_jacobi_kernel(int n, int NB, double *Mg, double *Vg, double *jbuf, in
 		z[(size_t)i * ldz + rank_of[j]] = Vg[(size_t)i * Np + j];
 	}
 	if (gtid == 0) {
-		*sweeps_out = sweep;
+		sweeps_out[0] = sweep;
+		sweeps_out[1] = converged;                        // the last sweep applied no rotation
 		for (int i = 0; i < 6; ++i) cycles[i] = cyc[i];
 	}
 }
@@ -338,6 +339,21 @@ __global__ void syev_init_kernel(int n, int Np, const double *a, int lda, double
 		Mg[idx] = (i < n && j < n) ? a[(size_t)i * lda + j] : 0.0;
 		Vg[idx] = (i == j) ? 1.0 : 0.0;
 	}
+}
+
+// device address of {sweeps, converged} of the most recent eigen-solve (callers that do not want a synchronisation
+// inside b200k_syev_jacobi read it together with the eigenvalues: b200k_syev_check)
+static int *g_syev_status;
+
+// 0 when the most recent b200k_syev_jacobi converged (the reference checks dsyevx's INFO, src/ops_eig_sol_gcg.c:1204);
+// synchronises.  The Ritz pairs of a non-converged projected problem must not steer the outer loop silently.
+extern "C" int b200k_syev_check(void)
+{
+	if (!g_syev_status) return 0;
+	int h[2] = {0, 1};
+	if (b200k_d2h(h, g_syev_status, sizeof(h))) return 1;
+	B200_CHECK(h[1] == 1, "syev: the Jacobi iteration of the projected eigenproblem did not converge (%d sweeps)", h[0]);
+	return 0;
 }
 
 extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
@@ -355,7 +371,7 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 	double *Mg = (double *)base, *Vg = Mg + nn, *jbuf = Vg + nn;
 	long long *cycles = (long long *)(jbuf + (size_t)m * BJ_T * BJ_T);
 	int *nrot = (int *)(cycles + 8), *rank_of = nrot + m, *ctr = rank_of + Np;
-	B200_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), st));
+	B200_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(int), st));
 	syev_init_kernel<<<b200_ceil_div((long long)Np * Np, 256), 256, 0, st>>>(n, Np, a_dev, lda, Mg, Vg);
 	B200_KERNEL_CHECK();
 	int per_sm = 0;
@@ -372,10 +388,14 @@ extern "C" int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, d
 	void *args[] = {&n, &NB, &Mg, &Vg, &jbuf, &nrot, &w_dev, &z_dev, &ldz, &max_sweeps, &rot, &rank_of, &sw, &cycles};
 	B200_CUDA(cudaLaunchCooperativeKernel((void *)syev_block_jacobi_kernel, dim3(blocks), dim3(256), args, 0, st));
 	B200_LAUNCHED();
+	g_syev_status = sw;
 	if (sweeps_host) {
-		if (b200k_d2h(sweeps_host, sw, sizeof(int))) return 1;
+		int h[2];
+		if (b200k_d2h(h, sw, sizeof(h))) return 1;
+		*sweeps_host = h[0];
+		B200_CHECK(h[1] == 1, "syev: the Jacobi iteration did not converge in %d sweeps (n = %d)", max_sweeps, n);
 	}
-	if (getenv("B200_SYEV_PROF")) {
+	if (b200_opt(B200_OPT_SYEV_PROF)) {
 		long long cyc[6];
 		if (b200k_d2h(cyc, cycles, sizeof(cyc))) return 1;
 		fprintf(stderr, "syev n=%d grid=%d clock64 ticks: phase1 %lld (tile load %lld, rotations %lld) barrier %lld phase2 %lld barrier %lld\n",

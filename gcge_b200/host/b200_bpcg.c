@@ -40,8 +40,7 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	if (b200k_bpcg_begin(n, &st, b, ldb, r, ldr, prm->tol, prm->tol_type == 1)) return 1;
 	/* B200_BPCG_TRACE=1 (diagnostic, synchronises every iteration): column-iterations really needed
 	 * vs. launched -- how much a compaction of the active columns could save */
-	static int trace = -1;
-	if (trace < 0) trace = getenv("B200_BPCG_TRACE") != NULL;
+	const int trace = b200k_opt(B200K_OPT_BPCG_TRACE);
 	long long act_sum = 0, iters_run = 0;
 	for (int it = 0; it < prm->max_iter; ++it) {
 		if (trace) {
@@ -84,7 +83,7 @@ static int bpcg_chunk(const b200_mat *A, const b200_mat *B, long long n,
 	return 0;
 }
 
-int b200_block_pcg(const b200_mat *A, const b200_mat *B, const b200_mv *b, b200_mv *x,
+int b200_block_pcg(const b200_mat *A, const b200_mat *B, b200_mv *b, b200_mv *x,
                    const int *start, const int *end, const b200_bpcg_params *prm,
                    b200_mv *ws_r, b200_mv *ws_p, b200_mv *ws_w, int *niter, double *residual)
 {
@@ -109,7 +108,7 @@ int b200_block_pcg(const b200_mat *A, const b200_mat *B, const b200_mv *b, b200_
 	if (wk < 1) return b200_fail("b200_block_pcg: workspaces have no columns");
 	for (int c0 = 0; c0 < k; c0 += wk) {
 		const int kc = (k - c0 < wk) ? k - c0 : wk;
-		if (bpcg_chunk(A, B, n, (double *)b->d + start[0] + c0, b->ld, x->d + start[1] + c0, x->ld, kc, prm,
+		if (bpcg_chunk(A, B, n, b->d + start[0] + c0, b->ld, x->d + start[1] + c0, x->ld, kc, prm,
 		               ws_r->d, ws_r->ld, ws_p->d, ws_p->ld, ws_w->d, ws_w->ld, niter, residual))
 			return 1;
 	}

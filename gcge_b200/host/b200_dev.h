@@ -88,6 +88,9 @@ void b200_gcg_free_cache(void);               /* b200_gcg.c: the solver's cached
 void *b200_scratch(int slot, size_t bytes);   /* growable device scratch; NULL on failure */
 void *b200_pinned(int slot, size_t bytes);    /* growable pinned host staging */
 int  b200k_num_sms(void);
+/* cached run-time switch (b200_runtime.cu; ids of b200_internal.h) for the host-side C drivers */
+int  b200k_opt(int id);
+#define B200K_OPT_BPCG_TRACE 10
 
 /* synchronising small transfers */
 int b200k_d2h(void *host, const void *dev, size_t bytes);
@@ -139,6 +142,11 @@ int b200k_rm_to_cm(long long n, int k, const double *rm, int ld_rm, double *cm, 
 int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n_live_dev,
                     const double *scale_in, double *scale_out);
 
+/* t (n x (n - lin_dep), row-major) = z[:, lin_dep:n] diag(w[lin_dep:n])^(-1/2): the update block of OrthSelfEVP */
+int b200k_evp_coef(int n, int lin_dep, const double *w_dev, const double *z_dev, double *t_dev);
+/* *out_dev = max |v_dev[i]| over a small coefficient block (one CTA) */
+int b200k_absmax(long long count, const double *v_dev, double *out_dev);
+
 /* ---- BlockPCG (b200_bpcg.cu): device-resident scalars and masks ----------------------- */
 typedef struct b200_bpcg_state_ {
 	int k;
@@ -179,6 +187,8 @@ int b200k_bpcg_update_px(long long n, const b200_bpcg_state *st, const double *r
  * (i,j) at z[i*ldz+j]).  a is destroyed.  Parallel-order cyclic Jacobi, cooperative grid. */
 int b200k_syev_jacobi(int n, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
                       int *sweeps_host);
+/* non-zero (with a message) when the most recent eigen-solve ran out of sweeps; synchronises */
+int b200k_syev_check(void);
 
 /* ---- GCG helpers (b200_gcgk.cu) --------------------------------------------------------- */
 /* res[j] = || ax[:,j] - lam[j] * bx[:,j] ||_2 ; ax is overwritten with the residual */

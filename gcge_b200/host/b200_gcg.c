@@ -31,6 +31,7 @@
 #include "b200_dev.h"
 
 #define TRY(call) do { if ((call) != 0) return 1; } while (0)
+#define GCG_MAX_BLOCK 512      /* the reference is run at block_size = 200 (test/test_eig_sol_PHG_MAT.c:38-39) */
 
 typedef struct {
 	const b200_mat *A, *B;
@@ -59,6 +60,11 @@ typedef struct {
 	b200_gcg_stats st;
 	int timing;
 } gcg_t;
+
+static int orth_by(int method, b200_mv *x, int start_x, int *end_x, const b200_mat *B, const b200_orth_params *op, b200_mv *ws)
+{
+	return method == 1 ? b200_mv_orth_bgs(x, start_x, end_x, B, op, ws) : b200_mv_orth(x, start_x, end_x, B, op, ws);
+}
 
 static double tick(gcg_t *g) { return g->timing ? b200_wtime() : 0.0; }
 
@@ -122,6 +128,7 @@ static int rayleigh_ritz(gcg_t *g, int nevConv)
 	TRY(b200k_syev_jacobi(N, g->matA_d, ldE, g->eval_d + g->sizeC, g->evec_d, ldE, NULL));
 	if (p->compW_cg_shift != 0.0) TRY(b200k_set_diag(N, g->matA_d, ldE, NULL, -p->compW_cg_shift));
 	TRY(b200k_d2h(g->eval_h + g->sizeC, g->eval_d + g->sizeC, sizeof(double) * (size_t)N));
+	TRY(b200k_syev_check());     /* the reference asserts on dsyevx's INFO, :1204 */
 	if (p->compW_cg_shift != 0.0)
 		for (int i = 0; i < N; ++i) g->eval_h[g->sizeC + i] -= p->compW_cg_shift;
 	/* reference :1353-1355 / :1488-1490 */
@@ -209,7 +216,7 @@ static int compute_p(gcg_t *g, const int *offset)
 	const int ldE = g->ldE;
 	double t0 = tick(g);
 	const int N = g->sizeV - g->sizeC, c0 = g->sizeX - g->sizeC;
-	int idx_h[512], np = 0;
+	int idx_h[GCG_MAX_BLOCK], np = 0;
 	for (int b = 0; b < offset[0]; ++b)
 		for (int o = offset[b * 2 + 1]; o < offset[b * 2 + 2]; ++o) idx_h[np++] = o - g->sizeC;
 	TRY(b200k_h2d(g->idx_d, idx_h, sizeof(int) * (size_t)np));
@@ -228,7 +235,7 @@ static int compute_p(gcg_t *g, const int *offset)
 	op.block_size = p->compP_orth_block_size; op.max_reorth = p->compP_orth_max_reorth;
 	op.orth_zero_tol = p->compP_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
 	int endP = c0 + np;
-	TRY(b200_mv_orth(&E, c0, &endP, NULL, &op, &W));
+	TRY(orth_by(p->compP_orth_method, &E, c0, &endP, NULL, &op, &W));
 	g->sizeP = endP - c0;
 	g->startP = g->sizeX; g->endP = g->startP + g->sizeP;
 	/* P = V[:,startN:endW] * coef (:425-436; there through a workspace because V is source and
@@ -250,7 +257,7 @@ static int compute_w(gcg_t *g, const int *offset)
 		sigma = -g->eval_h[g->sizeC] + (g->eval_h[g->sizeC + 1] - g->eval_h[g->sizeC]) * 0.01;
 	sigma += p->compW_cg_shift;
 	g->startW = g->endP;
-	double scal_h[512];
+	double scal_h[GCG_MAX_BLOCK];
 	int acc = 0;
 	for (int b = 0; b < offset[0]; ++b)
 		for (int o = offset[b * 2 + 1]; o < offset[b * 2 + 2]; ++o) scal_h[acc++] = g->eval_h[o] + sigma;
@@ -278,7 +285,7 @@ static int compute_w(gcg_t *g, const int *offset)
 	b200_orth_params op;
 	op.block_size = p->compW_orth_block_size; op.max_reorth = p->compW_orth_max_reorth;
 	op.orth_zero_tol = p->compW_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
-	TRY(b200_mv_orth(g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
+	TRY(orth_by(p->compW_orth_method, g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
 	g->sizeW = g->endW - g->startW;
 	double t3 = tick(g);
 	g->st.compW += t3 - t0; g->st.linsol += t2 - t1;
@@ -305,7 +312,7 @@ static int compute_w12(gcg_t *g, const int *offset)
 	const int half = total / 2;
 	g->startW = g->endP;
 	const int b0 = offset[1];
-	double scal_h[512];
+	double scal_h[GCG_MAX_BLOCK];
 	/* x = Ritz vectors, b = (lambda + sigma) B x for the first `half` unconverged columns, :744-772 */
 	int acc = 0;
 	for (int b = 0; b < offset[0] && acc < half; ++b) {
@@ -346,7 +353,7 @@ static int compute_w12(gcg_t *g, const int *offset)
 	b200_orth_params op;
 	op.block_size = p->compW_orth_block_size; op.max_reorth = p->compW_orth_max_reorth;
 	op.orth_zero_tol = p->compW_orth_zero_tol; op.reorth_tol = 50 * DBL_EPSILON;
-	TRY(b200_mv_orth(g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
+	TRY(orth_by(p->compW_orth_method, g->V, g->startW, &g->endW, g->B, &op, g->ws[0]));
 	g->sizeW = g->endW - g->startW;
 	g->st.compW += tick(g) - t0;
 	return 0;
@@ -429,10 +436,10 @@ static int gcg_run(gcg_t *g, double *eval, int nevGiven, int *nevConv)
 		int ng = nevGiven;
 		if (ng > 0) {
 			TRY(b200k_axpby(g->n, ng, 1.0, g->ritz->d, g->ritz->ld, 0.0, g->V->d, g->V->ld));
-			TRY(b200_mv_orth(g->V, 0, &ng, g->B, &op, g->ritz));
+			TRY(orth_by(p->initX_orth_method, g->V, 0, &ng, g->B, &op, g->ritz));
 		}
 		TRY(b200_mv_set_random(g->V, ng, g->sizeX));
-		TRY(b200_mv_orth(g->V, ng, &g->endX, g->B, &op, g->ritz));
+		TRY(orth_by(p->initX_orth_method, g->V, ng, &g->endX, g->B, &op, g->ritz));
 		if (g->endX != g->sizeX) return b200_fail("gcg: initial block is rank deficient (%d of %d), reference assert :143", g->endX, g->sizeX);
 	}
 	g->st.initX += tick(g) - t0;
@@ -499,7 +506,7 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
 	if (A->nrows != A->ncols || evec->nrows != A->nrows) return b200_fail("b200_gcg_solve: shape mismatch");
 	if (B && (B->nrows != A->nrows || B->ncols != A->ncols)) return b200_fail("b200_gcg_solve: B shape mismatch");
 	const int bs = prm->block_size, nevMax = prm->nevMax;
-	if (bs < 1 || bs > 128) return b200_fail("b200_gcg_solve: block_size %d (1..128 supported)", bs);
+	if (bs < 1 || bs > GCG_MAX_BLOCK) return b200_fail("b200_gcg_solve: block_size %d (1..%d supported)", bs, GCG_MAX_BLOCK);
 	if (evec->ncols < nevMax) return b200_fail("b200_gcg_solve: evec has %d columns, nevMax = %d", evec->ncols, nevMax);
 	gcg_t g; memset(&g, 0, sizeof(g));
 	g.A = A; g.B = B; g.p = prm; g.n = A->nrows; g.ritz = evec; g.timing = 1;

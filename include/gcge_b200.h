@@ -68,6 +68,15 @@ int  b200_prof_get(int cls, const char **name, double *ms, long long *calls, dou
  * (unclassified kernels, copies, collectives, idle time): where the step's time outside the classes goes */
 int  b200_prof_get_gap(int cls, double *ms);
 
+/* Run-time switches (diagnosis and A/B measurements; DESIGN.md lists them).  Each one is read ONCE from the
+ * environment variable B200_<NAME> when the library initialises; afterwards b200_option_set changes it.  The OPS
+ * adaptor maps the command-line options -b200_<name> <int> onto them through the reference's
+ * GetOptionFromCommandLine (reference src/ops_multi_vec.c:58-95): B200_SetOptionsFromCommandLine, app_b200.h. */
+int  b200_option_count(void);
+const char *b200_option_name(int i);
+int  b200_option_set(const char *name, int value);
+int  b200_option_get(const char *name, int *value);
+
 /* ---- on-disk matrices ---------------------------------------------------------
  * MatrixMarket "matrix coordinate real|integer|pattern general|symmetric|skew-symmetric" into CCS
  * arrays (malloc'ed; release with b200_ccs_free): rows ascending inside every column, symmetric
@@ -198,6 +207,13 @@ typedef struct b200_orth_params_ {
 int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
                  const b200_orth_params *prm, b200_mv *ws);
 
+/* The same through BinaryGramSchmidt with OrthSelfEVP leaves (recursive halving; a leaf is orthonormalised through the
+ * eigen-decomposition of its Gram matrix, on the device Jacobi kernel).  Replaces BinaryGramSchmidt / OrthBinary /
+ * OrthSelfEVP, reference src/ops_orth.c:518-600, :415-516, :122-201 (-gcge_*_orth_method bgs).  ws: as many columns as
+ * the widest block it has to hold (the reference's rule: end_x - start_x). */
+int b200_mv_orth_bgs(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
+                     const b200_orth_params *prm, b200_mv *ws);
+
 /* Block CG on A x = b for columns b[:,s0:e0], x[:,s1:e1], per-column convergence
  * masks, device-resident scalars.  shift != 0 solves (A + shift*B) x = b (B may be
  * NULL => identity).  Replaces BlockPCG, reference src/ops_lin_sol.c:140-437, and the
@@ -209,7 +225,10 @@ typedef struct b200_bpcg_params_ {
 	int    tol_type;       /* 0 "abs", 1 "rel" (reference src/ops_lin_sol.c:175-200) */
 	double shift;
 } b200_bpcg_params;
-int b200_block_pcg(const b200_mat *A, const b200_mat *B, const b200_mv *b, b200_mv *x,
+/* NOTE: with shift != 0 and B != NULL the right-hand side columns b[:,s0:e0] are used as workspace once the
+ * initial residual has been formed (they hold B p afterwards) -- exactly what the reference's shifted operator
+ * does with the block GCG hands it (src/ops_eig_sol_gcg.c:63-96); callers that need b afterwards keep a copy. */
+int b200_block_pcg(const b200_mat *A, const b200_mat *B, b200_mv *b, b200_mv *x,
                    const int *start, const int *end, const b200_bpcg_params *prm,
                    b200_mv *ws_r, b200_mv *ws_p, b200_mv *ws_w, int *niter, double *residual);
 
@@ -234,6 +253,9 @@ typedef struct b200_gcg_params_ {
 	double compRR_tol;
 	int    compW_cg_order;      /* 1: ComputeW; 2: ComputeW12 (W = [W1 W2], reference src/ops_eig_sol_gcg.c:697-923) */
 	int    verbose;
+	/* 0 "mgs" (b200_mv_orth), 1 "bgs" (b200_mv_orth_bgs): -gcge_{initX,compP,compW}_orth_method,
+	 * reference src/ops_eig_sol_gcg.c:1757-1785 */
+	int    initX_orth_method, compP_orth_method, compW_orth_method;
 } b200_gcg_params;
 typedef struct b200_gcg_stats_ {
 	int    numIter, nevConv;

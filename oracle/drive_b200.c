@@ -100,6 +100,7 @@ int drive_gcg_b200(int tier, int n,
 		gs->compW_cg_order = 1; gs->compW_cg_shift = 0.0; gs->compW_cg_auto_shift = 0;
 	}
 	EigenSolverSetParametersFromCommandLine_GCG(argc, argv, ops);
+	B200_SetOptionsFromCommandLine(argc, argv, ops);
 	ops->EigenSolver(A, B, eval, evec, nevGiven, &nevConv, ops);
 	double t1 = ops->GetWtime();
 

@@ -155,6 +155,82 @@ def test_device_gcg_order2_krylov_W(b200, refmod, golden):
         assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
 
 
+def test_device_gcg_binary_gram_schmidt(b200, refmod, golden):
+    """Tier B with -gcge_*_orth_method bgs: the device BinaryGramSchmidt / OrthSelfEVP in all three
+    places against the reference's recorded run with the same options and the live reference."""
+    pen = P.p1_fem_kuhn(12)
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    o = b200.gcg_solve(A, B, nev=10, initX_orth_method=1, compP_orth_method=1, compW_orth_method=1)
+    argv = ("-gcge_initX_orth_method", "bgs", "-gcge_compP_orth_method", "bgs", "-gcge_compW_orth_method", "bgs")
+    case = _golden_case(golden, 12, 10, argv)
+    assert o["nev_conv"] >= 10
+    assert abs(o["num_iter"] - case["num_iter"]) <= ITER_TOL, (o["num_iter"], case["num_iter"])
+    assert rel(o["eval"][:10], np.array(case["eval"][:10])) < 1e-10
+    ok, res = residual_test(pen, o["eval"][:10], o["evec_mv"].numpy(0, 10))
+    assert ok, res
+    if refmod is not None:
+        pen2 = P.p1_fem_kuhn(16)
+        r = refmod.gcg_solve(pen2.A, pen2.B, nev=30, want_evec=False, argv=argv)
+        o2 = b200.gcg_solve(b200.Mat(pen2.A), b200.Mat(pen2.B), nev=30, initX_orth_method=1, compP_orth_method=1, compW_orth_method=1)
+        assert abs(o2["num_iter"] - r["num_iter"]) <= ITER_TOL, (o2["num_iter"], r["num_iter"])
+        k = min(o2["nev_conv"], r["nev_conv"])
+        assert rel(o2["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+def test_device_gcg_block_size_200(b200, refmod):
+    """block_size = 200 -- the value the reference's large runs use (test/test_eig_sol_PHG_MAT.c:38-39,
+    test/submit.sh:30-34) and beyond the 128 of round 1: nev = 50, nevMax = 300, projected problems of order up to 700.
+    Against the live reference with the same -nevMax / -blockSize."""
+    pen = P.p1_fem_kuhn(13)
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    o = b200.gcg_solve(A, B, nev=50, nev_max=300, block_size=200)
+    assert o["nev_conv"] >= 50
+    ok, res = residual_test(pen, o["eval"][:50], o["evec_mv"].numpy(0, 50))
+    assert ok, res
+    if refmod is not None:
+        r = refmod.gcg_solve(pen.A, pen.B, nev=50, nev_max=300, block_size=200, want_evec=False)
+        assert abs(o["num_iter"] - r["num_iter"]) <= ITER_TOL, (o["num_iter"], r["num_iter"])
+        k = min(o["nev_conv"], r["nev_conv"])
+        assert rel(o["eval"][:k], r["eval"][:k]) < 1e-10
+
+
+def test_runtime_options_from_command_line(b200, drive_b200):
+    """-b200_<name> <int> reaches the library through the OPS table's GetOptionFromCommandLine
+    (B200_SetOptionsFromCommandLine in the adaptor), like the reference's own -gcge_* options."""
+    if drive_b200 is None:
+        pytest.skip("oracle/_ref (reference + driver) not present on this box")
+    import ctypes as C
+    L = b200.lib()
+    pen = P.p1_fem_kuhn(8)
+    v = C.c_int(-1)
+    try:
+        a = drive_b200(0, pen.A, pen.B, nev=4, argv=("-b200_no_fused_dot", 1, "-b200_lat_ns", 5))
+        assert a["nev_conv"] >= 4
+        assert L.b200_option_get(b"no_fused_dot", C.byref(v)) == 0 and v.value == 1
+        assert L.b200_option_get(b"lat_ns", C.byref(v)) == 0 and v.value == 5
+    finally:
+        L.b200_option_set(b"no_fused_dot", 0); L.b200_option_set(b"lat_ns", 0)
+
+
+def test_runtime_options_table(b200):
+    """-b200_* switches: one table, read once from the environment, changeable at run time (include/gcge_b200.h)."""
+    import ctypes as C
+    L = b200.lib()
+    L.b200_option_name.restype = C.c_char_p
+    names = [L.b200_option_name(i).decode() for i in range(L.b200_option_count())]
+    assert "no_lat" in names and "no_fused_dot" in names and len(set(names)) == len(names)
+    v = C.c_int(-1)
+    assert L.b200_option_get(b"no_lat", C.byref(v)) == 0 and v.value == 0
+    pen = P.p1_fem_kuhn(8)
+    try:
+        assert L.b200_option_set(b"no_lat", 1) == 0
+        assert b200.Mat(pen.A).storage()["lat_s1"] == 0            # the switch is honoured without a restart
+    finally:
+        assert L.b200_option_set(b"no_lat", 0) == 0
+    assert b200.Mat(pen.A).storage()["lat_s1"] == 8
+    assert L.b200_option_set(b"no_such_option", 1) != 0
+
+
 def test_device_gcg_from_matrix_market_files(b200, tmp_path):
     """On-disk input: pencil written as MatrixMarket, read by the library's reader,
     solved on device: the same bits in, so the same eigenvalues out."""

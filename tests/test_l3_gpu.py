@@ -58,6 +58,56 @@ def test_orth_against_previous_block(b200, k, start):
     assert np.abs(v @ coef - old).max() < 1e-10 * np.abs(old).max()
 
 
+@pytest.mark.parametrize("with_B", [False, True])
+def test_orth_bgs_rank_deficient_like_reference_TestOrth(b200, refmod, with_B):
+    """BinaryGramSchmidt + OrthSelfEVP on the device (reference src/ops_orth.c:122-201,415-640):
+    the TestOrth case with 20 columns of which 8 repeat earlier ones, and the same call to the live reference's
+    BinaryGramSchmidt: same number of surviving columns, X^T B X = I, and the same span."""
+    pen = P.p1_fem_kuhn(8)
+    n = pen.A.ncols
+    Bm = b200.Mat(pen.B) if with_B else None
+    Bd = pen.B.to_scipy() if with_B else None
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.random((n, 20)))
+    x[:, 12:20] = x[:, 0:8]
+    for start in (0, 3):
+        X = b200.MultiVec.from_numpy(x)
+        if start:
+            assert b200.orth_bgs(X, 0, start, B=Bm, block_size=4, orth_zero_tol=1e-8) == start
+        end = b200.orth_bgs(X, start, 20, B=Bm, block_size=4, max_reorth=3, orth_zero_tol=1e-8)
+        assert end == 12
+        v = X.numpy()
+        assert gram_err(v, Bd, end) < 1e-12
+        if refmod is not None:
+            xr = x.copy(order="F")
+            if start:
+                assert refmod.multivec_orth(xr, 0, start, B=pen.B if with_B else None, method="bgs", block_size=4, orth_zero_tol=1e-8) == start
+            er = refmod.multivec_orth(xr, start, 20, B=pen.B if with_B else None, method="bgs", block_size=4, max_reorth=3,
+                                      orth_zero_tol=1e-8)
+            assert er == end
+            m = xr[:, :end].T @ ((Bd @ v[:, :end]) if Bd is not None else v[:, :end])
+            assert np.linalg.svd(m, compute_uv=False).min() > 1 - 1e-10          # same span
+
+
+@pytest.mark.parametrize("k,start,block", [(16, 0, -1), (40, 60, 8), (80, 100, 16), (100, 20, -1), (64, 0, 80)])
+def test_orth_bgs_against_previous_block(b200, k, start, block):
+    pen = P.p1_fem_kuhn(10)
+    n = pen.A.ncols
+    Bm = b200.Mat(pen.B); Bd = pen.B.to_scipy()
+    rng = np.random.default_rng(k + start)
+    x = np.asfortranarray(rng.random((n, start + k)))
+    X = b200.MultiVec.from_numpy(x)
+    if start:
+        assert b200.orth_bgs(X, 0, start, B=Bm, block_size=16) == start
+    end = b200.orth_bgs(X, start, start + k, B=Bm, block_size=block)
+    assert end == start + k
+    v = X.numpy()
+    assert gram_err(v, Bd, end) < 1e-12
+    old = x[:, start:start + k]
+    coef = v.T @ (Bd @ old)
+    assert np.abs(v @ coef - old).max() < 1e-10 * np.abs(old).max()
+
+
 def test_orth_tiny_and_scaled_columns(b200):
     """Columns that are almost inside span(X0) (remainder 1e-12): the case the reference's
     absolute re-orthogonalisation test mishandles (tests/test_oracle.py)."""
