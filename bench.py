@@ -132,11 +132,13 @@ def iters_full(m: int, nev: int, fallback: int) -> tuple[int, str]:
         return fallback, "fallback (no recorded B200 run for this size)"
 
 
-WORKLOADS = {"p1_fem": "p1_fem_kuhn", "laplace7": "laplace3d_7pt", "q1_27pt": "q1_27pt"}
+WORKLOADS = {"p1_fem": "p1_fem_kuhn", "laplace7": "laplace3d_7pt", "q1_27pt": "q1_27pt", "cube4": "cube4_p1"}
 
 
 def make_pencil(workload: str, m: int):
     from gcge_b200 import problems as P
+    if workload == "cube4":                       # config 1: the reference's mesh, two refinements: 15^3 unknowns
+        return P.cube4_p1(2)
     return getattr(P, WORKLOADS[workload])(m)
 
 
@@ -222,14 +224,17 @@ def workload_config(a, n_gpus: int) -> dict:
     bs = nev // 5 if nev >= 30 else nev
     what = {"p1_fem": "3D P1-FEM stiffness/mass pencil A x = lambda B x (Kuhn triangulation)",
             "laplace7": "3D 7-point Laplacian, standard problem A x = lambda x (B = NULL)",
-            "q1_27pt": "3D 27-point trilinear (Q1) stiffness/mass pencil A x = lambda B x"}[a.workload]
+            "q1_27pt": "3D 27-point trilinear (Q1) stiffness/mass pencil A x = lambda B x",
+            "cube4": "P1 stiffness/mass pencil on the reference's mesh data/cube4.dat after two regular refinements "
+                     "(BASELINE config 1 restated)"}[a.workload]
     par = "single GPU" if n_gpus == 1 else (
         f"1-D row blocks over {n_gpus} GPUs (SpMM halos by copy-engine P2P mailboxes over NVLink, CG scalars "
         f"allreduced in-kernel over NVLink, Gram blocks by ncclAllReduce, replicated Rayleigh-Ritz)")
     mv_gb = 8.0 * m ** 3 * (2 * (2 * nev + 2 * bs) + 2 * nev + 3 * bs) / 1e9
     return {"workload": f"{what}, n = {m}^3 = {m ** 3}, nev = {nev} (nevMax {2 * nev}, block_size {bs}), "
                         f"{'B-orthogonal ' if a.workload != 'laplace7' else ''}GCG with BlockPCG, tol = (1e-1, 1e-8), srand(0)",
-            "generator": f"gcge_b200.problems.{WORKLOADS[a.workload]}", "m": m, "nev": nev,
+            "generator": f"gcge_b200.problems.{WORKLOADS[a.workload]}" + (" (pencil_rows: each rank its own planes)" if getattr(a, "local_gen", False) else ""),
+            "m": m, "nev": nev,
             "parallelism": par,
             "l2": f"inputs >> L2 (multi-vectors {mv_gb:.1f} GB at m={m}); no flush needed" if mv_gb > 1.0 else
                   "L2 flushed between solves (b200_flush_l2)"}
@@ -322,13 +327,32 @@ def run_b200(a) -> int:
             par_gold = [{"error": str(exc)[:300], "ok": False}]
 
     t0 = time.time()
-    pen = make_pencil(a.workload, a.m)
-    n, nnz = pen.A.ncols, pen.A.nnz
-    host_arrays = [pen.A.j_col, pen.A.i_row, pen.A.data] + ([] if pen.B is None else [pen.B.j_col, pen.B.i_row, pen.B.data])
+    n = a.m ** 3
+    if a.local_gen:
+        # every rank generates and uploads ONLY its own row block (whole lattice planes): what the reference's
+        # distributed back ends do (app/app_phg.c:292-357); needed once the whole CCS no longer fits a host / a GPU
+        if a.m % world:
+            raise SystemExit(f"--local-gen needs the lattice size {a.m} to be a multiple of the rank count {world}")
+        k0, k1 = (a.m // world) * rank, (a.m // world) * (rank + 1)
+        rowsA, rowsB = P.pencil_rows(WORKLOADS[a.workload], a.m, k0, k1)
+        pen = None
+        host_arrays = list(rowsA) + ([] if rowsB is None else list(rowsB))
+        nnz = int(rowsA[0][-1])
+
+        def make_mats():
+            Am = api.Mat.from_local_rows(n, k0 * a.m * a.m, *rowsA)
+            return Am, (None if rowsB is None else api.Mat.from_local_rows(n, k0 * a.m * a.m, *rowsB))
+    else:
+        pen = make_pencil(a.workload, a.m)
+        nnz = pen.A.nnz
+        host_arrays = [pen.A.j_col, pen.A.i_row, pen.A.data] + ([] if pen.B is None else [pen.B.j_col, pen.B.i_row, pen.B.data])
+
+        def make_mats():
+            return api.Mat(pen.A), (None if pen.B is None else api.Mat(pen.B))
     for h in host_arrays:
         api.host_register(h)
     t_gen = time.time() - t0
-    A, B = api.Mat(pen.A), (None if pen.B is None else api.Mat(pen.B))
+    A, B = make_mats()
     prm = api.default_params(a.nev)
     evec = api.MultiVec(n, prm.nevMax)
 
@@ -394,7 +418,7 @@ def run_b200(a) -> int:
     for i in range(a.e2e_steps):
         barrier()
         w0 = time.time()
-        A2, B2 = api.Mat(pen.A), (None if pen.B is None else api.Mat(pen.B))
+        A2, B2 = make_mats()
         o2 = solve(A2, B2)
         evec.numpy_local(0, nev_out, out=host_vec)
         ev_host = o2["eval"][:nev_out].copy()
@@ -408,7 +432,8 @@ def run_b200(a) -> int:
         t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = float(t.item())
-    h2d = sum(h.nbytes for h in host_arrays) * world      # every rank receives the whole CCS and cuts out its slab on the device
+    # whole-CCS input: every rank receives the whole CCS and cuts out its slab on the device; --local-gen: its rows only
+    h2d = sum(h.nbytes for h in host_arrays) * world
     d2h = 8 * n * nev_out + 8 * prm.nevMax            # all ranks together
 
     if rank != 0:
@@ -464,7 +489,7 @@ def run_b200(a) -> int:
 
     # ---- CPU baseline: the reference itself on the host cores, bounded sample, and the same-size pair -----
     cpu, same = None, None
-    if world == 1 and not a.no_cpu:
+    if world == 1 and not a.no_cpu and pen is not None:
         try:
             from oracle import ref
             if ref.available():
@@ -556,6 +581,8 @@ def main() -> int:
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-m", type=int, default=24, help="lattice size of the reference's bounded sample")
     ap.add_argument("--ref-iters", type=int, default=500, help="outer-iteration cap of the reference's bounded sample")
+    ap.add_argument("--local-gen", action="store_true", help="every rank generates and uploads only its own row block "
+                    "(b200_mat_create_from_local_rows); for sizes whose whole CCS does not fit (config 4: q1_27pt m=400)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / same_size leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity solves before the timed region")
     ap.add_argument("--same-m", type=int, default=40, help="lattice size of the measured same-size pair (reference on the "
@@ -563,6 +590,10 @@ def main() -> int:
     ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: seconds the one real solve may take")
     ap.add_argument("--ref-big-m", type=int, default=0, help="--impl reference: lattice size of the real solve (0: pick by budget)")
     a = ap.parse_args()
+    if a.workload == "cube4":
+        a.m = 15
+        a.same_m = 15
+        a.ref_m = 15
     if a.impl == "reference":
         return run_reference(a)
     return run_b200(a)

@@ -284,6 +284,21 @@ class Mat:
         _chk(lib().b200_mat_create_from_ccs(ccs.nrows, ccs.ncols, _ip(j_col), _ip(i_row), _dp(data), C.byref(self.h)))
         self.nnz = int(j_col[-1])
 
+    @classmethod
+    def from_local_rows(cls, nrows_global: int, row0: int, rp, ci, va):
+        """This rank's row block only (b200_mat_create_from_local_rows): CSR-style arrays with global, ascending
+        column indices -- for symmetric matrices the CCS arrays of the columns [row0, row0 + nrows_local)."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        self.nrows = self.ncols = int(nrows_global)
+        rp = np.ascontiguousarray(rp, dtype=np.int32); ci = np.ascontiguousarray(ci, dtype=np.int32)
+        va = np.ascontiguousarray(va, dtype=np.float64)
+        L = lib()
+        L.b200_mat_create_from_local_rows.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, C.POINTER(C.c_void_p)]
+        _chk(L.b200_mat_create_from_local_rows(int(nrows_global), int(row0), len(rp) - 1, _ip(rp), _ip(ci), _dp(va), C.byref(self.h)))
+        self.nnz = int(rp[-1] - rp[0])
+        return self
+
     def to_ccs(self):
         j_col = np.empty(self.ncols + 1, np.int32)
         i_row = np.empty(max(self.nnz, 1), np.int32)

@@ -382,6 +382,135 @@ extern "C" int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, 
 	return 0;
 }
 
+// ---- slab-local construction ---------------------------------------------------------------------------------
+// Every rank hands over ONLY its row block (the reference's distributed back ends own only their rows:
+// app/app_phg.c:292-357, app/app_slepc.c): CSR-style arrays of rows [row0, row0 + nrows_local) with GLOBAL column
+// indices ascending inside a row -- for the symmetric matrices of the eigenproblem these are the CCS arrays of the
+// columns [row0, row0 + nrows_local).  The halo plan needs the column extent of every slab: one small allreduce.
+// Banded matrices only (every slab's off-slab columns lie in its two neighbouring ranges, as for
+// b200_mat_create_from_ccs's contiguous mode); the matrix is taken to be symmetric, as the reference assumes for
+// every matrix (app/app_ccs.c:140-150) -- a rank cannot check that on its rows alone.
+extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int nrows_local, const int *rp_in,
+                                               const int *ci_in, const double *va_in, b200_mat **out)
+{
+	B200_REQUIRE_INIT();
+	B200_CHECK(out && rp_in && nrows_global >= 0 && nrows_local >= 0, "b200_mat_create_from_local_rows: bad arguments");
+	const int nranks = g_b200.nranks > 1 ? g_b200.nranks : 1, rank = nranks > 1 ? g_b200.rank : 0;
+	long long lo = 0, hi = nrows_global;
+	if (nranks > 1) b200_partition_range(nrows_global, rank, nranks, &lo, &hi);
+	B200_CHECK(row0 == lo && nrows_local == hi - lo, "b200_mat_create_from_local_rows: rank %d owns rows [%lld, %lld), got [%d, %d)",
+	           rank, lo, hi, row0, row0 + nrows_local);
+	const int nloc = nrows_local, nnz = rp_in[nloc] - rp_in[0];
+	B200_CHECK(nnz >= 0 && (nnz == 0 || (ci_in && va_in)), "b200_mat_create_from_local_rows: bad arrays");
+	long long cmin = lo, cmax = hi - 1;
+	int max_row = 0;
+	for (int r = 0; r < nloc; ++r) {
+		const int e0 = rp_in[r] - rp_in[0], e1 = rp_in[r + 1] - rp_in[0];
+		B200_CHECK(e1 >= e0, "b200_mat_create_from_local_rows: row pointers not monotone at row %d", r);
+		if (e1 - e0 > max_row) max_row = e1 - e0;
+		for (int e = e0; e < e1; ++e) {
+			const int c = ci_in[e];
+			B200_CHECK(c >= 0 && c < nrows_global && (e == e0 || c > ci_in[e - 1]),
+			           "b200_mat_create_from_local_rows: columns of row %d not ascending / out of range", row0 + r);
+		}
+		if (e1 > e0) { if (ci_in[e0] < cmin) cmin = ci_in[e0]; if (ci_in[e1 - 1] > cmax) cmax = ci_in[e1 - 1]; }
+	}
+	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
+	A->nrows = nloc; A->ncols = (nranks == 1) ? nrows_global : nloc; A->nnz = nnz;
+	A->nrows_global = nrows_global; A->ncols_global = nrows_global; A->row0 = (int)lo; A->t_col0 = lo;
+	A->max_row_nnz = max_row; A->t_max_row_nnz = max_row; A->symmetric = 1;
+	std::vector<long long> ext_min((size_t)nranks, 0), ext_max((size_t)nranks, 0), rlo((size_t)nranks), rhi((size_t)nranks);
+	long long nnz_global = nnz;
+	if (nranks > 1) {
+		// extents and the global entry count of all ranks: one allreduce over a zero-padded array
+		double *buf = (double *)b200_scratch(3, sizeof(double) * (2 * (size_t)nranks + 2));
+		if (!buf) { free(A); return 1; }
+		std::vector<double> h(2 * (size_t)nranks + 1, 0.0);
+		h[2 * rank] = (double)cmin; h[2 * rank + 1] = (double)cmax; h[2 * nranks] = (double)nnz;
+		if (b200k_h2d(buf, h.data(), sizeof(double) * h.size()) || b200k_allreduce_sum(buf, h.size()) ||
+		    b200k_d2h(h.data(), buf, sizeof(double) * h.size())) { free(A); return 1; }
+		for (int q = 0; q < nranks; ++q) {
+			ext_min[q] = (long long)h[2 * q]; ext_max[q] = (long long)h[2 * q + 1];
+			b200_partition_range(nrows_global, q, nranks, &rlo[q], &rhi[q]);
+		}
+		nnz_global = (long long)h[2 * nranks];
+		bool contiguous = true;
+		for (int q = 0; q < nranks; ++q)
+			if ((rlo[q] - ext_min[q]) + (ext_max[q] + 1 - rhi[q]) > (rhi[q] - rlo[q])) contiguous = false;
+		if (!contiguous) {
+			free(A);
+			return b200_fail("b200_mat_create_from_local_rows: the off-slab columns of some rank exceed its own slab (not a banded "
+			                 "matrix in this partition); hand the whole matrix to b200_mat_create_from_ccs instead");
+		}
+		A->halo_contiguous = 1;
+		A->halo_below = (int)(lo - ext_min[rank]);
+		A->nhalo = (int)((lo - ext_min[rank]) + (ext_max[rank] + 1 - hi));
+		std::vector<int> nbr, recv_cnt, send_cnt;
+		std::vector<std::vector<int>> send((size_t)nranks);
+		std::vector<int> rc((size_t)nranks, 0);
+		for (int q = 0; q < nranks; ++q) {
+			if (q == rank) continue;
+			// rows of q inside my two ranges
+			long long a0 = std::max(ext_min[rank], rlo[q]), a1 = std::min(lo, rhi[q]);
+			if (a1 > a0) rc[q] += (int)(a1 - a0);
+			a0 = std::max(hi, rlo[q]); a1 = std::min(ext_max[rank] + 1, rhi[q]);
+			if (a1 > a0) rc[q] += (int)(a1 - a0);
+			// my rows inside q's two ranges, ascending
+			a0 = std::max(ext_min[q], lo); a1 = std::min(rlo[q], hi);
+			for (long long c = a0; c < a1; ++c) send[q].push_back((int)(c - lo));
+			a0 = std::max(rhi[q], lo); a1 = std::min(ext_max[q] + 1, hi);
+			for (long long c = a0; c < a1; ++c) send[q].push_back((int)(c - lo));
+		}
+		for (int q = 0; q < nranks; ++q) if (q != rank && (rc[q] || !send[q].empty())) nbr.push_back(q);
+		A->nnbr = (int)nbr.size();
+		A->nbr = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->recv_off = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->send_off = (int *)malloc(sizeof(int) * (nbr.size() + 1));
+		A->halo_cols = (int *)malloc(sizeof(int) * ((size_t)A->nhalo + 1));
+		{
+			int h2 = 0;
+			for (long long c = ext_min[rank]; c < lo; ++c) A->halo_cols[h2++] = (int)c;
+			for (long long c = hi; c <= ext_max[rank]; ++c) A->halo_cols[h2++] = (int)c;
+		}
+		int so = 0, ro = 0;
+		for (size_t i = 0; i < nbr.size(); ++i) {
+			A->nbr[i] = nbr[i]; A->recv_off[i] = ro; A->send_off[i] = so;
+			ro += rc[nbr[i]]; so += (int)send[nbr[i]].size();
+		}
+		A->recv_off[nbr.size()] = ro; A->send_off[nbr.size()] = so;
+		A->send_rows = (int *)malloc(sizeof(int) * (size_t)(so > 0 ? so : 1));
+		for (size_t i = 0; i < nbr.size(); ++i)
+			memcpy(A->send_rows + A->send_off[i], send[nbr[i]].data(), sizeof(int) * send[nbr[i]].size());
+	}
+	B200_CHECK(nnz_global < 0x7fffffffLL, "b200_mat_create_from_local_rows: %lld entries in all (32-bit counts)", nnz_global);
+	A->nnz_global = (int)nnz_global;
+	// local CSR with remapped columns (global - row0; halo rows in front of / behind the local ones)
+	std::vector<int> rp((size_t)nloc + 1), ci((size_t)(nnz > 0 ? nnz : 1));
+	for (int r = 0; r <= nloc; ++r) rp[r] = rp_in[r] - rp_in[0];
+	for (int e = 0; e < nnz; ++e) ci[e] = ci_in[rp_in[0] + e] - (int)lo;
+	const double *va = va_in + rp_in[0];
+	cudaStream_t st = g_b200.stream;
+	const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+	B200_CUDA(cudaMalloc(&A->rp, sizeof(int) * ((size_t)nloc + 1)));
+	B200_CUDA(cudaMalloc(&A->ci, sizeof(int) * nz));
+	B200_CUDA(cudaMalloc(&A->va, sizeof(double) * nz));
+	B200_CUDA(cudaMemcpyAsync(A->rp, rp.data(), sizeof(int) * ((size_t)nloc + 1), cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->ci, ci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->va, va, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	if (nranks == 1) { A->t_rp = A->rp; A->t_ci = A->ci; A->t_va = A->va; A->t_shared = 1; }   // symmetric by contract
+	if (nranks > 1) {
+		const int ns = A->send_off[A->nnbr];
+		B200_CUDA(cudaMalloc(&A->send_rows_dev, sizeof(int) * (size_t)(ns > 0 ? ns : 1)));
+		B200_CUDA(cudaMemcpyAsync(A->send_rows_dev, A->send_rows, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
+		b200_note_halo_capacity(A->ncols_global, A->nhalo);
+	}
+	B200_CUDA(cudaStreamSynchronize(st));
+	if (dia_build(A, rp.data(), ci.data(), va, nranks) || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
+	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
+	*out = A;
+	return 0;
+}
+
 extern "C" int b200_mat_destroy(b200_mat *A)
 {
 	if (!A) return 0;

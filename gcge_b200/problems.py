@@ -18,6 +18,8 @@ import itertools
 from dataclasses import dataclass
 from typing import Optional
 
+from pathlib import Path
+
 import numpy as np
 
 
@@ -125,6 +127,63 @@ def stencil_to_ccs(m: int, offsets, coefs) -> CCS:
     return CCS(n, n, j_col.astype(np.int32), i_row, data)
 
 
+def stencil_rows(m: int, offsets, coefs, k0: int, k1: int):
+    """Rows [k0 m^2, k1 m^2) of the operator stencil_to_ccs builds, as CSR-style arrays (rp, ci, va) with GLOBAL
+    column indices ascending inside a row: what one rank of a row-partitioned run owns (planes k0 .. k1-1 of the
+    lattice).  Entry (r, c) of sum_s coefs[s] shift(offsets[s]) has c = r - lin(offsets[s]); for the symmetric
+    stencils of this module the arrays equal the CCS arrays of the same columns (tests/test_partition.py)."""
+    offsets = np.asarray(offsets, dtype=np.int64).reshape(-1, 3)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    lin = offsets[:, 0] + m * (offsets[:, 1] + m * offsets[:, 2])
+    order = np.argsort(-lin, kind="stable")                 # ascending column = descending offset
+    offsets, coefs, lin = offsets[order], coefs[order], lin[order]
+    ns = len(lin)
+    idx1 = np.arange(m, dtype=np.int64)
+    ok = [((idx1[None, :] - offsets[:, a:a + 1]) >= 0) & ((idx1[None, :] - offsets[:, a:a + 1]) < m) for a in range(3)]
+    nrows = (k1 - k0) * m * m
+    rp = np.zeros(nrows + 1, np.int64)
+    parts_c, parts_v = [], []
+    planes = max(1, int(4_000_000 // (m * m)))
+    pos = 0
+    for ka in range(k0, k1, planes):
+        kb = min(k1, ka + planes)
+        kk = np.arange(ka, kb, dtype=np.int64)
+        rows = (idx1[None, None, :] + m * (idx1[None, :, None] + m * kk[:, None, None])).reshape(-1)
+        valid = (ok[0][:, None, None, :] & ok[1][:, None, :, None] & ok[2][:, kk][:, :, None, None])
+        valid = valid.reshape(ns, -1).T                     # [row, s], s in ascending column order
+        cols = rows[:, None] - lin[None, :]
+        cnt = valid.sum(axis=1)
+        r0 = (ka - k0) * m * m
+        rp[r0 + 1:r0 + 1 + len(rows)] = pos + np.cumsum(cnt)
+        pos += int(cnt.sum())
+        parts_c.append(cols[valid].astype(np.int32))
+        parts_v.append(np.broadcast_to(coefs[None, :], valid.shape)[valid])
+    assert pos < 2**31, "int32 index overflow"
+    return rp.astype(np.int32), np.concatenate(parts_c), np.concatenate(parts_v)
+
+
+def pencil_rows(name: str, m: int, k0: int, k1: int):
+    """((rp, ci, va) of A, the same of B or None) for the planes [k0, k1) of one of this module's lattice pencils
+    ("laplace3d_7pt", "q1_27pt", "p1_fem_kuhn"): the slab a rank owns, generated without the whole matrix."""
+    if name == "laplace3d_7pt":
+        offs = [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+        return stencil_rows(m, offs, [6.0] + [-1.0] * 6, k0, k1), None
+    if name == "q1_27pt":
+        h = 1.0 / (m + 1)
+        K1 = (-1.0 / h, 2.0 / h, -1.0 / h)
+        M1 = (h / 6.0, 4.0 * h / 6.0, h / 6.0)
+        offs, ca, cb = [], [], []
+        for dx, dy, dz in itertools.product((-1, 0, 1), repeat=3):
+            offs.append((dx, dy, dz))
+            ca.append(sum(fx[dx + 1] * fy[dy + 1] * fz[dz + 1] for fx, fy, fz in [(K1, M1, M1), (M1, K1, M1), (M1, M1, K1)]))
+            cb.append(M1[dx + 1] * M1[dy + 1] * M1[dz + 1])
+        return stencil_rows(m, offs, ca, k0, k1), stencil_rows(m, offs, cb, k0, k1)
+    if name == "p1_fem_kuhn":
+        ca, cb = _p1_kuhn_coefs(m)
+        return stencil_rows(m, _KUHN_OFFS, ca, k0, k1), stencil_rows(m, _KUHN_OFFS, cb, k0, k1)
+    raise KeyError(name)
+
+
 def laplace3d_7pt(m: int) -> Pencil:
     """Config 2: 7-point Laplacian on an m**3 grid, values 6/-1, B = None.
     Eigenvalues 6 - 2cos(i t) - 2cos(j t) - 2cos(k t), t = pi/(m+1)."""
@@ -217,11 +276,9 @@ _KUHN_OFFS = [(0, 0, 0),
               (1, 1, 1), (-1, -1, -1)]
 
 
-def p1_fem_kuhn(m: int) -> Pencil:
-    """Config 3 (SURVEY §8d): P1 stiffness / consistent mass pencil on the Kuhn
-    triangulation, n = m**3, 15 nnz/row, A and B with identical pattern.  The stencil
-    coefficients are read off a genuine assembly at m=3 (centre row) and scaled:
-    stiffness ~ h, mass ~ h**3."""
+def _p1_kuhn_coefs(m: int):
+    """stencil coefficients of the P1 stiffness / mass operators at mesh width 1/(m+1), read off a genuine
+    element-by-element assembly at m = 3 (centre row) and scaled: stiffness ~ h, mass ~ h**3"""
     A3, B3, h3 = p1_kuhn_assemble(3)
     centre = 1 + 3 * (1 + 3 * 1)
     h = 1.0 / (m + 1)
@@ -232,9 +289,113 @@ def p1_fem_kuhn(m: int) -> Pencil:
         cb.append(float(B3[r, centre]) * (h / h3) ** 3)
     # diagonal-edge stiffness entries are exact zeros analytically; snap assembly noise
     ca = [0.0 if abs(c) < 1e-12 * abs(ca[0]) else c for c in ca]
+    return ca, cb
+
+
+def p1_fem_kuhn(m: int) -> Pencil:
+    """Config 3 (SURVEY §8d): P1 stiffness / consistent mass pencil on the Kuhn
+    triangulation, n = m**3, 15 nnz/row, A and B with identical pattern.  The stencil
+    coefficients are read off a genuine assembly at m=3 (centre row) and scaled:
+    stiffness ~ h, mass ~ h**3."""
+    ca, cb = _p1_kuhn_coefs(m)
+    h = 1.0 / (m + 1)
     A = stencil_to_ccs(m, _KUHN_OFFS, ca)
     B = stencil_to_ccs(m, _KUHN_OFFS, cb)
     return Pencil("p1_fem_kuhn", A, B, {"m": m, "n": m**3, "h": h})
+
+
+# ------------------------------------------------------------------ config 1: the reference's mesh file
+_CUBE4_FIXTURE = Path(__file__).resolve().parents[1] / "tests" / "golden" / "cube4_mesh.json"
+
+
+def read_albert_mesh(path):
+    """ALBERT macro-triangulation file (the format of reference data/cube4.dat:1-6,133,519): returns
+    (vertices float64 [nv, 3], elements int64 [ne, 4])."""
+    import re
+    txt = Path(path).read_text()
+    nv = int(re.search(r"number of vertices:\s*(\d+)", txt).group(1))
+    ne = int(re.search(r"number of elements:\s*(\d+)", txt).group(1))
+
+    def section(name, nxt):
+        a = txt.index(name) + len(name)
+        return txt[a:txt.index(nxt, a)]
+
+    V = np.array(section("vertex coordinates:", "element vertices:").split(), float).reshape(nv, 3)
+    T = np.array(section("element vertices:", "element boundaries:").split(), np.int64).reshape(ne, 4)
+    return V, T
+
+
+def cube4_mesh():
+    """The mesh of reference data/cube4.dat from the committed fixture (tests/golden/make_cube4_fixture.py)."""
+    import json
+    d = json.loads(_CUBE4_FIXTURE.read_text())
+    return np.array(d["vertices_quarter_units"], float) * d["unit"], np.array(d["elements"], np.int64)
+
+
+def refine_uniform(V: np.ndarray, T: np.ndarray):
+    """One regular (red) refinement of a tetrahedral mesh: every edge gets its midpoint, every tetrahedron becomes
+    4 corner tetrahedra + 4 from the inner octahedron (split along the midpoint pair (01|23) -- any fixed choice gives
+    a conforming mesh).  Vertices keep their numbers, midpoints follow in order of first appearance."""
+    edges = {}
+    Vn = [tuple(v) for v in V]
+
+    def mid(a, b):
+        key = (a, b) if a < b else (b, a)
+        if key not in edges:
+            edges[key] = len(Vn)
+            Vn.append(tuple(0.5 * (np.asarray(Vn[a]) + np.asarray(Vn[b]))))
+        return edges[key]
+
+    Tn = []
+    for (a, b, c, d) in T.tolist():
+        ab, ac, ad, bc, bd, cd = mid(a, b), mid(a, c), mid(a, d), mid(b, c), mid(b, d), mid(c, d)
+        Tn += [(a, ab, ac, ad), (ab, b, bc, bd), (ac, bc, c, cd), (ad, bd, cd, d),
+               (ab, cd, ac, ad), (ab, cd, ad, bd), (ab, cd, bd, bc), (ab, cd, bc, ac)]
+    return np.array(Vn, float), np.array(Tn, np.int64)
+
+
+def p1_assemble_mesh(V: np.ndarray, T: np.ndarray):
+    """P1 stiffness and consistent mass matrices on a tetrahedral mesh (all vertices), vectorised over elements;
+    scipy CSC with the union pattern kept."""
+    import scipy.sparse as sp
+    X = V[T]                                                   # [ne, 4, 3]
+    M = np.concatenate([np.ones((len(T), 4, 1)), X], axis=2)   # [ne, 4, 4]
+    vol = np.abs(np.linalg.det(M)) / 6.0
+    grads = np.linalg.inv(M)[:, 1:, :]                         # [ne, 3, 4]
+    Ke = vol[:, None, None] * np.einsum("eda,edb->eab", grads, grads)
+    Me = vol[:, None, None] / 20.0 * (np.ones((4, 4)) + np.eye(4))[None]
+    r = np.repeat(T, 4, axis=1).reshape(-1)
+    c = np.tile(T, (1, 4)).reshape(-1)
+    nv = len(V)
+    A = sp.coo_matrix((Ke.reshape(-1), (r, c)), shape=(nv, nv)).tocsc()
+    B = sp.coo_matrix((Me.reshape(-1), (r, c)), shape=(nv, nv)).tocsc()
+    return A, B
+
+
+def cube4_p1(refine: int = 2, order: str = "lattice") -> Pencil:
+    """Config 1 restated: P1 stiffness / mass pencil on the mesh of reference data/cube4.dat after
+    `refine` regular refinements, homogeneous Dirichlet vertices (on the faces of [0,1]^3) removed.  refine = 2:
+    17^3 vertices, 15^3 = 3375 unknowns.  order = "lattice": unknowns in natural lattice order x + m (y + m z) (a
+    27-neighbour pattern with element-dependent coefficients: the device takes it for a lattice operator);
+    order = "mesh": in the mesh's own hierarchical vertex order (an unstructured matrix: the CSR kernels)."""
+    V, T = cube4_mesh()
+    for _ in range(refine):
+        V, T = refine_uniform(V, T)
+    A, B = p1_assemble_mesh(V, T)
+    inner = np.all((V > 1e-12) & (V < 1 - 1e-12), axis=1)
+    keep = np.nonzero(inner)[0]
+    if order == "lattice":
+        h = 0.25 / 2 ** refine
+        q = np.rint(V[keep] / h).astype(np.int64) - 1
+        m = int(round(1.0 / h)) - 1
+        keep = keep[np.argsort(q[:, 0] + m * (q[:, 1] + m * q[:, 2]), kind="stable")]
+
+    def ccs(M):
+        M = M[keep][:, keep].tocsc()
+        M.sort_indices()
+        return CCS(M.shape[0], M.shape[1], M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64))
+
+    return Pencil("cube4_p1", ccs(A), ccs(B), {"refine": refine, "order": order, "n": len(keep)})
 
 
 def ccs_to_dense(M: CCS) -> np.ndarray:

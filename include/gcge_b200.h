@@ -124,6 +124,14 @@ int  b200_plan_destroy(b200_plan *p);
  *      (reference test/test_app_ccs.c:99-102, :142-184) ------------------------ */
 int b200_mat_create_from_ccs(int nrows, int ncols, const int *j_col, const int *i_row,
                              const double *data, b200_mat **out);
+/* Several ranks, large matrices: every rank hands over ONLY its own row block [row0, row0 + nrows_local) =
+ * b200_partition_range(nrows_global, rank, nranks) as CSR-style arrays (rp[nrows_local + 1], global column indices
+ * ascending inside a row) -- for the symmetric matrices of the eigenproblem exactly the CCS arrays of those columns.
+ * What the reference's distributed back ends do (every rank owns its rows only, app/app_phg.c:292-357); collective.
+ * Banded matrices only; the matrix is taken to be symmetric (the reference assumes that for every matrix,
+ * app/app_ccs.c:140-150).  Works on one rank too (the block is then the whole matrix). */
+int b200_mat_create_from_local_rows(int nrows_global, int row0, int nrows_local, const int *rp, const int *ci,
+                                    const double *va, b200_mat **out);
 int b200_mat_destroy(b200_mat *A);
 int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nnz);
 /* gather the device matrix back to CCS arrays; bit-exact round trip */

@@ -1,5 +1,5 @@
-"""BASELINE config 5: kernel sweep.  SpMM (Y = A X), Gram (X^T Y), LinearComb (X C), axpby and
-the fused BlockPCG kernels at k = block widths on an n-row P1-FEM pencil, timed with CUDA
+"""BASELINE config 5: kernel sweep.  SpMM (Y = A X), Gram (X^T Y, 3k x k), LinearComb (X C), axpby, dots and
+the B-orthogonalisation of a k-block against a 2k-block (TestOrth's shape) at k = 16 ... 512 on an n-row P1-FEM pencil, timed with CUDA
 events on the library stream (L2 flushed between repetitions), reported as achieved HBM GB/s
 or FP64 TFLOP/s from the ALGORITHMIC bytes/flops of SURVEY.md §8d."""
 import argparse, json, sys
@@ -11,9 +11,9 @@ from gcge_b200 import api, problems as P
 ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=200)
 ap.add_argument("--gen", default="p1_fem_kuhn")
-ap.add_argument("--ks", default="10,16,32,40,64,128")
+ap.add_argument("--ks", default="16,32,64,128,256,512")
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--ops", default="spmm,axpby,gram,lincomb,dots")
+ap.add_argument("--ops", default="spmm,axpby,gram,lincomb,dots,orth")
 ap.add_argument("--p", type=int, default=0, help="Gram/LinearComb inner width (default 3k)")
 ap.add_argument("--noflush", type=int, default=0)
 a = ap.parse_args()
@@ -73,5 +73,32 @@ for k in [int(v) for v in a.ks.split(",")]:
         med, best = timeit(lambda: api.multivec_linear_comb(X, Y, (0, 0), (p, k), coef, p, None, 0), a.reps)
         fl = 2.0 * n * p * k; byt = 8 * n * (p + k)
         row["lincomb_ms"] = round(med, 4); row["lincomb_TF"] = round(fl / med / 1e9, 2); row["lincomb_GBs"] = round(byt / med / 1e6, 1)
+    if "orth" in ops and p >= 3 * k:
+        # B-orthonormalise the k columns [2k, 3k) against the 2k columns in front of them (reference TestOrth,
+        # test/test_orth.c:44-111, at scale): 2k-block prepared once, the k-block refilled before every repetition
+        Bm = api.Mat(pen.B) if pen.B is not None else None
+        ws = api.MultiVec(n, min(k, 80))
+        api.libc_srand(3); X.set_random(0, 3 * k)
+        end0 = api.orth(X, 0, 2 * k, B=Bm, ws=ws, block_size=80)
+        ts = []
+        for _ in range(max(2, a.reps // 2)):
+            X.set_random(2 * k, 3 * k)
+            api.sync()
+            api.timer_start(); end = api.orth(X, 2 * k, 3 * k, B=Bm, ws=ws, block_size=80); ts.append(api.timer_stop())
+        med = float(np.median(ts))
+        nb = (k + 79) // 80                                        # blocks of 80 columns, two rounds each
+        # algorithmic traffic: per block and round one B x (SpMM bytes), Gram + update against everything
+        # in front (read X0 twice, read + write the block), panel Gram + update
+        byt = 0.0; fl = 0.0
+        for b in range(nb):
+            kb = min(80, k - 80 * b); m0 = 2 * k + 80 * b
+            spmm_b = (pen.B.nnz * 12 + (n + 1) * 4 + 16 * n * kb) if pen.B is not None else 0
+            byt += 2 * (2 * spmm_b + 8 * n * (2 * m0 + 3 * kb) + 8 * n * 3 * kb)
+            fl += 2 * (4.0 * n * m0 * kb + 4.0 * n * kb * kb)
+        row["orth_ms"] = round(med, 3); row["orth_end"] = [int(end0), int(end)]
+        row["orth_GBs"] = round(byt / med / 1e6, 1); row["orth_TF"] = round(fl / med / 1e9, 2)
+        ws.close()
+        if Bm is not None:
+            Bm.close()
     print(json.dumps(row), flush=True)
     X.close(); Y.close()

@@ -86,6 +86,23 @@ for kind, dims in (("p1", (12, 9, 4 * world)), ("27pt", (10, 6, 3 * world)), ("7
             got = gather_rows(Yl, 0, k, nl)
             check(np.array_equal(got, oracle_spmm(M, np.asfortranarray(xl[:, 2:2 + k]))), f"lattice SpMM {kind} k={k} rep={rep}")
 
+# ---- slab-local construction: every rank hands over only its own planes (b200_mat_create_from_local_rows) ------
+mloc = 4 * world
+penl = P.p1_fem_kuhn(mloc)
+nl = mloc ** 3
+rowsA, rowsB = P.pencil_rows("p1_fem_kuhn", mloc, (mloc // world) * rank, (mloc // world) * (rank + 1))
+Awhole = api.Mat(penl.A); Bwhole = api.Mat(penl.B)
+Aloc = api.Mat.from_local_rows(nl, (mloc // world) * rank * mloc * mloc, *rowsA)
+Bloc = api.Mat.from_local_rows(nl, (mloc // world) * rank * mloc * mloc, *rowsB)
+check(Aloc.storage() == Awhole.storage(), f"storage differs: {Aloc.storage()} vs {Awhole.storage()}")
+xl = np.asfortranarray(np.random.default_rng(9).standard_normal((nl, 16)))
+Xl = api.MultiVec.from_numpy(xl); Y1 = api.MultiVec(nl, 16); Y2 = api.MultiVec(nl, 16)
+api.mat_dot_multivec(Awhole, Xl, Y1, (0, 0), (16, 16)); api.mat_dot_multivec(Aloc, Xl, Y2, (0, 0), (16, 16))
+g1 = gather_rows(Y1, 0, 16, nl)
+check(np.array_equal(g1, gather_rows(Y2, 0, 16, nl)) and np.array_equal(g1, oracle_spmm(penl.A, xl)), "local-rows SpMM")
+o1 = api.gcg_solve(Awhole, Bwhole, nev=8); o2 = api.gcg_solve(Aloc, Bloc, nev=8)
+check(o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"], o2["eval"]), "local-rows solve differs from whole-CCS solve")
+
 # ---- the first slab rows lack the farthest sub-diagonal, so the halo plan's extent (from the entries
 # those rows have) is SHORTER than the reach of the diagonal image; rows further inside still need halo rows and
 # must not be multiplied before the halo has arrived ------------------------------------------------------------

@@ -39,6 +39,10 @@ CASES = [
                                     "-gcge_compW_orth_method", "bgs")),
     ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_compW_cg_auto_shift", 1)),
     ("p1_fem_kuhn", {"m": 12}, 10, ("-gcge_compW_cg_shift", 3.0)),
+    # BASELINE config 1 restated: P1 on the reference's own mesh data/cube4.dat after two regular
+    # refinements (15^3 unknowns), nev = 10; unknowns in lattice order and in the mesh's own vertex order
+    ("cube4_p1", {"refine": 2}, 10),
+    ("cube4_p1", {"refine": 2, "order": "mesh"}, 10),
 ]
 
 

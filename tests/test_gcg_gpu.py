@@ -69,6 +69,27 @@ def test_device_gcg_vs_golden(b200, golden, idx):
     assert o["stats"]["launches"] > 0
 
 
+@pytest.mark.parametrize("order", ["lattice", "mesh"])
+def test_device_gcg_config1_cube4_mesh(b200, golden, drive_b200, order):
+    """BASELINE config 1 restated: P1 pencil on the reference's own mesh data/cube4.dat after two regular
+    refinements (15^3 unknowns), nev = 10 (nevMax 20, block_size 10) -- device GCG and the reference's GCG over
+    OPS_B200_Set against the reference's recorded CCS+OpenMP run.  In lattice order the matrix has a 27-neighbour
+    pattern with element-dependent coefficients (lattice SpMM kernel); in the mesh's own order it is unstructured."""
+    case = [c for c in golden["cases"] if c["generator"] == "cube4_p1" and c["args"].get("order", "lattice") == order][0]
+    pen = gen(case)
+    A = b200.Mat(pen.A); B = b200.Mat(pen.B)
+    assert (A.storage()["lat_s1"] == 15) == (order == "lattice")
+    o = b200.gcg_solve(A, B, nev=10)
+    assert o["nev_conv"] >= 10
+    assert abs(o["num_iter"] - case["num_iter"]) <= ITER_TOL, (o["num_iter"], case["num_iter"])
+    assert rel(o["eval"][:10], np.array(case["eval"][:10])) < 1e-10
+    ok, r = residual_test(pen, o["eval"][:10], o["evec_mv"].numpy(0, 10))
+    assert ok, r
+    if drive_b200 is not None:
+        a = drive_b200(0, pen.A, pen.B, nev=10)
+        assert abs(a["num_iter"] - case["num_iter"]) <= 1 and rel(a["eval"][:10], np.array(case["eval"][:10])) < 1e-10
+
+
 def test_device_gcg_analytic_7pt(b200):
     m, nev = 24, 12
     pen = P.laplace3d_7pt(m)

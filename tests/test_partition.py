@@ -127,3 +127,21 @@ def test_world_size_2_gloo_halo_exchange():
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
     assert "halo exchange ok" in outs[0]
+
+
+@pytest.mark.parametrize("name,m", [("p1_fem_kuhn", 9), ("q1_27pt", 8), ("laplace3d_7pt", 10)])
+def test_slab_generators_equal_the_whole_matrix_columns(name, m):
+    """problems.pencil_rows (what a rank generates for itself with bench.py --local-gen) == the CCS columns of the
+    whole-matrix generator for the same planes, bit for bit."""
+    pen = getattr(P, name)(m)
+    for (k0, k1) in ((0, m), (2, 5), (m - 1, m)):
+        rowsA, rowsB = P.pencil_rows(name, m, k0, k1)
+        c0, c1 = k0 * m * m, k1 * m * m
+        for M, rows in ((pen.A, rowsA), (pen.B, rowsB)):
+            if M is None:
+                assert rows is None
+                continue
+            rp, ci, va = rows
+            assert np.array_equal(rp, M.j_col[c0:c1 + 1] - M.j_col[c0])
+            assert np.array_equal(ci, M.i_row[M.j_col[c0]:M.j_col[c1]])
+            assert np.array_equal(va, M.data[M.j_col[c0]:M.j_col[c1]])

@@ -285,6 +285,26 @@ def test_spmm_lattice_kernel_bitexact(b200, kind, dims, k, monkeypatch):
         assert not got[:, :yo].any() and not got[:, yo + k:].any()
 
 
+@pytest.mark.parametrize("name,m", [("p1_fem_kuhn", 9), ("q1_27pt", 8), ("laplace3d_7pt", 10)])
+def test_matrix_from_local_rows_matches_whole_ccs(b200, name, m):
+    """b200_mat_create_from_local_rows (a rank hands over only its rows; here one rank = all rows) builds the same
+    device matrix as b200_mat_create_from_ccs: same storage decisions, bit-identical SpMM, bit-identical solve."""
+    from gcge_b200 import api
+    pen = getattr(P, name)(m)
+    rowsA, rowsB = P.pencil_rows(name, m, 0, m)
+    n = pen.A.ncols
+    A1 = b200.Mat(pen.A); A2 = api.Mat.from_local_rows(n, 0, *rowsA)
+    assert A1.storage() == A2.storage() and A2.storage()["lat_s1"] == m
+    x = np.asfortranarray(np.random.default_rng(1).standard_normal((n, 20)))
+    X = b200.MultiVec.from_numpy(x); Y1 = b200.MultiVec(n, 20); Y2 = b200.MultiVec(n, 20)
+    api.mat_dot_multivec(A1, X, Y1, (0, 0), (20, 20)); api.mat_dot_multivec(A2, X, Y2, (0, 0), (20, 20))
+    assert np.array_equal(Y1.numpy(), Y2.numpy()) and np.array_equal(Y1.numpy(), oracle_spmm(pen.A, x))
+    B1 = None if pen.B is None else b200.Mat(pen.B)
+    B2 = None if rowsB is None else api.Mat.from_local_rows(n, 0, *rowsB)
+    o1 = b200.gcg_solve(A1, B1, nev=6); o2 = b200.gcg_solve(A2, B2, nev=6)
+    assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"], o2["eval"])
+
+
 def test_spmm_lattice_recognition_rejects_wrap_around(b200):
     """A periodic operator has the same diagonals (plus the wrap diagonals) but couples across the lattice faces:
     it must NOT be taken for a Dirichlet lattice (the tiles would read zero-filled rows outside the lattice),
