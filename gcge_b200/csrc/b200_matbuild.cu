@@ -360,7 +360,7 @@ int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_
 		for (long long d : table_h) if (d != MB_EMPTY) offs.push_back(d);
 		std::sort(offs.begin(), offs.end());
 		const int nd = (int)offs.size();
-		bool ok = nd >= 1 && nd <= 32 && !((double)nnz_loc < 0.5 * (double)nd * nloc);
+		bool ok = nd >= 1 && nd <= 32 && !((double)nnz_loc < 0.45 * (double)nd * nloc);
 		for (long long d : offs) if (d > 0x3fffffff || d < -0x3fffffff) ok = false;
 		if (ok) {
 			int ng = 0, ndp = 0;
