@@ -474,6 +474,7 @@ def run_b200(a) -> int:
         tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
         if tr.get("workload", {}).get("m") == a.m and world == 1 and top in tr:
             roof["traffic"] = tr[top]["traffic_bytes_per_launch"]
+            roof["traffic_algorithmic_at_capture"] = tr[top].get("algorithmic_bytes_per_launch")
             roof["traffic_source"] = f'{tr[top]["kernel"]}: {tr[top]["source"]}'
     except Exception:
         pass

@@ -123,3 +123,64 @@ int drive_gcg_b200(int tier, int n,
 	OPS_Destroy(&ops);
 	return 0;
 }
+
+/* ---- the reference's BlockAMG (src/ops_lin_sol.c:466-715) UNCHANGED over OPS_B200_Set ------
+ * Same call sequence as ref_block_amg_dense (oracle/ref_driver.c) and the reference's TestMultiGrid
+ * (test/test_multi_grid.c:95-125), with the hierarchy as device matrices: A_l square, P_l rectangular
+ * (n_l x n_{l+1}); restriction is the true transposed multiply of the device back end. */
+#include "ops_lin_sol.h"
+int drive_block_amg_b200(int num_levels, const int *n_l,
+		int **A_j_col, int **A_i_row, double **A_data,
+		int **P_j_col, int **P_i_row, double **P_data, int k,
+		const double *b, double *x, int *max_iter, double *rate, double *tol)
+{
+	OPS *ops = NULL;
+	OPS_Create(&ops);
+	OPS_B200_Set(ops);
+	OPS_Setup(ops);
+	ops->Printf = quiet_printf; ops->lapack_ops->Printf = quiet_printf;
+	B200MAT *A = calloc(num_levels, sizeof(B200MAT)), *P = calloc(num_levels, sizeof(B200MAT));
+	void **A_array = calloc(num_levels, sizeof(void *)), **P_array = calloc(num_levels, sizeof(void *));
+	for (int l = 0; l < num_levels; ++l) {
+		CCSMAT c;
+		c.nrows = n_l[l]; c.ncols = n_l[l]; c.j_col = A_j_col[l]; c.i_row = A_i_row[l]; c.data = A_data[l];
+		B200_MatCreateFromCCS(&A[l], &c);
+		A_array[l] = (void *)&A[l];
+		if (l + 1 < num_levels) {
+			c.nrows = n_l[l]; c.ncols = n_l[l + 1]; c.j_col = P_j_col[l]; c.i_row = P_i_row[l]; c.data = P_data[l];
+			B200_MatCreateFromCCS(&P[l], &c);
+			P_array[l] = (void *)&P[l];
+		}
+	}
+	void ***mv_ws[5];
+	for (int i = 0; i < 5; ++i) {
+		mv_ws[i] = malloc(num_levels * sizeof(void **));
+		for (int l = 0; l < num_levels; ++l) ops->MultiVecCreateByMat(&mv_ws[i][l], k, A_array[l], ops);
+	}
+	double *dbl_ws = calloc(4096 + 16 * (size_t)k, sizeof(double));
+	int *int_ws = calloc(1024 + 4 * (size_t)k, sizeof(int));
+	void **Bv, **Xv;
+	ops->MultiVecCreateByMat(&Bv, k, A_array[0], ops);
+	ops->MultiVecCreateByMat(&Xv, k, A_array[0], ops);
+	if (b200_mv_upload((b200_mv *)Bv, 0, k, b, n_l[0]) || b200_mv_upload((b200_mv *)Xv, 0, k, x, n_l[0])) {
+		fprintf(stderr, "drive_block_amg_b200: %s\n", b200_last_error());
+		abort();
+	}
+	int start[2] = {0, 0}, end[2] = {k, k};
+	MultiLinearSolverSetup_BlockAMG(max_iter, rate, tol, "abs", A_array, P_array, num_levels,
+			mv_ws, dbl_ws, int_ws, NULL, ops);
+	ops->MultiLinearSolver(A_array[0], Bv, Xv, start, end, ops);
+	if (b200_mv_download((b200_mv *)Xv, 0, k, x, n_l[0])) {
+		fprintf(stderr, "drive_block_amg_b200: %s\n", b200_last_error());
+		abort();
+	}
+	ops->MultiVecDestroy(&Bv, k, ops); ops->MultiVecDestroy(&Xv, k, ops);
+	for (int i = 0; i < 5; ++i) {
+		for (int l = 0; l < num_levels; ++l) ops->MultiVecDestroy(&mv_ws[i][l], k, ops);
+		free(mv_ws[i]);
+	}
+	for (int l = 0; l < num_levels; ++l) { B200_MatDestroy(&A[l]); if (l + 1 < num_levels) B200_MatDestroy(&P[l]); }
+	free(dbl_ws); free(int_ws); free(A); free(P); free(A_array); free(P_array);
+	OPS_Destroy(&ops);
+	return 0;
+}

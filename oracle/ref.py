@@ -169,3 +169,18 @@ def gcg_solve(A, B=None, nev=10, nev_max=0, block_size=0, nev_init=0, tol=(1e-1,
                         _dp(None if evec_given is None else _F(np.asfortranarray(evec_given, dtype=np.float64))))
     return {"eval": ev, "evec": evec, "num_iter": num_iter.value, "nev_conv": nev_conv.value,
             "seconds": secs.value}
+
+
+def block_amg_dense(A_levels, P_levels, b, x, max_iter, rate, tol):
+    """The reference's BlockAMG (src/ops_lin_sol.c:466-715) over its dense LAPACK back end (the CCS back end
+    cannot run it: no MultiGridCreate, transposed multiply assumes symmetry).  A_levels[l]: dense n_l x n_l,
+    P_levels[l]: dense n_l x n_{l+1}; x is updated in place."""
+    L = len(A_levels)
+    A = [np.asfortranarray(a, dtype=np.float64) for a in A_levels]
+    P = [np.asfortranarray(p, dtype=np.float64) for p in P_levels]
+    n_l = (C.c_int * L)(*[a.shape[0] for a in A])
+    Ap = (c_dbl_p * L)(*[_dp(a) for a in A])
+    Pp = (c_dbl_p * L)(*([_dp(p) for p in P] + [None]))
+    mi = (C.c_int * len(max_iter))(*max_iter); ra = (C.c_double * len(rate))(*rate); to = (C.c_double * len(tol))(*tol)
+    lib().ref_block_amg_dense(L, n_l, Ap, Pp, int(x.shape[1]), _dp(_F(b)), _dp(_F(x)), mi, ra, to)
+    return x

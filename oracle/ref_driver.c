@@ -277,3 +277,48 @@ int ref_gcg_solve(int n,
 	OPS_Destroy(&ops);
 	return 0;
 }
+
+/* ---- BlockAMG (reference src/ops_lin_sol.c:466-715) over the reference's dense LAPACK back end ----------
+ * The CCS back end cannot run it: its MatTransDotMultiVec assumes a square symmetric matrix (reference
+ * app/app_ccs.c:140-150) and it has no MultiGridCreate.  The hierarchy comes from the caller: A_dense[l] is
+ * n_l x n_l, P_dense[l] is n_l x n_{l+1} (prolongation, fine rows x coarse columns), all column-major.
+ * Follows the sequence of the reference's TestMultiGrid (test/test_multi_grid.c:95-125). */
+int ref_block_amg_dense(int num_levels, const int *n_l, double **A_dense, double **P_dense, int k,
+		double *b, double *x, int *max_iter, double *rate, double *tol)
+{
+	OPS *ops = NULL;
+	OPS_Create(&ops);
+	OPS_LAPACK_Set(ops);
+	OPS_Setup(ops);
+	ops->Printf = quiet_printf;
+	LAPACKMAT *A = calloc(num_levels, sizeof(LAPACKMAT)), *P = calloc(num_levels, sizeof(LAPACKMAT));
+	void **A_array = calloc(num_levels, sizeof(void *)), **P_array = calloc(num_levels, sizeof(void *));
+	for (int l = 0; l < num_levels; ++l) {
+		A[l].nrows = n_l[l]; A[l].ncols = n_l[l]; A[l].ldd = n_l[l]; A[l].data = A_dense[l];
+		A_array[l] = (void *)&A[l];
+		if (l + 1 < num_levels) {
+			P[l].nrows = n_l[l]; P[l].ncols = n_l[l + 1]; P[l].ldd = n_l[l]; P[l].data = P_dense[l];
+			P_array[l] = (void *)&P[l];
+		}
+	}
+	void ***mv_ws[5];
+	for (int i = 0; i < 5; ++i) {
+		mv_ws[i] = malloc(num_levels * sizeof(void **));
+		for (int l = 0; l < num_levels; ++l) ops->MultiVecCreateByMat(&mv_ws[i][l], k, A_array[l], ops);
+	}
+	double *dbl_ws = calloc(4096 + 16 * (size_t)k, sizeof(double));
+	int *int_ws = calloc(1024 + 4 * (size_t)k, sizeof(int));
+	LAPACKVEC Bv, Xv;
+	wrap_mv(&Bv, b, n_l[0], k); wrap_mv(&Xv, x, n_l[0], k);
+	int start[2] = {0, 0}, end[2] = {k, k};
+	MultiLinearSolverSetup_BlockAMG(max_iter, rate, tol, "abs", A_array, P_array, num_levels,
+			mv_ws, dbl_ws, int_ws, NULL, ops);
+	ops->MultiLinearSolver(A_array[0], (void **)&Bv, (void **)&Xv, start, end, ops);
+	for (int i = 0; i < 5; ++i) {
+		for (int l = 0; l < num_levels; ++l) ops->MultiVecDestroy(&mv_ws[i][l], k, ops);
+		free(mv_ws[i]);
+	}
+	free(dbl_ws); free(int_ws); free(A); free(P); free(A_array); free(P_array);
+	OPS_Destroy(&ops);
+	return 0;
+}

@@ -101,4 +101,20 @@ def drive_b200(refmod):
                            dp(None if evec_given is None else np.asfortranarray(evec_given, dtype=np.float64)))
         return {"eval": ev, "evec": evec, "num_iter": it.value, "nev_conv": nc.value, "seconds": secs.value}
 
+    def block_amg(A_levels, P_levels, b, x, max_iter, rate, tol):
+        """the reference's BlockAMG unchanged over OPS_B200_Set (oracle/drive_b200.c: drive_block_amg_b200);
+        A_levels / P_levels: problems.CCS per level (P rectangular n_l x n_{l+1}); x updated in place"""
+        L = len(A_levels)
+        ipp, dpp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        n_l = (C.c_int * L)(*[a.ncols for a in A_levels])
+        mk = lambda typ, arrs: (typ * L)(*arrs)
+        Aj = mk(ipp, [a.j_col.ctypes.data_as(ipp) for a in A_levels]); Ai = mk(ipp, [a.i_row.ctypes.data_as(ipp) for a in A_levels])
+        Ad = mk(dpp, [a.data.ctypes.data_as(dpp) for a in A_levels])
+        Pj = mk(ipp, [p.j_col.ctypes.data_as(ipp) for p in P_levels] + [None]); Pi = mk(ipp, [p.i_row.ctypes.data_as(ipp) for p in P_levels] + [None])
+        Pd = mk(dpp, [p.data.ctypes.data_as(dpp) for p in P_levels] + [None])
+        mi = (C.c_int * len(max_iter))(*max_iter); ra = (C.c_double * len(rate))(*rate); to = (C.c_double * len(tol))(*tol)
+        drv.drive_block_amg_b200(L, n_l, Aj, Ai, Ad, Pj, Pi, Pd, int(x.shape[1]), b.ctypes.data_as(dpp), x.ctypes.data_as(dpp), mi, ra, to)
+        return x
+
+    run.block_amg = block_amg
     return run
