@@ -307,11 +307,11 @@ class Mat:
         return j_col, i_row[:self.nnz], data[:self.nnz]
 
     def storage(self) -> dict:
-        """{'dia_nd', 'lat_s1', 'lat_s2'}: which SpMM storage the matrix got (b200_mat_storage)."""
-        v = [C.c_int(0) for _ in range(3)]
-        lib().b200_mat_storage.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p]
+        """{'dia_nd', 'lat_s1', 'lat_s2', 'lat_const'}: which SpMM storage the matrix got (b200_mat_storage)."""
+        v = [C.c_int(0) for _ in range(4)]
+        lib().b200_mat_storage.argtypes = [C.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p]
         _chk(lib().b200_mat_storage(self.h, *[C.byref(x) for x in v]))
-        return {"dia_nd": v[0].value, "lat_s1": v[1].value, "lat_s2": v[2].value}
+        return {"dia_nd": v[0].value, "lat_s1": v[1].value, "lat_s2": v[2].value, "lat_const": v[3].value}
 
     def axpby(self, alpha, X, beta):
         """self = alpha*X + beta*self (slot MatAxpby)."""

@@ -51,6 +51,35 @@ __device__ __forceinline__ void dia_run_ct(double (&acc)[RB][2 * CP], const doub
 }
 
 
+// The same with ROW-INVARIANT coefficients (a constant stencil): the run's values a0, a1, a2 come from the caller's
+// registers / the constant bank instead of a shared-memory image -- no value traffic at all.
+template <int RB, int W, int K, int KP, bool DOT>
+__device__ __forceinline__ void dia_run_const(double (&acc)[RB][2], const double *tile, double a0, double a1, double a2,
+                                              double2 (&pst)[RB][1], int zrow)
+{
+	double2 xv[RB + W - 1];
+#pragma unroll
+	for (int t = 0; t < RB + W - 1; ++t) xv[t] = *reinterpret_cast<const double2 *>(tile + t * K);
+	if (DOT && zrow >= 0) {
+#pragma unroll
+		for (int i = 0; i < RB; ++i)
+			pst[i][0] = (W >= 3 && zrow == 2) ? xv[i + (W >= 3 ? 2 : 0)] : ((W >= 2 && zrow == 1) ? xv[i + (W >= 2 ? 1 : 0)] : xv[i]);
+	}
+#pragma unroll
+	for (int i = 0; i < RB; ++i) {
+		acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a0, xv[i].x));
+		acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a0, xv[i].y));
+		if (W >= 2) {
+			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a1, xv[i + (W >= 2 ? 1 : 0)].x));
+			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a1, xv[i + (W >= 2 ? 1 : 0)].y));
+		}
+		if (W >= 3) {
+			acc[i][0] = __dadd_rn(acc[i][0], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].x));
+			acc[i][1] = __dadd_rn(acc[i][1], __dmul_rn(a2, xv[i + (W >= 3 ? 2 : 0)].y));
+		}
+	}
+}
+
 // 1-D bulk copy whose lines are the first to leave L2: the matrix values are read once per SpMM,
 // the x rows pulled by the neighbouring TMA boxes up to 2 m^2 rows later must stay
 __device__ __forceinline__ void bulk_load_1d_evict_first(void *dst, const void *src, unsigned bytes, unsigned long long *bar)

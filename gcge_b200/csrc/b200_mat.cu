@@ -537,12 +537,13 @@ extern "C" int b200_mat_shape(const b200_mat *A, int *nrows, int *ncols, int *nn
 	return 0;
 }
 
-extern "C" int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2)
+extern "C" int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2, int *lat_const)
 {
 	B200_CHECK(A, "b200_mat_storage: NULL matrix");
 	if (dia_nd) *dia_nd = A->dia_nd;
 	if (lat_s1) *lat_s1 = A->lat_s1;
 	if (lat_s2) *lat_s2 = A->lat_s2;
+	if (lat_const) *lat_const = A->lat_const;
 	return 0;
 }
 
@@ -715,5 +716,7 @@ extern "C" int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200
 			B200_KERNEL_CHECK();
 		}
 	}
-	return 0;
+	// the values changed: the constant-stencil coefficients kept on the host (lattice SpMM without value loads)
+	// must follow them, and a constant stencil may have stopped being one (or have become one)
+	return b200k_lat_detect(Y);
 }

@@ -40,9 +40,14 @@ struct LatParams {
 	int slice_bytes, val_bytes;                        // one slice / one value buffer (bytes a copy delivers)
 	int slice_stride, val_stride;                      // ... and their 128-byte aligned strides in the rings
 	LatRun run[32];
+	double coef[40];                                   // CONST: the stencil's coefficients by value slot (one row of the image)
 };
 
-template <int KP, int NT, bool DOT>
+// CONST: the operator is a constant stencil (every row carries the same coefficients, entries exist exactly where
+// the neighbour is inside the lattice): the coefficients come from the kernel parameters, no value tile is loaded, and
+// rows outside the lattice contribute a_d * 0 because the copy engine zero-fills them -- +-0 added to an accumulator
+// that starts at +0.0 changes nothing, so the result is still the reference's, bit for bit, for every finite x.
+template <int KP, int NT, bool DOT, bool CONST>
 __global__ void __launch_bounds__(NT + 32, 1)
 spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmv,
                 const __grid_constant__ LatParams P, double *y, int ldy, const int *__restrict__ gate, double *dot_part)
@@ -80,7 +85,7 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 					mbar_expect_tx(full + slot, (unsigned)P.slice_bytes);
 					tma_load_4d(smem_raw + (size_t)slot * P.slice_stride, &tmx, 0, I0 - 1, J0 - 1, k0 - 1 + t + P.xshift, full + slot);
 					if (++slot == NS) { slot = 0; phase ^= 1u; }
-					if (t >= 2) {
+					if (!CONST && t >= 2) {
 						// the values of output plane k0 + t - 2, needed together with the slice just requested
 						mbar_spin(vempty + vslot, vphase ^ 1u);
 						mbar_expect_tx(vfull + vslot, (unsigned)P.val_bytes);
@@ -112,7 +117,7 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 			ring0 = ring1; ring1 = ring2; ring2 = slot;
 			if (++slot == NS) { slot = 0; phase ^= 1u; }
 			if (t < 2) continue;
-			mbar_spin(vfull + vslot, vphase);
+			if (!CONST) mbar_spin(vfull + vslot, vphase);
 			const double *vals = reinterpret_cast<const double *>(vbuf + (size_t)vslot * P.val_stride);
 			const long long prow = (long long)(k0 + t - 2) * P.s1 * P.my;     // first row of the output plane
 			if (live) {
@@ -132,7 +137,13 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 						const double *tile = reinterpret_cast<const double *>(smem_raw + (size_t)sl * P.slice_stride) +
 						                     (rbase + r.rowoff) * K + c;
 						const int zrow = (DOT && g == P.zero_run) ? P.zero_pos : -1;
-						if (r.w == 2)      dia_run_ct<RB, 2, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
+						if (CONST) {
+							const double a0 = P.coef[r.sp], a1 = P.coef[r.sp + 1], a2 = P.coef[r.sp + 2];
+							if (r.w == 2)      dia_run_const<RB, 2, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
+							else if (r.w == 3) dia_run_const<RB, 3, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
+							else               dia_run_const<RB, 1, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
+						}
+						else if (r.w == 2) dia_run_ct<RB, 2, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
 						else if (r.w == 3) dia_run_ct<RB, 3, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
 						else               dia_run_ct<RB, 1, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
 					}
@@ -158,7 +169,7 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) {
-				mbar_arrive(vempty + vslot);
+				if (!CONST) mbar_arrive(vempty + vslot);
 				mbar_arrive(empty + ring0);                    // plane k - 1 of this step is not needed again
 				if (t == len + 1) { mbar_arrive(empty + ring1); mbar_arrive(empty + ring2); }      // end of the segment
 			}
@@ -210,6 +221,36 @@ __global__ void lat_violations_kernel(int nrows, long long row0, int s1, int my,
 	if (bad) atomicAdd(count, bad);
 }
 
+// rows whose image differs from the constant stencil `coef` (coefficient where the neighbour is inside the lattice,
+// +0.0 where it is not; padding slots are zero in both)
+__global__ void lat_const_kernel(int nrows, long long row0, int s1, int my, long long nz, int ng,
+                                 const int *__restrict__ off, const int *__restrict__ grp, int ndp,
+                                 const double *__restrict__ val, const double *__restrict__ coef, int *count)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	const long long R = row0 + r, s2 = (long long)s1 * my;
+	const int i = (int)(R % s1), j = (int)((R / s1) % my);
+	const long long k = R / s2;
+	int bad = 0;
+	for (int g = 0; g < ng; ++g) {
+		const int w = grp[2 * g + 1], sp = grp[2 * g];
+		for (int t = 0; t < w; ++t) {
+			const long long d = (long long)off[g] + t;
+			long long q = d + s2 / 2;
+			const long long dk = q >= 0 ? q / s2 : -((-q + s2 - 1) / s2);
+			const long long rem = d - dk * s2;
+			q = rem + s1 / 2;
+			const long long dj = q >= 0 ? q / s1 : -((-q + s1 - 1) / s1);
+			const long long di = rem - dj * s1;
+			const bool inside = i + di >= 0 && i + di < s1 && j + dj >= 0 && j + dj < my && k + dk >= 0 && k + dk < nz;
+			const double want = inside ? coef[sp + t] : 0.0;
+			if (!(val[(size_t)r * ndp + sp + t] == want)) ++bad;
+		}
+	}
+	if (bad) atomicAdd(count, bad);
+}
+
 // Every run of consecutive offsets must lie on one (dj, dk) line of the lattice: first offset = di0 + dj s1 + dk s2
 // with -1 <= di0 and di0 + w - 1 <= 1, one run per line.  runs[g].rowoff comes back as ((1 + dj) << 8) | (1 + di0);
 // the launch turns it into a row offset once the tile width is known.
@@ -239,7 +280,7 @@ static bool lat_decompose(const b200_mat *A, long long s1, long long s2, LatRun 
 // called once per matrix, after its diagonal image exists (b200_mat.cu); sets A->lat_s1 / lat_s2 (0: not a lattice)
 int b200k_lat_detect(b200_mat *A)
 {
-	A->lat_s1 = 0; A->lat_s2 = 0;
+	A->lat_s1 = 0; A->lat_s2 = 0; A->lat_const = 0;
 	if (A->dia_nd <= 0 || A->nrows <= 0 || b200_opt(B200_OPT_NO_LAT)) return 0;
 	const long long n = A->nrows_global;
 	// the central run must hold offset 0; s1 comes from the first run above it, s2 from the runs beyond
@@ -274,6 +315,30 @@ int b200k_lat_detect(b200_mat *A)
 	// several ranks: slabs must be whole planes, and every rank must see the same lattice
 	if (A->row0 % best2 || A->nrows % best2) return 0;
 	A->lat_s1 = (int)best1; A->lat_s2 = (int)best2;
+	// ---- constant stencil?  take the coefficients of one interior row and compare every row of the slab with
+	// (coefficient where the neighbour is inside the lattice, 0 where it is not)
+	A->lat_const = 0;
+	const int s1 = A->lat_s1, my = A->lat_s2 / A->lat_s1, np = A->nrows / A->lat_s2;
+	const long long nz = n / best2, gk0 = A->row0 / best2;
+	int kk = -1;
+	for (int q = 0; q < np && kk < 0; ++q) if (gk0 + q >= 1 && gk0 + q <= nz - 2) kk = q;
+	if (kk >= 0 && s1 >= 3 && my >= 3 && A->dia_ndp <= 40) {
+		const size_t rstar = (size_t)kk * best2 + (size_t)(my / 2) * s1 + s1 / 2;
+		double *coef_dev = (double *)b200_scratch(3, sizeof(double) * 40 + 64);
+		if (!coef_dev) return 1;
+		int *cnt = (int *)(coef_dev + 40);
+		B200_CUDA(cudaMemcpyAsync(coef_dev, A->dia_val + rstar * A->dia_ndp, sizeof(double) * A->dia_ndp, cudaMemcpyDeviceToDevice, g_b200.stream));
+		B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), g_b200.stream));
+		lat_const_kernel<<<b200_ceil_div(A->nrows, 256), 256, 0, g_b200.stream>>>(
+			A->nrows, A->row0, s1, my, nz, A->dia_ng, A->dia_off, A->dia_grp, A->dia_ndp, A->dia_val, coef_dev, cnt);
+		B200_KERNEL_CHECK();
+		int bad = 1;
+		if (b200k_d2h(&bad, cnt, sizeof(int))) return 1;
+		if (bad == 0) {
+			if (b200k_d2h(A->lat_coef, coef_dev, sizeof(double) * A->dia_ndp)) return 1;
+			A->lat_const = 1;
+		}
+	}
 	return 0;
 }
 
@@ -302,7 +367,7 @@ static int lat_vpitch(int ndp)
 
 // returns 0 launched, 1 error, 2 not applicable; mode 0: all planes, 1: interior planes (no halo plane needed),
 // 2: the boundary planes; *nparts (DOT): per-CTA partial rows written to dot_part
-template <int KP, int NT, bool DOT>
+template <int KP, int NT, bool DOT, bool CONST>
 static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
                            double *dot_part, int dot_cap, int *nparts, int mode)
 {
@@ -328,7 +393,7 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 			// TMA destinations are 128-byte aligned
 			const int pitch = lat_pitch(TI, K);
 			const size_t slice = ((size_t)pitch * (TJ + 2) * K * 8 + 127) & ~(size_t)127;
-			const size_t vb = ((size_t)TI * TJ * lat_vpitch(P.ndp) * 8 + 127) & ~(size_t)127;
+			const size_t vb = CONST ? 0 : (((size_t)TI * TJ * lat_vpitch(P.ndp) * 8 + 127) & ~(size_t)127);
 			for (int NS = 4; NS <= LAT_MAX_NS; ++NS) {
 				if (env_ns && NS != env_ns) continue;
 				const int NV = NS - 2;
@@ -339,8 +404,10 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 				const double busy = (double)rounds * NG / tasks;                           // 1 / (share of groups with a task)
 				// shared-memory wavefronts (128 bytes) per matrix row: sliding x reads, broadcast value reads, TMA writes
 				const double reads = cover * busy * (sum_reads / (double)LAT_RB) * K * 8 / 128.0;
-				const double vals = cover * busy * (P.ng + n3) * KP / 32.0;
-				const double writes = (double)nti * ntj * pitch * (TJ + 2) / ((double)s1 * my) * K * 8 / 128.0 + cover * P.ndp * 8 / 128.0;
+				// (a broadcast LDS.128 costs a wavefront per quarter-warp: 4 per warp instruction, like distinct data)
+				const double vals = CONST ? 0.0 : cover * busy * (4.0 * P.ng + 2.0 * n3) * KP / 32.0;
+				const double writes = (double)nti * ntj * pitch * (TJ + 2) / ((double)s1 * my) * K * 8 / 128.0 +
+				                      (CONST ? 0.0 : cover * P.ndp * 8 / 128.0);
 				// a ring of 4 leaves the copy engine one plane step of lead; 5 and more hide its latency fully
 				const double est = (reads + vals + writes) * (NS >= 5 ? 1.0 : 1.06);
 				if (est < best) { best = est; bTI = TI; bTJ = TJ; bNS = NS; }
@@ -348,12 +415,13 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 		}
 	}
 	if (!bTI) return 2;
-	P.TI = bTI; P.TJ = bTJ; P.NS = bNS; P.NV = bNS - 2;
+	P.TI = bTI; P.TJ = bTJ; P.NS = bNS; P.NV = CONST ? 0 : bNS - 2;
+	if (CONST) for (int i = 0; i < 40; ++i) P.coef[i] = i < M->dia_ndp ? M->lat_coef[i] : 0.0;
 	P.NTI = (s1 + P.TI - 1) / P.TI; P.NTJ = (my + P.TJ - 1) / P.TJ;
 	P.pitch = lat_pitch(P.TI, K);
 	P.slice_bytes = P.pitch * (P.TJ + 2) * K * 8;           // bytes one copy delivers; the ring strides are rounded up
 	P.vpitch = lat_vpitch(P.ndp);
-	P.val_bytes = P.TI * P.TJ * P.vpitch * 8;
+	P.val_bytes = CONST ? 0 : P.TI * P.TJ * P.vpitch * 8;
 	P.slice_stride = (P.slice_bytes + 127) & ~127;
 	P.val_stride = (P.val_bytes + 127) & ~127;
 	for (int g = 0; g < P.ng; ++g) {
@@ -362,8 +430,8 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 	}
 	const size_t smem = (size_t)P.NS * P.slice_stride + (size_t)P.NV * P.val_stride;
 	if (b200_opt(B200_OPT_LAT_VERBOSE))
-		fprintf(stderr, "spmm_lat k=%d dot=%d lattice %d x %d x %d: tile TI=%d TJ=%d pitch=%d ring %d + %d, %zu bytes smem, est %.1f wavefronts/row\n",
-		        K, (int)DOT, s1, my, np, P.TI, P.TJ, P.pitch, P.NS, P.NV, smem, best);
+		fprintf(stderr, "spmm_lat k=%d dot=%d const=%d lattice %d x %d x %d: tile TI=%d TJ=%d pitch=%d ring %d + %d, %zu bytes smem, est %.1f wavefronts/row\n",
+		        K, (int)DOT, (int)CONST, s1, my, np, P.TI, P.TJ, P.pitch, P.NS, P.NV, smem, best);
 	// ---- tensor maps: x as (K, s1, my, planes) with a halo plane in front / behind where a slab neighbour exists
 	tmap_encode_fn enc = tmap_encoder();
 	if (!enc) return 2;
@@ -382,7 +450,8 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 		        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
 			return 2;
 	}
-	{
+	if (CONST) tmv = tmx;                                // never used
+	else {
 		const cuuint64_t gdim[4] = {(cuuint64_t)P.ndp, (cuuint64_t)s1, (cuuint64_t)my, (cuuint64_t)np};
 		const cuuint64_t gstr[3] = {(cuuint64_t)P.ndp * 8, (cuuint64_t)P.ndp * 8 * s1, (cuuint64_t)P.ndp * 8 * s2};
 		// the box is wider than the image (vpitch >= ndp): the copy engine zero-fills the padding slots
@@ -394,7 +463,7 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 	}
 	static bool attr_set = false;
 	if (!attr_set) {
-		B200_CUDA(cudaFuncSetAttribute(spmm_lat_kernel<KP, NT, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+		B200_CUDA(cudaFuncSetAttribute(spmm_lat_kernel<KP, NT, DOT, CONST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
 		attr_set = true;
 	}
 	// ---- plane ranges: all, interior (planes whose k - 1 and k + 1 are local) or the two boundary planes
@@ -429,7 +498,7 @@ static int launch_spmm_lat(const b200_mat *M, const double *x, int ldx, double *
 			dp = dot_part + (size_t)used * K;
 			used += grid;
 		}
-		spmm_lat_kernel<KP, NT, DOT><<<grid, NT + 32, smem, g_b200.stream>>>(tmx, tmv, P, y, ldy, gate, dp);
+		spmm_lat_kernel<KP, NT, DOT, CONST><<<grid, NT + 32, smem, g_b200.stream>>>(tmx, tmv, P, y, ldy, gate, dp);
 		B200_KERNEL_CHECK();
 	}
 	if (DOT) *nparts = used;
@@ -440,8 +509,11 @@ template <int KP>
 static int launch_spmm_lat_kp(const b200_mat *M, const double *x, int ldx, double *y, int ldy, const int *gate,
                               double *dot_part, int dot_cap, int *nparts, int mode)
 {
-	if (dot_part) return launch_spmm_lat<KP, 480, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
-	return launch_spmm_lat<KP, 480, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
+	const bool cst = M->lat_const && M->dia_ndp <= 40 && !b200_opt(B200_OPT_LAT_NO_CONST);
+	if (dot_part && cst) return launch_spmm_lat<KP, 480, true, true>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
+	if (dot_part) return launch_spmm_lat<KP, 480, true, false>(M, x, ldx, y, ldy, gate, dot_part, dot_cap, nparts, mode);
+	if (cst) return launch_spmm_lat<KP, 480, false, true>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
+	return launch_spmm_lat<KP, 480, false, false>(M, x, ldx, y, ldy, gate, nullptr, 0, nullptr, mode);
 }
 
 // the block widths with a compile-time kernel (those of the 1-D warp-specialised kernel)

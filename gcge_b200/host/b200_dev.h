@@ -64,6 +64,10 @@ struct b200_mat_ {
 	 * (lat_s2 / lat_s1) k), every entry couples lattice neighbours (|di|, |dj|, |dk| <= 1), nothing crosses a
 	 * lattice face, slabs are whole planes.  0: not a lattice (the 1-D diagonal kernel or the CSR kernels run). */
 	int lat_s1, lat_s2;
+	/* ... and, when every row carries the same coefficients (a constant stencil: entries exist exactly where the
+	 * neighbour is inside the lattice), those coefficients by value slot: the lattice kernel then loads no values */
+	int lat_const;
+	double lat_coef[40];
 };
 
 /* host-side partition plan, usable without a device (tests): fills a zeroed b200_mat with

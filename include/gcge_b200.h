@@ -145,8 +145,9 @@ int b200_mat_local_csr(const b200_mat *A, int *rp, int *ci, double *va);
  * reference src/ops.h:52, used for the in-place shift A + sigma B, src/ops_eig_sol_gcg.c:594-602 */
 int b200_mat_axpby(double alpha, const b200_mat *X, double beta, b200_mat *Y);
 /* which SpMM storage the matrix got (diagnosis / tests): number of diagonals of its diagonal image (0: CSR
- * kernels only) and the lattice strides recognised in it (0, 0: none; else row = i + s1 (j + (s2/s1) k)) */
-int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2);
+ * kernels only), the lattice strides recognised in it (0, 0: none; else row = i + s1 (j + (s2/s1) k)), and whether
+ * it is a constant stencil on that lattice (the same coefficients in every row: no matrix values are streamed) */
+int b200_mat_storage(const b200_mat *A, int *dia_nd, int *lat_s1, int *lat_s2, int *lat_const);
 
 /* ---- multi-vector life cycle: reference app/app_ccs.c:40-49 (MultiVecCreateByMat),
  *      app/app_lapack.c:230-286 (create/destroy) ------------------------------ */

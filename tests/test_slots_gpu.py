@@ -305,6 +305,65 @@ def test_matrix_from_local_rows_matches_whole_ccs(b200, name, m):
     assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"], o2["eval"])
 
 
+@pytest.mark.parametrize("name,m", [("p1_fem_kuhn", 11), ("q1_27pt", 9), ("laplace3d_7pt", 12)])
+def test_spmm_constant_stencil_path(b200, name, m):
+    """Constant stencils (every row the same coefficients, entries exactly where the neighbour is inside the lattice:
+    all of BASELINE's lattice pencils) are recognised and multiplied WITHOUT streaming matrix values; the result is
+    bit-identical to the general lattice kernel (option lat_no_const) and to the reference's CCS scatter.  One
+    perturbed entry makes the matrix non-constant: the general kernel takes over, still exact."""
+    import ctypes as C
+    from gcge_b200 import api
+    L = b200.lib()
+    pen = getattr(P, name)(m)
+    n = pen.A.ncols
+    for M in (pen.A, pen.B):
+        if M is None:
+            continue
+        A = b200.Mat(M)
+        assert A.storage()["lat_const"] == 1 and A.storage()["lat_s1"] == m
+        for k in (10, 40):
+            x = np.asfortranarray(np.random.default_rng(k).standard_normal((n, k)))
+            X = b200.MultiVec.from_numpy(x); Y1 = b200.MultiVec(n, k); Y2 = b200.MultiVec(n, k)
+            api.mat_dot_multivec(A, X, Y1, (0, 0), (k, k))
+            try:
+                L.b200_option_set(b"lat_no_const", 1)
+                api.mat_dot_multivec(A, X, Y2, (0, 0), (k, k))
+            finally:
+                L.b200_option_set(b"lat_no_const", 0)
+            want = oracle_spmm(M, x)
+            assert np.array_equal(Y1.numpy(), want) and np.array_equal(Y2.numpy(), want)
+    data = pen.A.data.copy(); data[len(data) // 2] *= 1.0 + 2.0 ** -40
+    Mp = P.CCS(pen.A.nrows, pen.A.ncols, pen.A.j_col, pen.A.i_row, data)
+    Ap = b200.Mat(Mp)
+    assert Ap.storage()["lat_const"] == 0 and Ap.storage()["lat_s1"] == m
+    x = np.asfortranarray(np.random.default_rng(5).standard_normal((n, 16)))
+    Y = b200.MultiVec(n, 16)
+    api.mat_dot_multivec(Ap, b200.MultiVec.from_numpy(x), Y, (0, 0), (16, 16))
+    assert np.array_equal(Y.numpy(), oracle_spmm(Mp, x))
+
+
+def test_mat_axpby_keeps_the_stencil_flags_right(b200):
+    """A + sigma B of two constant stencils is one again (the in-place shift of the inner solve); adding a diagonal
+    with varying entries ends it -- the flag follows the values."""
+    import scipy.sparse as sp
+    from gcge_b200 import api
+    pen = P.p1_fem_kuhn(9)
+    n = pen.A.ncols
+    Y = b200.Mat(pen.A); X = b200.Mat(pen.B)
+    Y.axpby(2.5, X, 1.0)
+    assert Y.storage()["lat_const"] == 1
+    x = np.asfortranarray(np.random.default_rng(2).standard_normal((n, 10)))
+    Xv = b200.MultiVec.from_numpy(x); Yv = b200.MultiVec(n, 10)
+    api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
+    want = (pen.A.to_scipy() + 2.5 * pen.B.to_scipy()) @ x
+    assert rel(Yv.numpy(), want) < 1e-14
+    D = _ccs_from_scipy(sp.diags(np.linspace(1.0, 2.0, n)))
+    Y.axpby(1.0, b200.Mat(D), 1.0)
+    assert Y.storage()["lat_const"] == 0
+    api.mat_dot_multivec(Y, Xv, Yv, (0, 0), (10, 10))
+    assert rel(Yv.numpy(), want + np.linspace(1.0, 2.0, n)[:, None] * x) < 1e-14
+
+
 def test_spmm_lattice_recognition_rejects_wrap_around(b200):
     """A periodic operator has the same diagonals (plus the wrap diagonals) but couples across the lattice faces:
     it must NOT be taken for a Dirichlet lattice (the tiles would read zero-filled rows outside the lattice),
