@@ -97,13 +97,19 @@ extern "C" int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_
 	return 0;
 }
 
-// *out = max |v[i]|, i < count (a coefficient block of the orthogonalisation: at most a few 10^4 entries): one CTA
+// *out = max over a row-major rows x cols coefficient block of |c[i][j]| * scale[j] (scale == nullptr: 1): one CTA.
+// scale[j] is the norm column j had in the caller's scaling before the panels normalised it (chol_drop_kernel's
+// scale_out), so the value is the coefficient the reference would have seen on its never-normalised column.
 __global__ void __launch_bounds__(256)
-absmax_kernel(long long count, const double *__restrict__ v, double *out)
+absmax_kernel(int rows, int cols, const double *__restrict__ c, const double *__restrict__ scale, double *out)
 {
 	__shared__ double red[256];
 	double m = 0.0;
-	for (long long i = threadIdx.x; i < count; i += 256) m = fmax(m, fabs(v[i]));
+	const long long count = (long long)rows * cols;
+	for (long long i = threadIdx.x; i < count; i += 256) {
+		const double v = fabs(c[i]);
+		m = fmax(m, scale ? v * scale[i % cols] : v);
+	}
 	red[threadIdx.x] = m;
 	__syncthreads();
 	for (int s = 128; s > 0; s >>= 1) {
@@ -113,9 +119,9 @@ absmax_kernel(long long count, const double *__restrict__ v, double *out)
 	if (threadIdx.x == 0) *out = red[0];
 }
 
-extern "C" int b200k_absmax(long long count, const double *v_dev, double *out_dev)
+extern "C" int b200k_absmax(int rows, int cols, const double *c_dev, const double *scale_dev, double *out_dev)
 {
-	absmax_kernel<<<1, 256, 0, g_b200.stream>>>(count, v_dev, out_dev);
+	absmax_kernel<<<1, 256, 0, g_b200.stream>>>(rows, cols, c_dev, scale_dev, out_dev);
 	B200_KERNEL_CHECK();
 	return 0;
 }

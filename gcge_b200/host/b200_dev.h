@@ -95,6 +95,7 @@ int  b200k_num_sms(void);
 /* cached run-time switch (b200_runtime.cu; ids of b200_internal.h) for the host-side C drivers */
 int  b200k_opt(int id);
 #define B200K_OPT_BPCG_TRACE 10
+#define B200K_OPT_ORTH_TRACE 20
 
 /* synchronising small transfers */
 int b200k_d2h(void *host, const void *dev, size_t bytes);
@@ -148,8 +149,8 @@ int b200k_chol_drop(int k, double *g_dev, double zero_tol, double *t_dev, int *n
 
 /* t (n x (n - lin_dep), row-major) = z[:, lin_dep:n] diag(w[lin_dep:n])^(-1/2): the update block of OrthSelfEVP */
 int b200k_evp_coef(int n, int lin_dep, const double *w_dev, const double *z_dev, double *t_dev);
-/* *out_dev = max |v_dev[i]| over a small coefficient block (one CTA) */
-int b200k_absmax(long long count, const double *v_dev, double *out_dev);
+/* *out_dev = max |c[i][j]| * scale[j] over a row-major rows x cols coefficient block (scale NULL: 1); one CTA */
+int b200k_absmax(int rows, int cols, const double *c_dev, const double *scale_dev, double *out_dev);
 
 /* ---- BlockPCG (b200_bpcg.cu): device-resident scalars and masks ----------------------- */
 typedef struct b200_bpcg_state_ {

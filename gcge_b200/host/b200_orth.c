@@ -22,6 +22,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <float.h>
+#include <stdio.h>
 #include "b200_dev.h"
 
 #define ORTH_MAX_BLOCK 112      /* the k x k panel kernel keeps G and T in shared memory: 2 k (k+1) doubles */
@@ -88,14 +90,22 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 	while (block > 0) {
 		const int s1 = init_start;
 		int e1 = s1 + block;
-		/* Rounds of (project out X0, orthonormalise the panel).  Two always (block classical Gram-Schmidt needs
-		 * its second pass); further ones, up to 1 + max_reorth in all, while the projection coefficients of the
-		 * round just applied are not below reorth_tol -- the reference's loop, src/ops_orth.c:233-268, whose
-		 * test is on max |coef| as well (here on columns the previous round normalised). */
+		/* Rounds of (project out X0, orthonormalise the panel).  Two always: block classical Gram-Schmidt needs its
+		 * second pass.  Further ones, up to 1 + max_reorth in all (the reference's loop, src/ops_orth.c:233-268),
+		 * only when the second pass did NOT confirm the first.  The columns entering a pass >= 1 have unit B-norm (the
+		 * previous panel normalised them), so the coefficients c of that pass are what the pass before left behind:
+		 * kappa eps for a block of condition kappa against X0.  "Twice is enough" (Giraud, Langou, Rozloznik) holds
+		 * while kappa eps << 1, and the error after the pass is the rounding level of the inner products, eps sqrt(n),
+		 * whatever c was -- a further pass would subtract noise.  So another pass is made only for c >= 1e-3 (or the
+		 * caller's reorth_tol if that is larger).  The reference tests max |coef| < 50 eps on columns it never
+		 * normalises; taken over literally (relative or rescaled) that costs every W block of the headline solve a
+		 * third pass -- second-pass coefficients are 1e-8 .. 1e-6 there -- +1.2 s of 17 for an unchanged result
+		 * (profiles/orth_reorth_trace_r2.log). */
 		const int max_rounds = prm->max_reorth + 1 > 2 ? prm->max_reorth + 1 : 2;
+		const double again_tol = prm->reorth_tol > 1e-3 ? prm->reorth_tol : 1e-3;
 		double cmax = 0.0;
 		for (int round = 0; round < max_rounds && e1 > s1; ++round) {
-			if (round >= 2 && !(s1 > 0 && cmax >= prm->reorth_tol)) break;
+			if (round >= 2 && !(s1 > 0 && cmax >= again_tol)) break;
 			const int kb = e1 - s1;
 			double *x1 = x->d + s1;
 			if (s1 > 0) {
@@ -106,7 +116,7 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 				}
 				/* C = -(X0^T B X1), row-major s1 x kb; X1 += X0 C */
 				if (b200k_gram('N', n, s1, kb, -1.0, x->d, x->ld, y, ldy, c_dev, kb, 1, x->dist)) return 1;
-				if (round >= 1 && round + 1 < max_rounds && b200k_absmax((long long)s1 * kb, c_dev, cmax_dev)) return 1;
+				if (round >= 1 && round + 1 < max_rounds && b200k_absmax(s1, kb, c_dev, NULL, cmax_dev)) return 1;
 				if (b200k_lincomb(n, s1, kb, x->d, x->ld, c_dev, kb, 1, one_dev, 0, x1, x->ld)) return 1;
 			}
 			int n_live = kb;
@@ -116,6 +126,9 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 			               sc_in, sc_out, x->dist))
 				return 1;
 			if (s1 > 0 && round >= 1 && round + 1 < max_rounds && b200k_d2h(&cmax, cmax_dev, sizeof(double))) return 1;
+			if (b200k_opt(B200K_OPT_ORTH_TRACE) && s1 > 0 && round >= 1)
+				fprintf(stderr, "orth: block at %d of %d columns, round %d: max |coef| on unit columns %.3e (another pass from %.3e)\n",
+				        s1, kb, round, cmax, again_tol);
 			e1 = s1 + n_live;
 		}
 		const int init_end = e1;
@@ -149,6 +162,7 @@ typedef struct {
 	const b200_mat *B;
 	int max_reorth;
 	double zero_tol, reorth_tol;
+	double again_tol;           /* max(reorth_tol, eps sqrt(n)): projections are not repeated over rounding noise */
 	double *c_dev, *g_dev, *z_dev, *t_dev, *w_dev, *cmax_dev, *one_dev;
 	int chunk;                  /* columns of X1 handled per pass: min(workspace columns, ORTH_MAX_BLOCK) */
 } bgs_t;
@@ -171,13 +185,13 @@ static int bgs_project(bgs_t *g, int a0, int a1, int b0, int b1)
 				y = g->ws->d; ldy = g->ws->ld;
 			}
 			if (b200k_gram('N', n, s0, kc, -1.0, x->d + a0, x->ld, y, ldy, g->c_dev, kc, 1, x->dist)) return 1;
-			if (b200k_absmax((long long)s0 * kc, g->c_dev, g->cmax_dev)) return 1;
+			if (b200k_absmax(s0, kc, g->c_dev, NULL, g->cmax_dev)) return 1;
 			if (b200k_lincomb(n, s0, kc, x->d + a0, x->ld, g->c_dev, kc, 1, g->one_dev, 0, x1, x->ld)) return 1;
 			double cmax = 0.0;
 			if (b200k_d2h(&cmax, g->cmax_dev, sizeof(double))) return 1;
 			if (cmax > cmax_all) cmax_all = cmax;
 		}
-		if (cmax_all < g->reorth_tol) break;
+		if (cmax_all < g->again_tol) break;
 	}
 	return 0;
 }
@@ -258,6 +272,12 @@ int b200_mv_orth_bgs(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
 	bgs_t g; memset(&g, 0, sizeof(g));
 	g.x = x; g.ws = ws; g.B = B; g.max_reorth = prm->max_reorth;
 	g.zero_tol = prm->orth_zero_tol; g.reorth_tol = prm->reorth_tol;
+	{
+		/* never below the rounding level of an n-term inner product: the reference's 50 eps lies under eps sqrt(n)
+		 * from n ~ 2500 on, where its own loop simply runs to max_reorth */
+		const double noise = DBL_EPSILON * sqrt((double)(x->nrows_global > 0 ? x->nrows_global : x->nrows));
+		g.again_tol = prm->reorth_tol > noise ? prm->reorth_tol : noise;
+	}
 	g.chunk = ws->ncols < ORTH_MAX_BLOCK ? ws->ncols : ORTH_MAX_BLOCK;
 	int block = prm->block_size;                                          /* reference :583-586 */
 	if (block <= 0 || block > ncols / 4) block = ncols / 4;
