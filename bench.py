@@ -576,7 +576,9 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="p1_fem", choices=sorted(WORKLOADS),
                     help="p1_fem: BASELINE config 3 (default); laplace7: config 2; q1_27pt: config 4's operator")
-    ap.add_argument("--m", type=int, default=200, help="lattice size: n = m^3 unknowns (200 -> 8.0 M)")
+    ap.add_argument("--m", "--lattice", dest="m", type=int, default=200,
+                    help="lattice size: n = m^3 unknowns (200 -> 8.0 M); under torchrun write --lattice (torchrun's own parser "
+                         "takes --m for an abbreviation of its options)")
     ap.add_argument("--nev", type=int, default=200)
     ap.add_argument("--max-iter", type=int, default=0, help="cap on outer iterations (0 = reference default 500)")
     ap.add_argument("--e2e-steps", type=int, default=1)
