@@ -104,6 +104,7 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 	const int c = 2 * gl;
 	const int CH = P.TI / RB, ntasks = P.TJ * CH;      // tasks of one plane step: (line, chunk of RB rows)
 	const int pitch = P.pitch;                         // rows per line of a slice
+	const int ch_first = (live ? group : 0) / P.TJ;
 	double dot[2] = {0.0, 0.0};
 	int slot = 0, vslot = 0; unsigned phase = 0, vphase = 0;
 	int ring0 = 0, ring1 = 0, ring2 = 0;               // slots of the three most recent slices: planes k-1, k, k+1
@@ -124,7 +125,9 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 				for (int task = group; task < ntasks; task += NG) {
 					// neighbouring row groups take neighbouring LINES: their x rows are `pitch` rows apart, and with an
 					// odd pitch the 16-byte pieces two groups read in one quarter-warp never meet in a bank
-					const int ch = task / P.TJ, jj = task - ch * P.TJ, ii0 = ch * RB;
+					// (the group's first task -- usually its only one per plane step -- was decoded once, up front)
+					const int ch = (task == group) ? ch_first : task / P.TJ;
+					const int jj = task - ch * P.TJ, ii0 = ch * RB;
 					double acc[RB][2];
 					double2 pst[RB][1];
 #pragma unroll
@@ -136,16 +139,29 @@ spmm_lat_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 						const int sl = r.dk == 0 ? ring0 : (r.dk == 1 ? ring1 : ring2);
 						const double *tile = reinterpret_cast<const double *>(smem_raw + (size_t)sl * P.slice_stride) +
 						                     (rbase + r.rowoff) * K + c;
-						const int zrow = (DOT && g == P.zero_run) ? P.zero_pos : -1;
-						if (CONST) {
+						// the run that holds offset 0 also keeps the block's own x rows for the fused dot; every other run goes
+						// through the instantiation WITHOUT that code (if-converted selects would otherwise issue in all of them:
+						// ncu showed as many IMAD.MOV as DADD per task)
+						if (DOT && g == P.zero_run) {
+							const int zrow = P.zero_pos;
+							if (CONST) {
+								const double a0 = P.coef[r.sp], a1 = P.coef[r.sp + 1], a2 = P.coef[r.sp + 2];
+								if (r.w == 2)      dia_run_const<RB, 2, K, KP, true>(acc, tile, a0, a1, a2, pst, zrow);
+								else if (r.w == 3) dia_run_const<RB, 3, K, KP, true>(acc, tile, a0, a1, a2, pst, zrow);
+								else               dia_run_const<RB, 1, K, KP, true>(acc, tile, a0, a1, a2, pst, zrow);
+							}
+							else if (r.w == 2) dia_run_ct<RB, 2, K, KP, 1, true>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
+							else if (r.w == 3) dia_run_ct<RB, 3, K, KP, 1, true>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
+							else               dia_run_ct<RB, 1, K, KP, 1, true>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
+						} else if (CONST) {
 							const double a0 = P.coef[r.sp], a1 = P.coef[r.sp + 1], a2 = P.coef[r.sp + 2];
-							if (r.w == 2)      dia_run_const<RB, 2, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
-							else if (r.w == 3) dia_run_const<RB, 3, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
-							else               dia_run_const<RB, 1, K, KP, DOT>(acc, tile, a0, a1, a2, pst, zrow);
+							if (r.w == 2)      dia_run_const<RB, 2, K, KP, false>(acc, tile, a0, a1, a2, pst, -1);
+							else if (r.w == 3) dia_run_const<RB, 3, K, KP, false>(acc, tile, a0, a1, a2, pst, -1);
+							else               dia_run_const<RB, 1, K, KP, false>(acc, tile, a0, a1, a2, pst, -1);
 						}
-						else if (r.w == 2) dia_run_ct<RB, 2, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
-						else if (r.w == 3) dia_run_ct<RB, 3, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
-						else               dia_run_ct<RB, 1, K, KP, 1, DOT>(acc, tile, vrow + r.sp, P.vpitch, pst, zrow);
+						else if (r.w == 2) dia_run_ct<RB, 2, K, KP, 1, false>(acc, tile, vrow + r.sp, P.vpitch, pst, -1);
+						else if (r.w == 3) dia_run_ct<RB, 3, K, KP, 1, false>(acc, tile, vrow + r.sp, P.vpitch, pst, -1);
+						else               dia_run_ct<RB, 1, K, KP, 1, false>(acc, tile, vrow + r.sp, P.vpitch, pst, -1);
 					}
 					const int j = J0 + jj;
 					if (j < P.my) {
