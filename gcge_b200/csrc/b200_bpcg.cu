@@ -393,7 +393,9 @@ extern "C" int b200k_bpcg_spmm_ptw(const b200_mat *A, long long n, const b200_bp
 		return b200k_bpcg_ptw(n, st, p, ldp, w, ldw, 0.0, nullptr, 0);
 	}
 	{
-		B200Prof prof(B200_PROF_BPCG, 8.0 * nparts * k, 1.0 * nparts * k);
+		// booked with the small dense work: a one-CTA reduction of nparts x k partials -- counting it as a launch of
+		// the streaming class would halve that class's algorithmic bytes per launch for no traffic of its own
+		B200Prof prof(B200_PROF_SMALL, 8.0 * nparts * k, 1.0 * nparts * k);
 		bpcg_ptw_parts_kernel<<<1, ST_THREADS, 0, g_b200.stream>>>(nparts, k, defer, *st, ar);
 		B200_KERNEL_CHECK();
 	}
