@@ -220,6 +220,8 @@ extern "C" int b200_plan_destroy(b200_plan *p)
 // rp/ci/va: the local CSR slab with REMAPPED columns (see b200_partition_build).
 int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_row, const double *data, int rank,
                            int nranks, b200_mat *A);
+int b200k_local_rows_finish(b200_mat *A, int rp0, int *bad);
+int b200k_dia_build_device(b200_mat *A);
 void b200_note_halo_capacity(long long n_global, int nhalo);
 
 static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va, int nranks)
@@ -404,23 +406,23 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 	           rank, lo, hi, row0, row0 + nrows_local);
 	const int nloc = nrows_local, nnz = rp_in[nloc] - rp_in[0];
 	B200_CHECK(nnz >= 0 && (nnz == 0 || (ci_in && va_in)), "b200_mat_create_from_local_rows: bad arrays");
+	// column extent of the slab from the first / last entry of every row (columns ascend inside a row; the device
+	// checks that, and everything else about the arrays, once they are uploaded)
 	long long cmin = lo, cmax = hi - 1;
-	int max_row = 0;
 	for (int r = 0; r < nloc; ++r) {
 		const int e0 = rp_in[r] - rp_in[0], e1 = rp_in[r + 1] - rp_in[0];
-		B200_CHECK(e1 >= e0, "b200_mat_create_from_local_rows: row pointers not monotone at row %d", r);
-		if (e1 - e0 > max_row) max_row = e1 - e0;
-		for (int e = e0; e < e1; ++e) {
-			const int c = ci_in[e];
-			B200_CHECK(c >= 0 && c < nrows_global && (e == e0 || c > ci_in[e - 1]),
-			           "b200_mat_create_from_local_rows: columns of row %d not ascending / out of range", row0 + r);
+		B200_CHECK(e0 >= 0 && e1 >= e0 && e1 <= nnz, "b200_mat_create_from_local_rows: row pointers not monotone at row %d", r);
+		if (e1 > e0) {
+			const int *cr = ci_in + rp_in[0];
+			if (cr[e0] < cmin) cmin = cr[e0];
+			if (cr[e1 - 1] > cmax) cmax = cr[e1 - 1];
 		}
-		if (e1 > e0) { if (ci_in[e0] < cmin) cmin = ci_in[e0]; if (ci_in[e1 - 1] > cmax) cmax = ci_in[e1 - 1]; }
 	}
+	B200_CHECK(cmin >= 0 && cmax < nrows_global, "b200_mat_create_from_local_rows: column index out of range");
 	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
 	A->nrows = nloc; A->ncols = (nranks == 1) ? nrows_global : nloc; A->nnz = nnz;
 	A->nrows_global = nrows_global; A->ncols_global = nrows_global; A->row0 = (int)lo; A->t_col0 = lo;
-	A->max_row_nnz = max_row; A->t_max_row_nnz = max_row; A->symmetric = 1;
+	A->symmetric = 1;
 	std::vector<long long> ext_min((size_t)nranks, 0), ext_max((size_t)nranks, 0), rlo((size_t)nranks), rhi((size_t)nranks);
 	long long nnz_global = nnz;
 	if (nranks > 1) {
@@ -486,19 +488,16 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 	}
 	B200_CHECK(nnz_global < 0x7fffffffLL, "b200_mat_create_from_local_rows: %lld entries in all (32-bit counts)", nnz_global);
 	A->nnz_global = (int)nnz_global;
-	// local CSR with remapped columns (global - row0; halo rows in front of / behind the local ones)
-	std::vector<int> rp((size_t)nloc + 1), ci((size_t)(nnz > 0 ? nnz : 1));
-	for (int r = 0; r <= nloc; ++r) rp[r] = rp_in[r] - rp_in[0];
-	for (int e = 0; e < nnz; ++e) ci[e] = ci_in[rp_in[0] + e] - (int)lo;
-	const double *va = va_in + rp_in[0];
+	// the caller's arrays go to the device as they are; kernels validate them and turn them into the local CSR
+	// (row pointers from 0, columns minus row0: halo rows in front of / behind the local ones)
 	cudaStream_t st = g_b200.stream;
 	const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
 	B200_CUDA(cudaMalloc(&A->rp, sizeof(int) * ((size_t)nloc + 1)));
 	B200_CUDA(cudaMalloc(&A->ci, sizeof(int) * nz));
 	B200_CUDA(cudaMalloc(&A->va, sizeof(double) * nz));
-	B200_CUDA(cudaMemcpyAsync(A->rp, rp.data(), sizeof(int) * ((size_t)nloc + 1), cudaMemcpyHostToDevice, st));
-	B200_CUDA(cudaMemcpyAsync(A->ci, ci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-	B200_CUDA(cudaMemcpyAsync(A->va, va, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->rp, rp_in, sizeof(int) * ((size_t)nloc + 1), cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->ci, ci_in + rp_in[0], sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->va, va_in + rp_in[0], sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
 	if (nranks == 1) { A->t_rp = A->rp; A->t_ci = A->ci; A->t_va = A->va; A->t_shared = 1; }   // symmetric by contract
 	if (nranks > 1) {
 		const int ns = A->send_off[A->nnbr];
@@ -506,8 +505,13 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 		B200_CUDA(cudaMemcpyAsync(A->send_rows_dev, A->send_rows, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
 		b200_note_halo_capacity(A->ncols_global, A->nhalo);
 	}
-	B200_CUDA(cudaStreamSynchronize(st));
-	if (dia_build(A, rp.data(), ci.data(), va, nranks) || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
+	int bad = 0;
+	if (b200k_local_rows_finish(A, rp_in[0], &bad)) { b200_mat_destroy(A); return 1; }
+	if (bad) {
+		b200_mat_destroy(A);
+		return b200_fail("b200_mat_create_from_local_rows: columns of some row not ascending / out of range, or row pointers not monotone");
+	}
+	if (b200k_dia_build_device(A) || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
 	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }
 	*out = A;
 	return 0;

@@ -194,9 +194,125 @@ int grid_for(long long items)
 	return (int)g;
 }
 
+// The image itself, from the table of distinct offsets mb_offsets_kernel filled (read back as table_h) and the
+// local CSR in A->rp / ci / va: runs of at most 3 consecutive offsets, every run on an even slot.  Leaves
+// A->dia_nd == 0 when the matrix does not qualify (too many or too sparsely filled diagonals, duplicate entries).
+int dia_image_from_table(b200_mat *A, const std::vector<long long> &table_h, Temps &tmp, DevFlags *fl)
+{
+	cudaStream_t st = g_b200.stream;
+	const int nloc = A->nrows;
+	std::vector<long long> offs;
+	for (long long d : table_h) if (d != MB_EMPTY) offs.push_back(d);
+	std::sort(offs.begin(), offs.end());
+	const int nd = (int)offs.size();
+	if (nd < 1 || nd > 32 || (double)A->nnz < 0.45 * (double)nd * nloc) return 0;
+	for (long long d : offs) if (d > 0x3fffffff || d < -0x3fffffff) return 0;
+	int ng = 0, ndp = 0;
+	std::vector<int> slot_of((size_t)nd), offs_i((size_t)nd);
+	for (int s0 = 0; s0 < nd;) {
+		int w = 1;
+		while (w < 3 && s0 + w < nd && offs[s0 + w] == offs[s0] + w) ++w;
+		A->dia_grp_h[2 * ng] = ndp; A->dia_grp_h[2 * ng + 1] = w;
+		A->dia_off_h[ng] = (int)offs[s0];
+		for (int j = 0; j < w; ++j) slot_of[s0 + j] = ndp + j;
+		ndp += (w + 1) & ~1; ++ng; s0 += w;
+	}
+	for (int i = 0; i < nd; ++i) offs_i[i] = (int)offs[i];
+	const size_t npad = (((size_t)nloc + B200_DIA_PAD - 1) / B200_DIA_PAD) * B200_DIA_PAD + B200_DIA_PAD;
+	int *offs_d = tmp.get<int>(64), *slot_d = offs_d ? offs_d + 32 : nullptr;
+	double *val = nullptr;
+	if (!offs_d || cudaMalloc(&val, sizeof(double) * npad * ndp) != cudaSuccess) { cudaGetLastError(); return 0; }
+	B200_CUDA(cudaMemcpyAsync(offs_d, offs_i.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(slot_d, slot_of.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * npad * ndp, st));
+	mb_dia_fill_kernel<<<grid_for(nloc), 256, 0, st>>>(nloc, A->rp, A->ci, A->va, nd, offs_d, slot_d, ndp, val, fl);
+	B200_KERNEL_CHECK();
+	DevFlags fh;
+	B200_CUDA(cudaMemcpyAsync(&fh, fl, sizeof(DevFlags), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	if (fh.duplicate || fh.too_many_offsets) { cudaFree(val); return 0; }      // keep the CSR semantics
+	B200_CUDA(cudaMalloc(&A->dia_off, sizeof(int) * 32));
+	B200_CUDA(cudaMalloc(&A->dia_grp, sizeof(int) * 64));
+	B200_CUDA(cudaMemcpyAsync(A->dia_off, A->dia_off_h, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemcpyAsync(A->dia_grp, A->dia_grp_h, sizeof(int) * 2 * ng, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	A->dia_val = val; A->dia_ndp = ndp; A->dia_nd = nd; A->dia_ng = ng;
+	return 0;
+}
+
 }  // namespace
 
 void b200_note_halo_capacity(long long n_global, int nhalo);
+
+// ---- slab-local input (b200_mat_create_from_local_rows): the caller's arrays are uploaded as they are; these
+// kernels check them (row pointers monotone, columns ascending and in range), record the longest row and turn them
+// into the local CSR (row pointers from 0, columns minus the slab's first row)
+__global__ void mb_local_rows_kernel(int nloc, int nrows_global, long long lo, int rp0, int *__restrict__ rp, int *__restrict__ ci,
+                                     DevFlags *fl)
+{
+	for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += (long long)gridDim.x * blockDim.x) {
+		const int e0 = rp[r] - rp0, e1 = rp[r + 1] - rp0;
+		if (e1 < e0) { fl->bad_input = 1; continue; }
+		atomicMax(&fl->max_row_nnz, e1 - e0);
+		int prev = -1;
+		for (int e = e0; e < e1; ++e) {
+			const int c = ci[e];
+			if (c < 0 || c >= nrows_global || c <= prev) fl->bad_input = 1;
+			prev = c;
+			ci[e] = c - (int)lo;
+		}
+	}
+}
+__global__ void mb_shift_rp_kernel(int count, int rp0, int *rp)
+{
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) rp[i] -= rp0;
+}
+
+// A->rp / ci / va are already the slab's device arrays (A->nrows, nnz set); on return bad != 0 if the input was malformed
+int b200k_local_rows_finish(b200_mat *A, int rp0, int *bad)
+{
+	cudaStream_t st = g_b200.stream;
+	Temps tmp;
+	DevFlags *fl = tmp.get<DevFlags>(1);
+	if (!fl) return b200_fail("b200_mat_create_from_local_rows: out of device memory");
+	B200_CUDA(cudaMemsetAsync(fl, 0, sizeof(DevFlags), st));
+	mb_local_rows_kernel<<<grid_for(A->nrows), 256, 0, st>>>(A->nrows, A->nrows_global, (long long)A->row0, rp0, A->rp, A->ci, fl);
+	B200_KERNEL_CHECK();
+	mb_shift_rp_kernel<<<grid_for(A->nrows + 1), 256, 0, st>>>(A->nrows + 1, rp0, A->rp);
+	B200_KERNEL_CHECK();
+	DevFlags fh;
+	B200_CUDA(cudaMemcpyAsync(&fh, fl, sizeof(DevFlags), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	*bad = fh.bad_input;
+	A->max_row_nnz = fh.max_row_nnz; A->t_max_row_nnz = fh.max_row_nnz;
+	return 0;
+}
+
+// The diagonal image of a matrix whose local CSR is on the device (the rules of dia_build in b200_mat.cu); leaves
+// A->dia_nd == 0 when the matrix does not qualify.
+int b200k_dia_build_device(b200_mat *A)
+{
+	A->dia_nd = 0;
+	if (A->nrows <= 0 || A->nnz <= 0 || b200_opt(B200_OPT_NO_DIA)) return 0;
+	cudaStream_t st = g_b200.stream;
+	const int nloc = A->nrows;
+	Temps tmp;
+	long long *table = tmp.get<long long>(MB_TABLE);
+	DevFlags *fl = tmp.get<DevFlags>(1);
+	if (!table || !fl) return 0;
+	std::vector<long long> table_h(MB_TABLE, MB_EMPTY);
+	B200_CUDA(cudaMemcpyAsync(table, table_h.data(), sizeof(long long) * MB_TABLE, cudaMemcpyHostToDevice, st));
+	B200_CUDA(cudaMemsetAsync(fl, 0, sizeof(DevFlags), st));
+	mb_offsets_kernel<<<grid_for(nloc), 256, 0, st>>>(nloc, A->rp, A->ci, table, fl);
+	B200_KERNEL_CHECK();
+	DevFlags fh;
+	B200_CUDA(cudaMemcpyAsync(&fh, fl, sizeof(DevFlags), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaMemcpyAsync(table_h.data(), table, sizeof(long long) * MB_TABLE, cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	if (fh.too_many_offsets || fh.row_too_long) return 0;
+	if (dia_image_from_table(A, table_h, tmp, fl)) return 1;
+	return 0;
+}
 
 // 0: A is complete (device arrays, plan, diagonal image); 1: error; 2: not applicable
 int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_row, const double *data, int rank,
@@ -355,47 +471,7 @@ int b200k_mat_build_device(int nrows, int ncols, const int *j_col, const int *i_
 
 	// ---- diagonal image (the rules of dia_build in b200_mat.cu)
 	A->dia_nd = 0;
-	if (try_dia && !fh.too_many_offsets) {
-		std::vector<long long> offs;
-		for (long long d : table_h) if (d != MB_EMPTY) offs.push_back(d);
-		std::sort(offs.begin(), offs.end());
-		const int nd = (int)offs.size();
-		bool ok = nd >= 1 && nd <= 32 && !((double)nnz_loc < 0.45 * (double)nd * nloc);
-		for (long long d : offs) if (d > 0x3fffffff || d < -0x3fffffff) ok = false;
-		if (ok) {
-			int ng = 0, ndp = 0;
-			std::vector<int> slot_of((size_t)nd), offs_i((size_t)nd);
-			for (int s0 = 0; s0 < nd;) {
-				int w = 1;
-				while (w < 3 && s0 + w < nd && offs[s0 + w] == offs[s0] + w) ++w;
-				A->dia_grp_h[2 * ng] = ndp; A->dia_grp_h[2 * ng + 1] = w;
-				A->dia_off_h[ng] = (int)offs[s0];
-				for (int j = 0; j < w; ++j) slot_of[s0 + j] = ndp + j;
-				ndp += (w + 1) & ~1; ++ng; s0 += w;
-			}
-			for (int i = 0; i < nd; ++i) offs_i[i] = (int)offs[i];
-			const size_t npad = (((size_t)nloc + B200_DIA_PAD - 1) / B200_DIA_PAD) * B200_DIA_PAD + B200_DIA_PAD;
-			int *offs_d = tmp.get<int>(64), *slot_d = offs_d ? offs_d + 32 : nullptr;
-			double *val = nullptr;
-			if (offs_d && cudaMalloc(&val, sizeof(double) * npad * ndp) == cudaSuccess) {
-				B200_CUDA(cudaMemcpyAsync(offs_d, offs_i.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
-				B200_CUDA(cudaMemcpyAsync(slot_d, slot_of.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
-				B200_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * npad * ndp, st));
-				mb_dia_fill_kernel<<<grid_for(nloc), 256, 0, st>>>(nloc, A->rp, A->ci, A->va, nd, offs_d, slot_d, ndp, val, fl);
-				B200_KERNEL_CHECK();
-				B200_CUDA(cudaMemcpyAsync(&fh, fl, sizeof(DevFlags), cudaMemcpyDeviceToHost, st));
-				B200_CUDA(cudaStreamSynchronize(st));
-				if (fh.duplicate || fh.too_many_offsets) cudaFree(val);          // keep the CSR semantics
-				else {
-					B200_CUDA(cudaMalloc(&A->dia_off, sizeof(int) * 32));
-					B200_CUDA(cudaMalloc(&A->dia_grp, sizeof(int) * 64));
-					B200_CUDA(cudaMemcpyAsync(A->dia_off, A->dia_off_h, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-					B200_CUDA(cudaMemcpyAsync(A->dia_grp, A->dia_grp_h, sizeof(int) * 2 * ng, cudaMemcpyHostToDevice, st));
-					A->dia_val = val; A->dia_ndp = ndp; A->dia_nd = nd; A->dia_ng = ng;
-				}
-			} else cudaGetLastError();
-		}
-	}
+	if (try_dia && !fh.too_many_offsets && dia_image_from_table(A, table_h, tmp, fl)) return 1;
 	B200_CUDA(cudaStreamSynchronize(st));
 	return 0;
 }

@@ -305,6 +305,36 @@ def test_matrix_from_local_rows_matches_whole_ccs(b200, name, m):
     assert o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"], o2["eval"])
 
 
+def test_matrix_from_local_rows_rejects_malformed_rows(b200):
+    """The arrays are checked on the device after the upload: a row whose columns do not ascend, a column outside the
+    matrix and decreasing row pointers are errors, not silently different matrices.  An irregular (non-banded) matrix
+    handed over by rows keeps its CSR storage and multiplies exactly."""
+    from gcge_b200 import api
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    n = 300
+    S = sp.random(n, n, density=0.03, random_state=7, format="csr"); S = (S + S.T + sp.eye(n)).tocsr(); S.sort_indices()
+    rp = S.indptr.astype(np.int32); ci = S.indices.astype(np.int32); va = S.data.astype(np.float64)
+    A = api.Mat.from_local_rows(n, 0, rp, ci, va)
+    assert A.storage()["dia_nd"] == 0
+    x = np.asfortranarray(rng.standard_normal((n, 7)))
+    X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec(n, 7)
+    api.mat_dot_multivec(A, X, Y, (0, 0), (7, 7))
+    Sc = S.tocsc(); Sc.sort_indices()
+    M = P.CCS(n, n, Sc.indptr.astype(np.int32), Sc.indices.astype(np.int32), Sc.data.astype(np.float64))
+    assert np.array_equal(Y.numpy(), oracle_spmm(M, x))
+    r = int(np.argmax(np.diff(rp) >= 2))
+    bad = ci.copy(); bad[rp[r]], bad[rp[r] + 1] = ci[rp[r] + 1], ci[rp[r]]
+    with pytest.raises(RuntimeError, match="ascending"):
+        api.Mat.from_local_rows(n, 0, rp, bad, va)
+    bad = ci.copy(); bad[rp[r + 1] - 1] = n
+    with pytest.raises(RuntimeError, match="out of range"):
+        api.Mat.from_local_rows(n, 0, rp, bad, va)
+    badrp = rp.copy(); badrp[r + 1] = rp[r] - 1 if rp[r] > 0 else rp[r + 2] + 1
+    with pytest.raises(RuntimeError, match="monotone"):
+        api.Mat.from_local_rows(n, 0, badrp, ci, va)
+
+
 @pytest.mark.parametrize("name,m", [("p1_fem_kuhn", 11), ("q1_27pt", 9), ("laplace3d_7pt", 12)])
 def test_spmm_constant_stencil_path(b200, name, m):
     """Constant stencils (every row the same coefficients, entries exactly where the neighbour is inside the lattice:
