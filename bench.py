@@ -31,7 +31,9 @@ parity_vs_golden
          carries iteration counts, eigenvalue differences and whether all ranks hold identical bits.
 
 Other workloads of BASELINE.json (same line format): --workload laplace7 --m 100 --nev 50 (config 2,
-standard problem, analytic eigenvalues as the parity pin), --workload q1_27pt (config 4's operator).
+standard problem, analytic eigenvalues as the parity pin), --workload q1_27pt (config 4's operator), and
+--kernel-sweep (config 5: per-kernel sweep at n = m^3, k = 16 ... 512, with the reference's slots timed on the host
+cores at --sweep-cpu-m beside it; its own one-line format, `rows`).
 
 Multi-GPU (torchrun, one rank per GPU): the SAME pencil is split into 1-D row blocks over the N
 GPUs (strong scaling): SpMM halo rows travel by copy-engine peer-to-peer copies into IPC mailboxes
@@ -181,6 +183,76 @@ def pick_reference_size(cal: dict, m_full: int, budget_s: float) -> int:
     if m_full > best and per_row * m_full ** 3 * 2.0 <= budget_s:
         best = m_full
     return best
+
+
+def reference_kernel_slices(gen: str, m: int, ks, budget_s: float, cores: int) -> dict:
+    """BASELINE config 5 on the host cores (SURVEY 8d "per-kernel slices of config 5"): the reference's own slots --
+    CCS MatDotMultiVec, MultiVecInnerProd, MultiVecLinearComb, MultiVecAxpby, MultiVecOrth -- on the same kind of pencil at
+    a size the CPU finishes in seconds, same shapes as the GPU sweep (3k-wide left operand), OMP threads = cores."""
+    from oracle import ref
+    from gcge_b200 import problems as P
+    ref.set_threads(cores)
+    pen = getattr(P, gen)(m)
+    n, nnz = pen.A.ncols, pen.A.nnz
+    rows, t_begin = [], time.time()
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3
+
+    for k in ks:
+        if time.time() - t_begin > budget_s:
+            break
+        p = 3 * k
+        rng = np.random.default_rng(k)
+        X = np.asfortranarray(rng.random((n, p))); Y = np.zeros((n, k), order="F")
+        row = {"k": k, "p": p}
+        ms = best(lambda: ref.mat_dot_multivec(pen.A, X, Y, (0, 0), (k, k)))
+        row["spmm_ms"] = round(ms, 3); row["spmm_GBs"] = round((nnz * 12 + (n + 1) * 4 + 16 * n * k) / ms / 1e6, 2)
+        ms = best(lambda: ref.multivec_axpby(0.5, X, 1.5, Y, (0, 0), (k, k)))
+        row["axpby_ms"] = round(ms, 3); row["axpby_GBs"] = round(24 * n * k / ms / 1e6, 2)
+        d = np.zeros(k)
+        ms = best(lambda: ref.multivec_inner_prod("D", X, Y, (0, 0), (k, k), d, 1))
+        row["dots_ms"] = round(ms, 3); row["dots_GBs"] = round(16 * n * k / ms / 1e6, 2)
+        g = np.zeros((p, k), order="F")
+        ms = best(lambda: ref.multivec_inner_prod("N", X, Y, (0, 0), (p, k), g, p))
+        row["gram_ms"] = round(ms, 3); row["gram_TF"] = round(2.0 * n * p * k / ms / 1e9, 4)
+        coef = np.asfortranarray(rng.random((p, k)))
+        ms = best(lambda: ref.multivec_linear_comb(X, Y, (0, 0), (p, k), coef, p, None, 0))
+        row["lincomb_ms"] = round(ms, 3); row["lincomb_TF"] = round(2.0 * n * p * k / ms / 1e9, 4)
+        if time.time() - t_begin < budget_s:
+            end0 = ref.multivec_orth(X, 0, 2 * k, B=pen.B, block_size=80)
+            t0 = time.perf_counter(); end = ref.multivec_orth(X, 2 * k, 3 * k, B=pen.B, block_size=80)
+            row["orth_ms"] = round((time.perf_counter() - t0) * 1e3, 3); row["orth_end"] = [int(end0), int(end)]
+        rows.append(row)
+    return {"kind": "reference", "cores": cores, "unit": "ms per call (see rows)", "value": rows[0]["spmm_ms"] if rows else None,
+            "sample": f"the reference's slots on {gen} m={m} (n = {n}, nnz = {nnz}), k in {[r['k'] for r in rows]}, "
+                      f"best of 3 calls each, {cores} OpenMP threads", "rows": rows}
+
+
+def run_kernel_sweep(a) -> int:
+    """BASELINE config 5 (`--kernel-sweep`): scripts/kernel_sweep.py's rows at n = m^3 and the reference's slots on
+    the host cores at a reduced size, as ONE JSON line."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kernel_sweep", str(ROOT / "scripts" / "kernel_sweep.py"))
+    ks_mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(ks_mod)
+    sa = ks_mod.arguments(["--m", str(a.m), "--ks", a.sweep_ks])
+    sa.quiet = True
+    head, rows = ks_mod.sweep(sa)
+    line = {"metric": "kernel_sweep", "unit": "GB/s and TFLOP/s per kernel (rows)", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: SpMM / axpby / dots / Gram (3k x k) / LinearComb (3k -> k) / B-orth of k "
+                                   f"against 2k on the P1-FEM pencil, n = {head['n']}, k in {a.sweep_ks}", "m": a.m,
+                       "l2": "L2 flushed between repetitions (b200_flush_l2)"},
+            "peak_hbm_gbs": head["hbm_gbs"], "rows": rows}
+    if not a.no_cpu:
+        from oracle import ref
+        if ref.available():
+            cpu_ks = [int(v) for v in a.sweep_ks.split(",") if int(v) <= 128]
+            line["cpu_baseline"] = reference_kernel_slices("p1_fem_kuhn", a.sweep_cpu_m, cpu_ks, a.ref_budget / 2, host_cores())
+    print(json.dumps(line))
+    return 0
 
 
 def run_reference(a) -> int:
@@ -590,6 +662,10 @@ def main() -> int:
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity solves before the timed region")
     ap.add_argument("--same-m", type=int, default=40, help="lattice size of the measured same-size pair (reference on the "
                     "host cores and device solver on the same pencil); also the sample the cpu_baseline is scaled from")
+    ap.add_argument("--kernel-sweep", action="store_true", help="BASELINE config 5: per-kernel sweep at n = m^3 with the "
+                    "reference's slots on the host cores beside it (one JSON line)")
+    ap.add_argument("--sweep-ks", default="16,32,64,128,256,512")
+    ap.add_argument("--sweep-cpu-m", type=int, default=64, help="lattice size of the CPU slices of --kernel-sweep")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: seconds the one real solve may take")
     ap.add_argument("--ref-big-m", type=int, default=0, help="--impl reference: lattice size of the real solve (0: pick by budget)")
     a = ap.parse_args()
@@ -599,6 +675,8 @@ def main() -> int:
         a.ref_m = 15
     if a.impl == "reference":
         return run_reference(a)
+    if a.kernel_sweep:
+        return run_kernel_sweep(a)
     return run_b200(a)
 
 

@@ -17,6 +17,7 @@
 // two-wavefront (conflict-free) 64-bit access.
 #include "b200_internal.h"
 #include "b200_tma.cuh"
+#include "b200_stream.cuh"
 #include <cmath>
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
@@ -399,40 +400,47 @@ __global__ void gram_reduce_kernel(int p, int q, int chunks, const double *__res
 	if (symmetric && i > j) c[(size_t)j * c_rs + (size_t)i * c_cs] = s;
 }
 
-// 'D': column dot products.  blockDim = (CX, 256/CX); thread (tx,ty) owns column tx (+CX...)
-// for rows ty, ty+RY, ...; per-CTA partial per column, then the same fixed-order reduce.
-__global__ void __launch_bounds__(256)
-dots_partial_kernel(long long n, int k, const double *x, int ldx, const double *y, int ldy,
-                    long long rows_per_chunk, double *part)
+// 'D': column dot products, c[col * stride] = alpha * x[:, col] . y[:, col], on the geometry of the streaming kernels
+// (b200_stream.cuh): a thread owns one 16-byte column pair and every rp-th row of its CTA's chunk with ST_UNROLL rows
+// of both streams in flight, so every warp request is a run of whole row segments; per-CTA partials, and the last
+// CTA to arrive adds them in a fixed order (deterministic, identical on every rank).  The first version (blockDim =
+// (32, 8), 8-byte loads, column passes of 32) left 24 of 32 lanes idle on the second pass at k = 40 and ran at
+// 0.50-0.60 of HBM (profiles/config5_kernel_sweep_r2_n8M.log).
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+dots_stream_kernel(long long n, int k, StreamGeom g, const double *__restrict__ x, int ldx, const double *__restrict__ y, int ldy,
+                   double alpha, double *c, int stride, double *part, unsigned *ticket)
 {
-	extern __shared__ double sm[];           // [blockDim.y][k]
-	const int cx = blockDim.x, ry = blockDim.y;
-	const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
-	long long r_end = r_begin + rows_per_chunk; if (r_end > n) r_end = n;
-	for (int c = threadIdx.x; c < k; c += cx) {
-		double s = 0.0;
-#pragma unroll 8
-		for (long long r = r_begin + threadIdx.y; r < r_end; r += ry)
-			s = fma(x[(size_t)r * ldx + c], y[(size_t)r * ldy + c], s);
-		sm[threadIdx.y * k + c] = s;
+	const StreamThread t = stream_thread<VEC>(g);
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	double acc[1][VEC];
+#pragma unroll
+	for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+	if (t.active) {
+		for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+			StV<VEC> xv[ST_UNROLL], yv[ST_UNROLL];
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) { xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c); yv[u] = st_ld<VEC>(y + (size_t)row * ldy + t.c); }
+			}
+#pragma unroll
+			for (int u = 0; u < ST_UNROLL; ++u) {
+				const long long row = row0 + (long long)u * g.rp;
+				if (row < r_end) {
+#pragma unroll
+					for (int i = 0; i < VEC; ++i) acc[0][i] = fma(xv[u].v[i], yv[u].v[i], acc[0][i]);
+				}
+			}
+		}
 	}
-	__syncthreads();
-	const int tid = threadIdx.y * cx + threadIdx.x;
-	for (int c = tid; c < k; c += cx * ry) {
-		double s = 0.0;
-		for (int j = 0; j < ry; ++j) s += sm[j * k + c];
-		part[(size_t)blockIdx.x * k + c] = s;
+	if (!stream_reduce_and_elect<VEC, 1>(acc, k, g, t, part, ticket)) return;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int col = warp; col < k; col += ST_THREADS / 32) {
+		const double s = stream_total<1>(part, gridDim.x, k, 0, col);
+		if (lane == 0) c[(size_t)col * stride] = alpha * s;
 	}
-}
-
-__global__ void dots_reduce_kernel(int k, int chunks, const double *__restrict__ part, double alpha,
-                                   double *__restrict__ c, int stride)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= k) return;
-	double s = 0.0;
-	for (int ch = 0; ch < chunks; ++ch) s += part[(size_t)ch * k + idx];
-	c[(size_t)idx * stride] = alpha * s;
 }
 
 __global__ void fill2d_kernel(int p, int q, double v, double *c, int c_rs, int c_cs)
@@ -484,19 +492,21 @@ int b200k_gram(char mode, long long n, int p, int q, double alpha, const double 
 			fill2d_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, 1, 0.0, dst, d_rs, 0);
 			B200_KERNEL_CHECK();
 		} else {
-			int cx = 1; while (cx < k && cx < 32) cx <<= 1;
-			const int ry = 256 / cx;
-			long long chunks = g_b200.num_sms * 4;
-			long long rows_per_chunk = (n + chunks - 1) / chunks;
-			if (rows_per_chunk < ry) rows_per_chunk = ry;
-			chunks = (n + rows_per_chunk - 1) / rows_per_chunk;
-			double *part = (double *)b200_scratch(0, sizeof(double) * (size_t)chunks * k);
-			if (!part) return 1;
-			dots_partial_kernel<<<(unsigned)chunks, dim3(cx, ry), sizeof(double) * (size_t)ry * k, st>>>(
-				n, k, x, ldx, y, ldy, rows_per_chunk, part);
-			B200_KERNEL_CHECK();
-			dots_reduce_kernel<<<b200_ceil_div(k, 128), 128, 0, st>>>(k, (int)chunks, part, alpha, dst, d_rs);
-			B200_KERNEL_CHECK();
+			// at most DOTS_COLS columns per launch (the geometry wants a column group per thread of one CTA row pass)
+			constexpr int DOTS_COLS = 128;
+			for (int c0 = 0; c0 < k; c0 += DOTS_COLS) {
+				const int kc = (k - c0 < DOTS_COLS) ? k - c0 : DOTS_COLS;
+				const double *xc = x + c0, *yc = y + c0;
+				const StreamGeom g = stream_geometry(n, kc, stream_aligned16(xc, ldx) && stream_aligned16(yc, ldy));
+				char *base = (char *)b200_scratch(0, sizeof(double) * (size_t)(g.chunks + 1) * kc + 64);
+				if (!base) return 1;
+				double *part = (double *)base;
+				unsigned *ticket = (unsigned *)(part + (size_t)(g.chunks + 1) * kc);
+				B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+				ST_DISPATCH_VEC(g, (dots_stream_kernel<VEC><<<g.chunks, ST_THREADS, 0, st>>>(n, kc, g, xc, ldx, yc, ldy, alpha,
+				                                                                          dst + (size_t)c0 * d_rs, d_rs, part, ticket)));
+				B200_KERNEL_CHECK();
+			}
 		}
 		if (multi) {
 			if (b200k_allreduce_sum(dst, (size_t)k)) return 1;

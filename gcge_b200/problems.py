@@ -398,6 +398,11 @@ def cube4_p1(refine: int = 2, order: str = "lattice") -> Pencil:
     return Pencil("cube4_p1", ccs(A), ccs(B), {"refine": refine, "order": order, "n": len(keep)})
 
 
+def cube4_p1_mesh(refine: int = 2) -> Pencil:
+    """cube4_p1 in the mesh's own hierarchical vertex order: an unstructured matrix (no diagonal image; the CSR kernels)."""
+    return cube4_p1(refine, "mesh")
+
+
 def ccs_to_dense(M: CCS) -> np.ndarray:
     out = np.zeros((M.nrows, M.ncols))
     for j in range(M.ncols):

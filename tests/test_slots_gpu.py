@@ -476,6 +476,29 @@ def test_inner_prod_modes(b200, refmod, shape):
     assert np.array_equal(s, s.T)
 
 
+@pytest.mark.parametrize("k,xo,yo", [(1, 0, 0), (7, 1, 0), (40, 0, 2), (41, 3, 3), (128, 0, 0), (129, 1, 2), (300, 2, 5)])
+def test_inner_prod_column_dots(b200, refmod, k, xo, yo):
+    """'D' on the streaming geometry: any width (more than 128 columns go in several launches), odd column offsets
+    (8-byte path), a strided destination (ldIP: reference app/app_lapack.c:67-115), run-to-run identical bits."""
+    from gcge_b200 import api
+    rng = np.random.default_rng(k)
+    n = 5003
+    x = np.asfortranarray(rng.standard_normal((n, k + 4))); y = np.asfortranarray(rng.standard_normal((n, k + 6)))
+    X = b200.MultiVec.from_numpy(x); Y = b200.MultiVec.from_numpy(y)
+    want = np.einsum("ij,ij->j", x[:, xo:xo + k], y[:, yo:yo + k])
+    d = np.zeros(k); d2 = np.zeros(k)
+    api.multivec_inner_prod("D", X, Y, (xo, yo), (xo + k, yo + k), d, 1)
+    api.multivec_inner_prod("D", X, Y, (xo, yo), (xo + k, yo + k), d2, 1)
+    assert rel(d, want) < 1e-13 and np.array_equal(d, d2)
+    ds = np.full(3 * k, 7.0)
+    api.multivec_inner_prod("D", X, Y, (xo, yo), (xo + k, yo + k), ds, 3)
+    assert np.array_equal(ds[::3], d) and np.all(ds[1::3] == 7.0) and np.all(ds[2::3] == 7.0)
+    if refmod is not None:
+        r = np.zeros(k)
+        refmod.multivec_inner_prod("D", x, y, (xo, yo), (xo + k, yo + k), r, 1)
+        assert rel(d, r) < 1e-13
+
+
 def test_inner_prod_deterministic(b200):
     from gcge_b200 import api
     rng = np.random.default_rng(9)
