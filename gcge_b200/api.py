@@ -372,6 +372,15 @@ class MultiVec:
     def set_random(self, start: int, end: int):
         _chk(lib().b200_mv_set_random(self.h, start, end))
 
+    def view(self, start: int, end: int) -> "MultiVec":
+        """The columns [start, end) as a multi-vector of their own on the same storage (b200_mv_view; the reference's
+        GetVecFromMultiVec, app/app_lapack.c:270-286).  The view must not outlive self."""
+        v = MultiVec.__new__(MultiVec)
+        v.h = C.c_void_p()
+        v.nrows, v.ncols = self.nrows, int(end - start)
+        _chk(lib().b200_mv_view(self.h, int(start), int(end), C.byref(v.h)))
+        return v
+
     def close(self):
         if self.h:
             lib().b200_mv_destroy(self.h)

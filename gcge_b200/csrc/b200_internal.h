@@ -38,6 +38,8 @@ struct b200_ctx {
 	// the largest halo of any matrix with that many columns created so far
 	long long halo_n[8];
 	int halo_cap[8];
+	// != 0: narrow axpby calls are waiting to be launched as one kernel (b200_mv.cu, b200k_pending_flush)
+	int pending;
 };
 
 int b200k_allreduce_sum(double *buf_dev, size_t count);
@@ -70,7 +72,7 @@ int b200k_spmm_lat(const b200_mat *M, const double *x, int ldx, double *y, int l
 enum { B200_OPT_NO_DIA = 0, B200_OPT_NO_LAT, B200_OPT_SPMM_OLD_DIA, B200_OPT_NO_FUSED_DOT, B200_OPT_NO_TMA_DENSE,
        B200_OPT_HOST_BUILD, B200_OPT_NO_OVERLAP, B200_OPT_NO_P2P, B200_OPT_NO_KERNEL_ALLREDUCE, B200_OPT_SYEV_PROF,
        B200_OPT_BPCG_TRACE, B200_OPT_SPMM_CTAS, B200_OPT_SPMM_NS, B200_OPT_LAT_TI, B200_OPT_LAT_TJ, B200_OPT_LAT_NS,
-       B200_OPT_LAT_EVEN_PITCH, B200_OPT_LAT_NO_VPAD, B200_OPT_LAT_VERBOSE, B200_OPT_LAT_NO_CONST, B200_OPT_ORTH_TRACE, B200_OPT_COUNT };
+       B200_OPT_LAT_EVEN_PITCH, B200_OPT_LAT_NO_VPAD, B200_OPT_LAT_VERBOSE, B200_OPT_LAT_NO_CONST, B200_OPT_ORTH_TRACE, B200_OPT_NO_AXPBY_BATCH, B200_OPT_COUNT };
 extern int g_b200_opt[B200_OPT_COUNT];
 static inline int b200_opt(int id) { return g_b200_opt[id]; }
 static_assert(B200_OPT_BPCG_TRACE == B200K_OPT_BPCG_TRACE && B200_OPT_ORTH_TRACE == B200K_OPT_ORTH_TRACE, "b200_dev.h option id out of step");
@@ -86,10 +88,16 @@ static inline bool b200_multi() { return g_b200.nranks > 1; }
 			                 cudaGetErrorString(e_));                              \
 	} while (0)
 
+// every entry point that touches device data starts here: the library is up, and deferred work (the batch of narrow
+// axpby calls, b200_mv.cu) has been launched
 #define B200_REQUIRE_INIT()                                                        \
 	do {                                                                           \
 		if (!g_b200.initialised) {                                                 \
 			int rc_ = b200_init(-1);                                               \
+			if (rc_) return rc_;                                                   \
+		}                                                                          \
+		if (g_b200.pending) {                                                      \
+			int rc_ = b200k_pending_flush();                                       \
 			if (rc_) return rc_;                                                   \
 		}                                                                          \
 	} while (0)

@@ -1,6 +1,7 @@
 // Device multi-vector store (row-major n x ld) and the HBM-bound elementwise kernels:
 // axpby / scale / copy on column ranges, column-major <-> row-major staging, RNG fill.
 #include "b200_internal.h"
+#include "b200_stream.cuh"
 
 static int mv_ld_for(int ncols)
 {
@@ -44,6 +45,7 @@ extern "C" int b200_mv_create(int nrows, int ncols, b200_mv **out)
 extern "C" int b200_mv_destroy(b200_mv *x)
 {
 	if (!x) return 0;
+	if (g_b200.initialised && g_b200.pending) b200k_pending_flush();
 	if (x->owner) {
 		if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
 		cudaFree(x->alloc);
@@ -253,10 +255,140 @@ int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx, doub
 	return 0;
 }
 
+// ---- batching of narrow axpby calls ----------------------------------------------------------------------------
+// The reference's BlockPCG updates x, r and p ONE COLUMN PER CALL, each with its own alpha / beta
+// (src/ops_lin_sol.c:256-405): through OPS_B200_Set that is ~84 000 single-column launches per solve at n = 2 M,
+// nev = 100, each touching 8 bytes of every k*8-byte row -- 79 % of the time of the reference's GCG over the device
+// slots (profiles/tiers_prof_r2g.log).  The slot has no host-visible result, so a narrow call is DEFERRED: calls on
+// adjacent columns of the same two blocks are collected (alpha and beta per column) and launched as one kernel on the
+// streaming geometry -- when the next call does not extend the batch, when the batch is full, or at the start of any
+// other entry point (B200_REQUIRE_INIT).  Per element the arithmetic is the unbatched kernel's, so results are bit-identical.
+constexpr int AXB_MAX_COLS = 64;              // columns per batch (alpha/beta travel as kernel parameters)
+constexpr int AXB_MAX_CALL = 8;               // widest call that is deferred
+constexpr int AXB_SLOTS = 4;                  // batches open at a time (BlockPCG interleaves x += a p and r -= a w column by column)
+struct AxpbyCols { double alpha[AXB_MAX_COLS], beta[AXB_MAX_COLS]; };
+struct AxpbyBatch {
+	const double *x; double *y; int ldx, ldy, count; long long n;
+	AxpbyCols c;
+};
+static AxpbyBatch g_axb[AXB_SLOTS];
+
+template <int VEC>
+__global__ void __launch_bounds__(ST_THREADS)
+axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ AxpbyCols prm, const double *__restrict__ x, int ldx,
+                  double *__restrict__ y, int ldy)
+{
+	const StreamThread t = stream_thread<VEC>(g);
+	if (!t.active) return;
+	double a[VEC], b[VEC];
+#pragma unroll
+	for (int i = 0; i < VEC; ++i) { a[i] = prm.alpha[t.c + i]; b[i] = prm.beta[t.c + i]; }
+	const long long r_begin = (long long)blockIdx.x * g.rows_per_chunk;
+	long long r_end = r_begin + g.rows_per_chunk; if (r_end > n) r_end = n;
+	for (long long row0 = r_begin + t.rl; row0 < r_end; row0 += (long long)ST_UNROLL * g.rp) {
+		StV<VEC> xv[ST_UNROLL], yv[ST_UNROLL];
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) { xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c); yv[u] = st_ld<VEC>(y + (size_t)row * ldy + t.c); }
+		}
+#pragma unroll
+		for (int u = 0; u < ST_UNROLL; ++u) {
+			const long long row = row0 + (long long)u * g.rp;
+			if (row < r_end) {
+#pragma unroll
+				for (int i = 0; i < VEC; ++i) {
+					// as axpby_kernel: beta == 0 overwrites (NaN-safe), beta == 1 does not multiply, then one fma
+					double v = 0.0;
+					if (b[i] != 0.0) { v = yv[u].v[i]; if (b[i] != 1.0) v *= b[i]; }
+					yv[u].v[i] = fma(a[i], xv[u].v[i], v);
+				}
+				st_st<VEC>(y + (size_t)row * ldy + t.c, yv[u]);
+			}
+		}
+	}
+}
+
+static int axpby_batch_launch(AxpbyBatch &B)
+{
+	const int k = B.count;
+	B.count = 0;
+	if (k <= 0) return 0;
+	if (k == 1) return b200k_axpby(B.n, 1, B.c.alpha[0], B.x, B.ldx, B.c.beta[0], B.y, B.ldy);
+	B200Prof prof(B200_PROF_AXPBY, 24.0 * B.n * k, 2.0 * B.n * k);
+	const StreamGeom g = stream_geometry(B.n, k, stream_aligned16(B.x, B.ldx) && stream_aligned16(B.y, B.ldy));
+	ST_DISPATCH_VEC(g, (axpby_cols_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(B.n, k, g, B.c, B.x, B.ldx, B.y, B.ldy)));
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+// the open batches are independent of one another (axpby_defer keeps them so): any order is the program's order
+extern "C" int b200k_pending_flush(void)
+{
+	g_b200.pending = 0;
+	int rc = 0;
+	for (int i = 0; i < AXB_SLOTS; ++i) rc |= axpby_batch_launch(g_axb[i]);
+	return rc;
+}
+
+// do the column blocks (a: ca columns, leading dimension lda; b likewise; n rows each) share an element?  Blocks of
+// different allocations never do; blocks of one allocation start in its row 0, so with equal leading dimensions the
+// answer is whether their column intervals meet; anything else that overlaps in memory counts as shared
+static bool axpby_blocks_meet(const double *a, int ca, int lda, const double *b, int cb, int ldb, long long n)
+{
+	if (a + (size_t)(n - 1) * lda + ca <= b || b + (size_t)(n - 1) * ldb + cb <= a) return false;
+	if (lda != ldb) return true;
+	return a < b + cb && b < a + ca;
+}
+
+// take a narrow call into a batch; *taken = 0: the caller launches it itself (everything deferred has been launched)
+static int axpby_defer(double alpha, const double *x, int ldx, double beta, double *y, int ldy, long long n, int k, int *taken)
+{
+	*taken = 0;
+	int slot = -1;
+	for (int i = 0; i < AXB_SLOTS && slot < 0; ++i) {
+		const AxpbyBatch &B = g_axb[i];
+		if (B.count > 0 && x == B.x + B.count && y == B.y + B.count && ldx == B.ldx && ldy == B.ldy && n == B.n &&
+		    B.count + k <= AXB_MAX_COLS) slot = i;
+	}
+	// the call reads x and (if beta != 0) y and writes y: what it touches must not meet what any OTHER open batch writes,
+	// and what it writes must not meet what another batch reads -- and x must not meet y inside its own batch (a later
+	// column of x could be an earlier column of y: column copies inside one multi-vector go one by one in the reference,
+	// src/ops_orth.c:70,302)
+	const double *bx = slot >= 0 ? g_axb[slot].x : x; const double *by = slot >= 0 ? g_axb[slot].y : y;
+	const int bc = (slot >= 0 ? g_axb[slot].count : 0) + k;
+	bool clash = axpby_blocks_meet(bx, bc, ldx, by, bc, ldy, n);
+	for (int i = 0; i < AXB_SLOTS && !clash; ++i) {
+		const AxpbyBatch &B = g_axb[i];
+		if (i == slot || B.count == 0) continue;
+		clash = axpby_blocks_meet(x, k, ldx, B.y, B.count, B.ldy, B.n > n ? B.n : n) ||
+		        axpby_blocks_meet(y, k, ldy, B.y, B.count, B.ldy, B.n > n ? B.n : n) ||
+		        axpby_blocks_meet(y, k, ldy, B.x, B.count, B.ldx, B.n > n ? B.n : n);
+	}
+	if (clash) {
+		if (b200k_pending_flush()) return 1;
+		if (axpby_blocks_meet(x, k, ldx, y, k, ldy, n)) return 0;
+		slot = -1;
+	}
+	if (slot < 0) {
+		for (int i = 0; i < AXB_SLOTS && slot < 0; ++i) if (g_axb[i].count == 0) slot = i;
+		if (slot < 0) { if (b200k_pending_flush()) return 1; slot = 0; }
+		AxpbyBatch &B = g_axb[slot];
+		B.x = x; B.y = y; B.ldx = ldx; B.ldy = ldy; B.n = n; B.count = 0;
+	}
+	AxpbyBatch &B = g_axb[slot];
+	for (int i = 0; i < k; ++i) { B.c.alpha[B.count + i] = alpha; B.c.beta[B.count + i] = beta; }
+	B.count += k;
+	g_b200.pending = 1;
+	*taken = 1;
+	return 0;
+}
+
 extern "C" int b200_mv_axpby(double alpha, const b200_mv *x, double beta, b200_mv *y,
                              const int *start, const int *end)
 {
-	B200_REQUIRE_INIT();
+	if (!g_b200.initialised) { int rc_ = b200_init(-1); if (rc_) return rc_; }      // (no flush: this call may extend the batch)
+	if (!(y && start && end) && g_b200.pending && b200k_pending_flush()) return 1;
 	B200_CHECK(y && start && end, "b200_mv_axpby: bad arguments");
 	const int k = end[1] - start[1];
 	B200_CHECK(end[0] - start[0] == k, "b200_mv_axpby: column counts differ (%d vs %d)", end[0] - start[0], k);
@@ -274,6 +406,12 @@ extern "C" int b200_mv_axpby(double alpha, const b200_mv *x, double beta, b200_m
 			B200_CHECK(!overlap || start[0] == start[1], "b200_mv_axpby: overlapping column ranges on one multi-vector");
 		}
 	}
+	if (x && x != y && k <= AXB_MAX_CALL && !b200_opt(B200_OPT_NO_AXPBY_BATCH)) {
+		int taken = 0;
+		if (axpby_defer(alpha, x->d + start[0], x->ld, beta, y->d + start[1], y->ld, y->nrows, k, &taken)) return 1;
+		if (taken) return 0;
+	}
+	if (g_b200.pending && b200k_pending_flush()) return 1;
 	return b200k_axpby(y->nrows, k, alpha, x ? x->d + start[0] : nullptr, x ? x->ld : 0, beta,
 	                   y->d + start[1], y->ld);
 }

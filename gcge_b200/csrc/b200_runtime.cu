@@ -57,7 +57,7 @@ int g_b200_opt[B200_OPT_COUNT];
 static const char *const g_opt_names[B200_OPT_COUNT] = {
 	"no_dia", "no_lat", "spmm_old_dia", "no_fused_dot", "no_tma_dense", "host_build", "no_overlap", "no_p2p",
 	"no_kernel_allreduce", "syev_prof", "bpcg_trace", "spmm_ctas", "spmm_ns", "lat_ti", "lat_tj", "lat_ns",
-	"lat_even_pitch", "lat_no_vpad", "lat_verbose", "lat_no_const", "orth_trace"};
+	"lat_even_pitch", "lat_no_vpad", "lat_verbose", "lat_no_const", "orth_trace", "no_axpby_batch"};
 
 // B200_<NAME> in the environment: a number is taken as is, anything else (incl. an empty value) means 1
 static void options_from_environment(void)
@@ -102,6 +102,7 @@ extern "C" int b200k_opt(int id) { options_from_environment(); return (id >= 0 &
 extern "C" void b200_finalize(void)
 {
 	if (!g_b200.initialised) return;
+	if (g_b200.pending) b200k_pending_flush();
 	cudaStreamSynchronize(g_b200.stream);
 	b200_gcg_free_cache();
 	for (int i = 0; i < 10; ++i) {
@@ -158,6 +159,7 @@ extern "C" int b200_sync(void)
 
 extern "C" double b200_wtime(void)
 {
+	if (g_b200.initialised && g_b200.pending) b200k_pending_flush();
 	if (g_b200.initialised) cudaStreamSynchronize(g_b200.stream);
 	using clk = std::chrono::steady_clock;
 	return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
@@ -231,6 +233,7 @@ extern "C" int b200_timer_start(void)
 extern "C" int b200_timer_stop(double *ms)
 {
 	B200_CHECK(g_ev_ok && ms, "b200_timer_stop: timer not started");
+	if (g_b200.pending && b200k_pending_flush()) return 1;
 	B200_CUDA(cudaEventRecord(g_ev[1], g_b200.stream));
 	B200_CUDA(cudaEventSynchronize(g_ev[1]));
 	float f = 0.f;

@@ -89,6 +89,7 @@ int b200_block_pcg(const b200_mat *A, const b200_mat *B, b200_mv *b, b200_mv *x,
 {
 	if (!A || !b || !x || !start || !end || !prm || !ws_r || !ws_p || !ws_w)
 		return b200_fail("b200_block_pcg: bad arguments");
+	if (b200k_pending_flush()) return 1;
 	const int k = end[0] - start[0];
 	if (k != end[1] - start[1]) return b200_fail("b200_block_pcg: column counts differ");
 	if (k <= 0) return 0;

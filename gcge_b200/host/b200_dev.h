@@ -99,6 +99,8 @@ int  b200k_opt(int id);
 
 /* synchronising small transfers */
 int b200k_d2h(void *host, const void *dev, size_t bytes);
+/* launch what b200_mv_axpby deferred (a batch of narrow calls on adjacent columns); every entry point calls it first */
+int b200k_pending_flush(void);
 int b200k_h2d(void *dev, const void *host, size_t bytes);
 int b200k_memset(void *dev, int value, size_t bytes);
 int b200k_malloc(void **dev, size_t bytes);

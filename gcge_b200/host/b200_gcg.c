@@ -503,6 +503,7 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
                    b200_gcg_stats *stats)
 {
 	if (!A || !eval || !evec || !nevConv || !prm) return b200_fail("b200_gcg_solve: bad arguments");
+	if (b200k_pending_flush()) return 1;
 	if (A->nrows != A->ncols || evec->nrows != A->nrows) return b200_fail("b200_gcg_solve: shape mismatch");
 	if (B && (B->nrows != A->nrows || B->ncols != A->ncols)) return b200_fail("b200_gcg_solve: B shape mismatch");
 	const int bs = prm->block_size, nevMax = prm->nevMax;

@@ -58,6 +58,7 @@ int b200_mv_orth(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
                  const b200_orth_params *prm, b200_mv *ws)
 {
 	if (!x || !end_x || !prm || !ws) return b200_fail("b200_mv_orth: bad arguments");
+	if (b200k_pending_flush()) return 1;
 	if (*end_x <= start_x) return 0;
 	if (start_x < 0 || *end_x > x->ncols) return b200_fail("b200_mv_orth: range [%d,%d) outside %d columns", start_x, *end_x, x->ncols);
 	if (ws->nrows != x->nrows) return b200_fail("b200_mv_orth: workspace row count differs");
@@ -262,6 +263,7 @@ int b200_mv_orth_bgs(b200_mv *x, int start_x, int *end_x, const b200_mat *B,
                      const b200_orth_params *prm, b200_mv *ws)
 {
 	if (!x || !end_x || !prm || !ws) return b200_fail("b200_mv_orth_bgs: bad arguments");
+	if (b200k_pending_flush()) return 1;
 	if (*end_x <= start_x) return 0;
 	if (start_x < 0 || *end_x > x->ncols) return b200_fail("b200_mv_orth_bgs: range [%d,%d) outside %d columns", start_x, *end_x, x->ncols);
 	if (ws->nrows != x->nrows || ws->ncols < 1) return b200_fail("b200_mv_orth_bgs: workspace shape");

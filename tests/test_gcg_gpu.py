@@ -4,6 +4,7 @@ residual test, outer iteration counts agree, eigenvectors agree by subspace angl
 eigenvalue cluster.  Three arms: the reference (oracle/_ref, or its committed golden output),
 tier A = the reference's own GCG/orth/BlockPCG driving OPS_B200_Set unchanged, tier B = the
 device-resident GCG (b200_gcg_solve)."""
+import os
 import numpy as np
 import pytest
 
@@ -112,6 +113,45 @@ def test_tierA_reference_gcg_over_ops_b200(b200, refmod, drive_b200, golden):
         assert abs(a["num_iter"] - case["num_iter"]) <= 1, (a["num_iter"], case["num_iter"])
         k = min(a["nev_conv"], case["nev_conv"])
         assert rel(a["eval"][:k], np.array(case["eval"][:k])) < 1e-10
+
+
+@pytest.mark.skipif(not os.environ.get("GCGE_TIERS_AT"), reason="opt-in measurement: GCGE_TIERS_AT=<m>[,<nev>]")
+def test_tiers_side_by_side_at_size(b200, refmod, drive_b200):
+    """Measurement, not a gate (run with -s): the same P1 pencil at lattice size m solved (1) by the reference on
+    CCS + OpenMP, (2) by the reference's UNCHANGED GCG / ops_orth.c / ops_lin_sol.c over OPS_B200_Set (tier A: what a
+    user gets by swapping the one Set call) and (3) by the device GCG installed through the OPS table (tier B);
+    same iteration counts within 1, eigenvalues 1e-10; prints one JSON line with the three times."""
+    import json
+    if drive_b200 is None:
+        pytest.skip("oracle/_ref (reference + driver) not present on this box")
+    parts = os.environ["GCGE_TIERS_AT"].split(",")
+    m = int(parts[0]); nev = int(parts[1]) if len(parts) > 1 else 50
+    pen = P.p1_fem_kuhn(m)
+    out = {"m": m, "n": pen.A.ncols, "nev": nev}
+    a = drive_b200(0, pen.A, pen.B, nev=nev)
+    b = drive_b200(1, pen.A, pen.B, nev=nev)
+    b2 = drive_b200(1, pen.A, pen.B, nev=nev)                     # second solve: buffers cached, kernels loaded
+    out["tierA"] = {"seconds": a["seconds"], "num_iter": a["num_iter"], "nev_conv": a["nev_conv"]}
+    if os.environ.get("GCGE_TIERS_PROF"):
+        # where tier A's device time goes, per kernel class (events around every call: the solve itself gets slower)
+        from gcge_b200 import api
+        api.prof_enable(True)
+        ap = drive_b200(0, pen.A, pen.B, nev=nev)
+        rep = api.prof_report(); api.prof_enable(False)
+        out["tierA_profiled"] = {"seconds": ap["seconds"],
+                                 "classes": {k: {"ms": round(v["ms"], 1), "calls": v["calls"], "gap_before_ms": round(v.get("gap_before_ms", 0.0), 1)}
+                                             for k, v in rep.items() if v["calls"]}}
+    out["tierB"] = {"seconds": b2["seconds"], "first_call_seconds": b["seconds"], "num_iter": b["num_iter"], "nev_conv": b["nev_conv"]}
+    if os.environ.get("GCGE_TIERS_REF", "1") != "0":
+        refmod.set_threads(refmod.max_threads())
+        r = refmod.gcg_solve(pen.A, pen.B, nev=nev)
+        out["reference"] = {"seconds": r["seconds"], "num_iter": r["num_iter"], "nev_conv": r["nev_conv"], "threads": refmod.max_threads()}
+        assert abs(a["num_iter"] - r["num_iter"]) <= 1 and abs(b["num_iter"] - r["num_iter"]) <= 1, out
+        assert rel(a["eval"][:nev], r["eval"][:nev]) < 1e-10 and rel(b["eval"][:nev], r["eval"][:nev]) < 1e-10
+    else:
+        assert abs(a["num_iter"] - b["num_iter"]) <= 1, out
+        assert rel(a["eval"][:nev], b["eval"][:nev]) < 1e-10
+    print("TIERS " + json.dumps(out))
 
 
 def test_tierB_through_ops_table_and_live_reference(b200, refmod, drive_b200):

@@ -445,6 +445,95 @@ def test_axpby_semantics(b200, refmod):
     assert np.array_equal(Y.numpy()[:, 1:3], y[:, 7:9])
 
 
+def test_axpby_single_column_calls_are_batched_bit_exactly(b200):
+    """The reference's BlockPCG calls MultiVecAxpby one column at a time with per-column alpha / beta
+    (src/ops_lin_sol.c:256-405).  The slot defers such calls and launches runs of adjacent columns as one kernel:
+    same bits as the call-by-call path (option no_axpby_batch), in every order of calls -- adjacent runs, gaps, more
+    columns than a batch holds, beta = 0 over NaNs, a view of the same storage, other calls in between."""
+    from gcge_b200 import api
+    L = b200.lib()
+    rng = np.random.default_rng(3)
+    n, kx, ky = 4099, 90, 96
+    x = np.asfortranarray(rng.standard_normal((n, kx))); y0 = np.asfortranarray(rng.standard_normal((n, ky)))
+    y0[5, 7] = np.nan                                             # overwritten by a beta = 0 call below
+    alphas = rng.standard_normal(200); betas = rng.standard_normal(200)
+    betas[3] = 0.0; betas[11] = 1.0; alphas[4] = 0.0
+
+    def sequence(X, Y):
+        calls = 0
+        launches0 = L.b200_kernel_launches()
+        for j in range(80):                                       # one adjacent run, longer than a batch
+            api.multivec_axpby(alphas[j], X, betas[j] if j != 7 else 0.0, Y, (j + 2, j), (j + 3, j + 1)); calls += 1
+        for j in (0, 1, 2, 5, 6, 9, 20, 21, 22, 23):              # gaps: several short batches
+            api.multivec_axpby(alphas[100 + j], X, betas[100 + j], Y, (j, 80 + j // 2), (j + 1, 81 + j // 2)); calls += 1
+        api.multivec_axpby(0.5, X, 2.0, Y, (0, 90), (3, 93)); calls += 1           # a 3-column call joins ...
+        api.multivec_axpby(0.25, X, 1.0, Y, (3, 93), (4, 94)); calls += 1          # ... and is extended
+        d = np.zeros(2)
+        api.multivec_inner_prod("D", Y, Y, (92, 92), (94, 94), d, 1)               # any other call sees the result
+        Yv = Y.view(10, 20)                                                          # same storage through a view
+        api.multivec_axpby(1.5, Y, 0.5, Yv, (12, 1), (13, 2)); calls += 1           # reads column 12, writes column 11
+        api.multivec_axpby(1.5, Y, 0.5, Yv, (13, 2), (14, 3)); calls += 1           # reads column 13, writes column 12
+        api.multivec_axpby(-1.0, Yv, 0.0, Y, (2, 13), (3, 14)); calls += 1          # reads column 12 (just written)
+        out = Y.numpy()
+        return out, d, calls, L.b200_kernel_launches() - launches0
+
+    X = b200.MultiVec.from_numpy(x)
+    got, dg, calls, launched = sequence(X, b200.MultiVec.from_numpy(y0))
+    try:
+        L.b200_option_set(b"no_axpby_batch", 1)
+        want, dw, _, launched_plain = sequence(X, b200.MultiVec.from_numpy(y0))
+    finally:
+        L.b200_option_set(b"no_axpby_batch", 0)
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(dg, dw)
+    assert not np.isnan(got[5, 7])
+    assert launched < launched_plain - 60, (launched, launched_plain, calls)       # the run of 80 went in two launches
+    # numpy restatement of the first run (same formula: beta*y rounded, then one fma -- checked to a few ulps)
+    for j in (0, 3, 11, 40, 79):
+        b = betas[j] if j != 7 else 0.0
+        ref = alphas[j] * x[:, j + 2] + (b * y0[:, j] if b != 0.0 else 0.0)
+        if j not in range(11, 14) and j != 7:
+            assert np.allclose(got[:, j], ref, rtol=1e-14, atol=1e-14)
+
+
+def test_axpby_interleaved_streams_are_batched(b200):
+    """BlockPCG's update loop alternates x[:, c] += alpha_c p[:, c] and r[:, c] -= alpha_c w[:, c] column by column
+    (reference src/ops_lin_sol.c:330-345): two independent batches stay open side by side; a call that depends on an
+    open batch (reads what it writes) launches everything first.  Same bits as call by call."""
+    from gcge_b200 import api
+    L = b200.lib()
+    rng = np.random.default_rng(8)
+    n, k = 3001, 24
+    p = np.asfortranarray(rng.standard_normal((n, k))); w = np.asfortranarray(rng.standard_normal((n, k)))
+    x0 = np.asfortranarray(rng.standard_normal((n, k + 6))); r0 = np.asfortranarray(rng.standard_normal((n, k)))
+    al = rng.standard_normal(k)
+
+    def run():
+        Pm = b200.MultiVec.from_numpy(p); Wm = b200.MultiVec.from_numpy(w)
+        Xm = b200.MultiVec.from_numpy(x0); Rm = b200.MultiVec.from_numpy(r0)
+        l0 = L.b200_kernel_launches()
+        for c in range(k):
+            api.multivec_axpby(al[c], Pm, 1.0, Xm, (c, 3 + c), (c + 1, 4 + c))
+            api.multivec_axpby(-al[c], Wm, 1.0, Rm, (c, c), (c + 1, c + 1))
+        # depends on the open r batch: r[:, 0] is read
+        api.multivec_axpby(2.0, Rm, 0.0, Xm, (0, 0), (1, 1))
+        # p = r + beta p, column by column (src/ops_lin_sol.c:270-282)
+        for c in range(k):
+            api.multivec_axpby(1.0, Rm, al[c], Pm, (c, c), (c + 1, c + 1))
+        nl = L.b200_kernel_launches() - l0
+        return Xm.numpy(), Rm.numpy(), Pm.numpy(), nl
+
+    xg, rg, pg, nl = run()
+    try:
+        L.b200_option_set(b"no_axpby_batch", 1)
+        xw, rw, pw, nl_plain = run()
+    finally:
+        L.b200_option_set(b"no_axpby_batch", 0)
+    assert np.array_equal(xg, xw) and np.array_equal(rg, rw) and np.array_equal(pg, pw)
+    assert nl <= 6 and nl_plain == 3 * k + 1, (nl, nl_plain)
+    assert np.allclose(xg[:, 3:3 + k], x0[:, 3:3 + k] + p * al, rtol=1e-14, atol=1e-14)
+    assert np.allclose(xg[:, 0], 2.0 * (r0[:, 0] - al[0] * w[:, 0]), rtol=1e-14, atol=1e-14)
+
+
 @pytest.mark.parametrize("shape", [(2, 5), (1, 1), (17, 3), (40, 40), (100, 37), (70, 130)])
 def test_inner_prod_modes(b200, refmod, shape):
     """MultiVecInnerProd N / S / D (reference app/app_lapack.c:24-183 via :299-321;
