@@ -17,10 +17,14 @@
 //            P_j = M^(L 2^j), launches the kernel, and writes the state advanced by the number
 //            of values consumed back into glibc -- later rand() calls of the process continue
 //            the same stream as if rand() had been called that often;
-//   device : chunk c (L consecutive stream positions) gets its start state (M^L)^c S_0 from the
-//            binary expansion of c -- the high bits once per CTA, the low bits per thread --
-//            then runs the recurrence in registers and stores straight into the row-major
-//            multi-vector.
+//   device : the stream runs down the columns, the multi-vector is stored by rows.  A warp owns 32
+//            ADJACENT COLUMNS and a run of L rows: lane j jumps to its own stream position
+//            t = column_j * n + first row exactly -- M^t S_0 from the binary expansion of t with the
+//            powers M^(2^j) -- and then all lanes run the recurrence in registers in lockstep, one row
+//            per step, so every store of the warp is one contiguous 256-byte row segment.  (The first
+//            version gave a thread L consecutive stream positions = one column: 8-byte stores a row
+//            pitch apart, 141 ms for the 8 M x 400 block of the headline solve, 0.7 TB/s of sectors.)
+//            Several ranks fill only their own rows.
 #include "b200_internal.h"
 #include <vector>
 
@@ -28,11 +32,10 @@ namespace {
 
 constexpr int DEG = 31;                 // TYPE_3 degree
 constexpr int SEP = 3;                  // TYPE_3 separation
-constexpr int ROUNDS = 64;              // rounds of 31 values per thread
-constexpr long long CHUNK = (long long)DEG * ROUNDS;
-constexpr int RTHREADS = 128;           // chunks per CTA (power of two)
-constexpr int LOWBITS = 7;              // log2(RTHREADS)
-constexpr int NPOW = 48;                // P_0 .. P_47: chunk indices below 2^48
+constexpr int ROUNDS = 512;             // rounds of 31 rows per warp tile
+constexpr long long TILE_ROWS = (long long)DEG * ROUNDS;
+constexpr int RWARPS = 4;               // warp tiles per CTA
+constexpr int NPOW = 48;                // Q_0 .. Q_47 = M^(2^j): stream positions below 2^48
 
 struct Mat31 { uint32_t a[DEG][DEG]; };
 
@@ -116,7 +119,8 @@ void put_state(LiveState &ls, const uint32_t *S, unsigned long long consumed)
 void release_state(LiveState &ls) { setstate(reinterpret_cast<char *>(ls.words)); }
 
 // ---- device ------------------------------------------------------------------------------
-__device__ __forceinline__ void dev_mat_vec(const uint32_t *__restrict__ m, uint32_t (&s)[DEG])
+// s <- bit ? m s : s  for every lane (m: 31 x 31 row-major, the same for all lanes: broadcast loads)
+__device__ __forceinline__ void dev_mat_vec_if(const uint32_t *__restrict__ m, uint32_t (&s)[DEG], bool bit)
 {
 	uint32_t t[DEG];
 #pragma unroll
@@ -127,62 +131,40 @@ __device__ __forceinline__ void dev_mat_vec(const uint32_t *__restrict__ m, uint
 		t[i] = acc;
 	}
 #pragma unroll
-	for (int i = 0; i < DEG; ++i) s[i] = t[i];
+	for (int i = 0; i < DEG; ++i) s[i] = bit ? t[i] : s[i];
 }
 
-// pw: NPOW matrices, P_j = M^(CHUNK 2^j), row-major 31 x 31.  x: row-major destination block
-// (first element of the first column to fill); stream position t -> row t % n, column t / n.
-// Several ranks: n is the GLOBAL row count and x holds the rows [row_lo, row_hi) only; every
-// rank walks the same stream and keeps its own rows (chunks that miss the slab exit early).
-__global__ void __launch_bounds__(RTHREADS)
-rand_fill_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ pw, unsigned long long total,
+// pw: NPOW matrices Q_j = M^(2^j), row-major 31 x 31.  x: first element of the first column to fill of the row-major
+// block holding the rows [row_lo, row_hi) of the n global rows; stream position t -> row t % n, column t / n.
+// Warp tile w: columns 32 (w % ncg) .. + 31, rows row_lo + TILE_ROWS (w / ncg) .. + TILE_ROWS - 1.
+__global__ void __launch_bounds__(32 * RWARPS)
+rand_fill_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ pw, int ncols, int ncg, long long ntiles,
                  long long n, long long row_lo, long long row_hi, double *__restrict__ x, int ld)
 {
-	__shared__ uint32_t base[2][DEG];
-	const unsigned long long c0 = (unsigned long long)blockIdx.x * RTHREADS;
-	if (threadIdx.x < DEG) base[0][threadIdx.x] = s0[threadIdx.x];
-	__syncthreads();
-	// high bits of the chunk index, once per CTA: 31 threads own one output word each
-	int cur = 0;
-	for (int j = LOWBITS; j < NPOW; ++j) {
-		if (!((c0 >> j) & 1ull)) continue;                 // uniform over the CTA
-		if (threadIdx.x < DEG) {
-			const uint32_t *m = pw + (size_t)j * DEG * DEG + threadIdx.x * DEG;
-			uint32_t acc = 0;
-			for (int k = 0; k < DEG; ++k) acc += __ldg(m + k) * base[cur][k];
-			base[cur ^ 1][threadIdx.x] = acc;
-		}
-		__syncthreads();
-		cur ^= 1;
-	}
-	const unsigned long long c = c0 + threadIdx.x;
-	const unsigned long long t0 = c * (unsigned long long)CHUNK;
-	if (t0 >= total) return;
-	{
-		const unsigned long long len = (total - t0 < (unsigned long long)CHUNK) ? total - t0 : (unsigned long long)CHUNK;
-		const unsigned long long r_first = t0 % (unsigned long long)n;
-		if (r_first + len <= (unsigned long long)n &&
-		    (r_first >= (unsigned long long)row_hi || r_first + len <= (unsigned long long)row_lo))
-			return;                                    // no row of this chunk is ours
-	}
+	const int lane = threadIdx.x & 31;
+	const long long w = (long long)blockIdx.x * RWARPS + (threadIdx.x >> 5);
+	if (w >= ntiles) return;                                   // (whole warps)
+	const int col = 32 * (int)(w % ncg) + lane;
+	long long row = row_lo + TILE_ROWS * (w / ncg);
+	const long long row_end = (row + TILE_ROWS < row_hi) ? row + TILE_ROWS : row_hi;
+	const bool active = col < ncols;
+	const unsigned long long t = (unsigned long long)col * (unsigned long long)n + (unsigned long long)row;
 	uint32_t s[DEG];
 #pragma unroll
-	for (int i = 0; i < DEG; ++i) s[i] = base[cur][i];
-	for (int j = 0; j < LOWBITS; ++j)
-		if ((threadIdx.x >> j) & 1) dev_mat_vec(pw + (size_t)j * DEG * DEG, s);
-	long long col = (long long)(t0 / (unsigned long long)n);
-	long long row = (long long)(t0 - (unsigned long long)col * (unsigned long long)n);
-	unsigned long long left = total - t0;
-	for (int r = 0; r < ROUNDS && left > 0; ++r) {
+	for (int i = 0; i < DEG; ++i) s[i] = __ldg(s0 + i);
+	for (int j = 0; j < NPOW; ++j) {
+		const bool bit = active && ((t >> j) & 1ull);
+		if (!__any_sync(0xffffffffu, bit)) continue;
+		dev_mat_vec_if(pw + (size_t)j * DEG * DEG, s, bit);
+	}
+	double *dst = x + (size_t)(row - row_lo) * ld + col;
+	for (int r = 0; r < ROUNDS && row < row_end; ++r) {
 #pragma unroll
 		for (int i = 0; i < DEG; ++i) {
 			s[i] += s[(i + DEG - SEP) % DEG];
-			if (left > 0) {
-				if (row >= row_lo && row < row_hi)
-					x[(size_t)(row - row_lo) * ld + col] = (double)(s[i] >> 1) * (1.0 / 2147483648.0);
-				--left;
-				++row;
-				if (row == n) { row = 0; ++col; }
+			if (row < row_end) {                               // (warp-uniform)
+				if (active) *dst = (double)(s[i] >> 1) * (1.0 / 2147483648.0);
+				dst += ld; ++row;
 			}
 		}
 	}
@@ -194,15 +176,7 @@ int ensure_powers()
 {
 	if (g_pw_dev) return 0;
 	std::vector<Mat31> pw(NPOW);
-	Mat31 q; step_matrix(q);
-	// M^CHUNK by square-and-multiply
-	Mat31 acc; memset(&acc, 0, sizeof(acc));
-	for (int i = 0; i < DEG; ++i) acc.a[i][i] = 1;
-	for (unsigned long long e = (unsigned long long)CHUNK; e; e >>= 1) {
-		if (e & 1ull) mat_mul(acc, q, acc);
-		if (e > 1) mat_mul(q, q, q);
-	}
-	pw[0] = acc;
+	step_matrix(pw[0]);
 	for (int j = 1; j < NPOW; ++j) mat_mul(pw[j - 1], pw[j - 1], pw[j]);
 	B200_CUDA(cudaMalloc(&g_pw_dev, sizeof(Mat31) * NPOW));
 	B200_CUDA(cudaMemcpy(g_pw_dev, pw.data(), sizeof(Mat31) * NPOW, cudaMemcpyHostToDevice));
@@ -269,10 +243,11 @@ extern "C" int b200_mv_set_random(b200_mv *x, int start, int end)
 	if (!s_dev) { release_state(ls); return 1; }
 	cudaError_t e = cudaMemcpyAsync(s_dev, S, sizeof(S), cudaMemcpyHostToDevice, g_b200.stream);
 	if (e == cudaSuccess) {
-		const unsigned long long chunks = (total + CHUNK - 1) / CHUNK;
-		const unsigned long long ctas = (chunks + RTHREADS - 1) / RTHREADS;
-		rand_fill_kernel<<<(unsigned)ctas, RTHREADS, 0, g_b200.stream>>>(s_dev, g_pw_dev, total, n, x->row0, x->row0 + x->nrows,
-		                                                                 x->d + start, x->ld);
+		const int ncols = end - start, ncg = (ncols + 31) / 32;
+		const long long ntiles = (long long)ncg * ((x->nrows + TILE_ROWS - 1) / TILE_ROWS);
+		if (ntiles > 0)
+			rand_fill_kernel<<<(unsigned)((ntiles + RWARPS - 1) / RWARPS), 32 * RWARPS, 0, g_b200.stream>>>(
+				s_dev, g_pw_dev, ncols, ncg, ntiles, n, x->row0, x->row0 + x->nrows, x->d + start, x->ld);
 		B200_LAUNCHED();
 		e = cudaGetLastError();
 	}
