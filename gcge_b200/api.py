@@ -163,6 +163,12 @@ def prof_report() -> dict:
     return out
 
 
+def gcg_free_cache():
+    """Release the [X P W] buffer the solver keeps between solves (b200_gcg_free_cache)."""
+    lib().b200_gcg_free_cache.restype = None
+    lib().b200_gcg_free_cache()
+
+
 def host_register(a: np.ndarray):
     _chk(lib().b200_host_register(a.ctypes.data, a.nbytes))
 
