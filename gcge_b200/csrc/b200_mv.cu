@@ -236,12 +236,17 @@ __global__ void axpby_kernel(long long n, int k, int rows_per_cta, double alpha,
 	}
 }
 
+static int axpby_stream(long long n, int k, double alpha, const double *x, int ldx, double beta, double *y, int ldy);
+
 int b200k_axpby(long long n, int k, double alpha, const double *x, int ldx, double beta, double *y, int ldy)
 {
 	if (n <= 0 || k <= 0) return 0;
 	const bool has_x = (x != nullptr);
 	const bool has_y = (beta != 0.0);
 	if (!has_x && has_y && beta == 1.0) return 0;
+	// with an x operand: the streaming geometry (16-byte accesses, several rows of every stream in flight); the kernel
+	// below (8-byte accesses, an integer division per element: 3.0 TB/s in the solve) keeps the scale-only calls
+	if (has_x) return axpby_stream(n, k, alpha, x, ldx, beta, y, ldy);
 	B200Prof prof(B200_PROF_AXPBY, 8.0 * n * k * (1 + (has_x ? 1 : 0) + (has_y ? 1 : 0)), 2.0 * n * k);
 	int rows = 4096 / k; if (rows < 1) rows = 1;
 	const unsigned grid = (unsigned)((n + rows - 1) / rows);
@@ -273,10 +278,11 @@ struct AxpbyBatch {
 };
 static AxpbyBatch g_axb[AXB_SLOTS];
 
-template <int VEC>
+// LOADY == false: every beta is 0, y is only written (column copies and overwrites: two streams instead of three)
+template <int VEC, bool LOADY>
 __global__ void __launch_bounds__(ST_THREADS)
-axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ AxpbyCols prm, const double *__restrict__ x, int ldx,
-                  double *__restrict__ y, int ldy)
+axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ AxpbyCols prm, const double *x, int ldx,
+                  double *y, int ldy)
 {
 	const StreamThread t = stream_thread<VEC>(g);
 	if (!t.active) return;
@@ -290,7 +296,10 @@ axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ Axpb
 #pragma unroll
 		for (int u = 0; u < ST_UNROLL; ++u) {
 			const long long row = row0 + (long long)u * g.rp;
-			if (row < r_end) { xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c); yv[u] = st_ld<VEC>(y + (size_t)row * ldy + t.c); }
+			if (row < r_end) {
+				xv[u] = st_ld<VEC>(x + (size_t)row * ldx + t.c);
+				if (LOADY) yv[u] = st_ld<VEC>(y + (size_t)row * ldy + t.c);
+			}
 		}
 #pragma unroll
 		for (int u = 0; u < ST_UNROLL; ++u) {
@@ -300,7 +309,7 @@ axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ Axpb
 				for (int i = 0; i < VEC; ++i) {
 					// as axpby_kernel: beta == 0 overwrites (NaN-safe), beta == 1 does not multiply, then one fma
 					double v = 0.0;
-					if (b[i] != 0.0) { v = yv[u].v[i]; if (b[i] != 1.0) v *= b[i]; }
+					if (LOADY && b[i] != 0.0) { v = yv[u].v[i]; if (b[i] != 1.0) v *= b[i]; }
 					yv[u].v[i] = fma(a[i], xv[u].v[i], v);
 				}
 				st_st<VEC>(y + (size_t)row * ldy + t.c, yv[u]);
@@ -309,17 +318,36 @@ axpby_cols_kernel(long long n, int k, StreamGeom g, const __grid_constant__ Axpb
 	}
 }
 
+// y[:, c] = alpha[c] x[:, c] + beta[c] y[:, c] on k <= AXB_MAX_COLS adjacent columns, one launch on the streaming geometry
+static int axpby_cols_launch(long long n, int k, const AxpbyCols &c, const double *x, int ldx, double *y, int ldy)
+{
+	bool load_y = false;
+	for (int i = 0; i < k; ++i) load_y = load_y || c.beta[i] != 0.0;
+	B200Prof prof(B200_PROF_AXPBY, (load_y ? 24.0 : 16.0) * n * k, 2.0 * n * k);
+	const StreamGeom g = stream_geometry(n, k, stream_aligned16(x, ldx) && stream_aligned16(y, ldy));
+	if (load_y) ST_DISPATCH_VEC(g, (axpby_cols_kernel<VEC, true><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, c, x, ldx, y, ldy)));
+	else        ST_DISPATCH_VEC(g, (axpby_cols_kernel<VEC, false><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(n, k, g, c, x, ldx, y, ldy)));
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
+static int axpby_stream(long long n, int k, double alpha, const double *x, int ldx, double beta, double *y, int ldy)
+{
+	AxpbyCols c;
+	for (int i = 0; i < AXB_MAX_COLS; ++i) { c.alpha[i] = alpha; c.beta[i] = beta; }
+	for (int c0 = 0; c0 < k; c0 += AXB_MAX_COLS) {
+		const int kc = k - c0 < AXB_MAX_COLS ? k - c0 : AXB_MAX_COLS;
+		if (axpby_cols_launch(n, kc, c, x + c0, ldx, y + c0, ldy)) return 1;
+	}
+	return 0;
+}
+
 static int axpby_batch_launch(AxpbyBatch &B)
 {
 	const int k = B.count;
 	B.count = 0;
 	if (k <= 0) return 0;
-	if (k == 1) return b200k_axpby(B.n, 1, B.c.alpha[0], B.x, B.ldx, B.c.beta[0], B.y, B.ldy);
-	B200Prof prof(B200_PROF_AXPBY, 24.0 * B.n * k, 2.0 * B.n * k);
-	const StreamGeom g = stream_geometry(B.n, k, stream_aligned16(B.x, B.ldx) && stream_aligned16(B.y, B.ldy));
-	ST_DISPATCH_VEC(g, (axpby_cols_kernel<VEC><<<g.chunks, ST_THREADS, 0, g_b200.stream>>>(B.n, k, g, B.c, B.x, B.ldx, B.y, B.ldy)));
-	B200_KERNEL_CHECK();
-	return 0;
+	return axpby_cols_launch(B.n, k, B.c, B.x, B.ldx, B.y, B.ldy);
 }
 
 // the open batches are independent of one another (axpby_defer keeps them so): any order is the program's order
