@@ -229,6 +229,7 @@ static int dia_build(b200_mat *A, const int *rp, const int *ci, const double *va
 	const int nloc = A->nrows;
 	A->dia_nd = 0;
 	if (nloc <= 0 || A->nnz <= 0 || b200_opt(B200_OPT_NO_DIA)) return 0;
+	if (A->nrows_global != A->ncols_global) return 0;      // the diagonal kernels take the x window to be as long as the rows
 	if (nranks > 1 && !A->halo_contiguous) return 0;
 	const long long lo = A->row0;
 	auto gcol = [&](int c) -> long long {

@@ -205,6 +205,7 @@ int dia_image_from_table(b200_mat *A, const std::vector<long long> &table_h, Tem
 	for (long long d : table_h) if (d != MB_EMPTY) offs.push_back(d);
 	std::sort(offs.begin(), offs.end());
 	const int nd = (int)offs.size();
+	if (A->nrows_global != A->ncols_global) return 0;      // the diagonal kernels take the x window to be as long as the rows
 	if (nd < 1 || nd > 32 || (double)A->nnz < 0.45 * (double)nd * nloc) return 0;
 	for (long long d : offs) if (d > 0x3fffffff || d < -0x3fffffff) return 0;
 	int ng = 0, ndp = 0;

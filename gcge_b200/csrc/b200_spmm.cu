@@ -800,6 +800,64 @@ static int spmm_dia_ws_dispatch(const b200_mat *M, const double *x, int ldx, dou
 #undef WS
 }
 
+// ---- diagonal image, 1 ... 4 columns ---------------------------------------------------------------------------
+// The reference's OrthSelf multiplies B by ONE column at a time (src/ops_orth.c:45-118: thousands of calls per solve
+// when its own code runs over the slots), and small block sizes give 2 ... 4.  The CSR kernels then stream 12 bytes per
+// entry to multiply it with 8 k bytes of x; here a thread owns a row, walks its slots of the image in ascending
+// column order (runs ascending, offsets inside a run ascending: the order of every other kernel in this file) and
+// gathers the x rows itself -- neighbouring threads want neighbouring rows, so the gathers meet in L1.  Entries the
+// CCS input does not hold are +0.0 in the image and add a signed zero; columns outside the window are skipped.
+template <int K>
+__global__ void __launch_bounds__(256)
+spmm_dia_narrow_kernel(int nloc, int ng, const int *__restrict__ off, const int *__restrict__ grp, const double *__restrict__ val,
+                       int ndp, const double *x, int ldx, int lo, int hi, double *y, int ldy, const int *__restrict__ gate)
+{
+	if (gate != nullptr && *gate == 0) return;
+	__shared__ int off_s[32], slot_s[32], w_s[32];
+	if ((int)threadIdx.x < ng) {
+		off_s[threadIdx.x] = off[threadIdx.x]; slot_s[threadIdx.x] = grp[2 * threadIdx.x]; w_s[threadIdx.x] = grp[2 * threadIdx.x + 1];
+	}
+	__syncthreads();
+	const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+	if (row >= nloc) return;
+	const double *v = val + (size_t)row * ndp;
+	double acc[K];
+#pragma unroll
+	for (int c = 0; c < K; ++c) acc[c] = 0.0;
+	for (int g = 0; g < ng; ++g) {
+		const long long c0 = row + off_s[g];
+		const double *vs = v + slot_s[g];
+		for (int j = 0; j < w_s[g]; ++j) {
+			const long long col = c0 + j;
+			if (col < lo || col >= hi) continue;
+			const double a = __ldg(vs + j);
+			const double *xr = x + col * (long long)ldx;
+#pragma unroll
+			for (int c = 0; c < K; ++c) acc[c] = __dadd_rn(acc[c], __dmul_rn(a, xr[c]));
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < K; ++c) y[(size_t)row * ldy + c] = acc[c];
+}
+
+static int launch_spmm_dia_narrow(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate)
+{
+	const int hb = M->halo_below, lo = -hb, hi = M->nrows + M->nhalo - hb;
+	const unsigned grid = (unsigned)(((long long)M->nrows + 255) / 256);
+#define NARROW(K_) spmm_dia_narrow_kernel<K_><<<grid, 256, 0, g_b200.stream>>>(M->nrows, M->dia_ng, M->dia_off, M->dia_grp, \
+		M->dia_val, M->dia_ndp, x, ldx, lo, hi, y, ldy, gate)
+	switch (k) {
+	case 1: NARROW(1); break;
+	case 2: NARROW(2); break;
+	case 3: NARROW(3); break;
+	case 4: NARROW(4); break;
+	default: return 2;
+	}
+#undef NARROW
+	B200_KERNEL_CHECK();
+	return 0;
+}
+
 // diagonal image, at most 64 columns
 static int spmm_dia_dispatch(const b200_mat *M, const double *x, int ldx, double *y, int ldy, int k, const int *gate)
 {
@@ -937,13 +995,14 @@ int b200k_spmm(const b200_mat *M, int trans, const double *x, int ldx, double *y
 	if (nrows <= 0) return 0;
 	B200Prof prof(B200_PROF_SPMM, 12.0 * M->nnz + 4.0 * (nrows + 1) + 8.0 * k * ((double)M->nrows + M->ncols),
 	              2.0 * M->nnz * k);
-	if (!trans && M->dia_nd > 0 && k > 4) {
-		// diagonal image, 64 columns per pass; whatever it cannot take (misaligned block, a tail of
-		// at most 4 columns) goes to the CSR kernels
+	if (!trans && M->dia_nd > 0 && M->nrows > 0) {
+		// diagonal image, 64 columns per pass (1 ... 4 columns: the narrow kernel); whatever it cannot take
+		// (a misaligned or odd block) goes to the CSR kernels
 		int c0 = 0;
 		for (; c0 < k; c0 += 64) {
 			const int kc = k - c0 < 64 ? k - c0 : 64;
-			const int rc = (kc > 4) ? spmm_dia_dispatch(M, x + c0, ldx, y + c0, ldy, kc, gate) : 2;
+			const int rc = (kc > 4) ? spmm_dia_dispatch(M, x + c0, ldx, y + c0, ldy, kc, gate)
+			                        : launch_spmm_dia_narrow(M, x + c0, ldx, y + c0, ldy, kc, gate);
 			if (rc == 1) return 1;
 			if (rc == 2) break;
 		}
