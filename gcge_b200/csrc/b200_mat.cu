@@ -409,17 +409,25 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 	B200_CHECK(nnz >= 0 && (nnz == 0 || (ci_in && va_in)), "b200_mat_create_from_local_rows: bad arrays");
 	// column extent of the slab from the first / last entry of every row (columns ascend inside a row; the device
 	// checks that, and everything else about the arrays, once they are uploaded)
+	// Malformed input must fail on EVERY rank (the construction below is collective): what this rank finds wrong with
+	// its own arrays is summed over the ranks before anybody gives up.
 	long long cmin = lo, cmax = hi - 1;
-	for (int r = 0; r < nloc; ++r) {
+	int bad_rows = 0;
+	for (int r = 0; r < nloc && !bad_rows; ++r) {
 		const int e0 = rp_in[r] - rp_in[0], e1 = rp_in[r + 1] - rp_in[0];
-		B200_CHECK(e0 >= 0 && e1 >= e0 && e1 <= nnz, "b200_mat_create_from_local_rows: row pointers not monotone at row %d", r);
+		if (!(e0 >= 0 && e1 >= e0 && e1 <= nnz)) { bad_rows = 1; break; }
 		if (e1 > e0) {
 			const int *cr = ci_in + rp_in[0];
 			if (cr[e0] < cmin) cmin = cr[e0];
 			if (cr[e1 - 1] > cmax) cmax = cr[e1 - 1];
 		}
 	}
-	B200_CHECK(cmin >= 0 && cmax < nrows_global, "b200_mat_create_from_local_rows: column index out of range");
+	if (!(cmin >= 0 && cmax < nrows_global)) bad_rows |= 2;
+	if (nranks == 1) {
+		B200_CHECK(!(bad_rows & 1), "b200_mat_create_from_local_rows: row pointers not monotone");
+		B200_CHECK(!(bad_rows & 2), "b200_mat_create_from_local_rows: column index out of range");
+	}
+	if (bad_rows) { cmin = lo; cmax = hi - 1; }
 	b200_mat *A = (b200_mat *)calloc(1, sizeof(b200_mat));
 	A->nrows = nloc; A->ncols = (nranks == 1) ? nrows_global : nloc; A->nnz = nnz;
 	A->nrows_global = nrows_global; A->ncols_global = nrows_global; A->row0 = (int)lo; A->t_col0 = lo;
@@ -428,12 +436,18 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 	long long nnz_global = nnz;
 	if (nranks > 1) {
 		// extents and the global entry count of all ranks: one allreduce over a zero-padded array
-		double *buf = (double *)b200_scratch(3, sizeof(double) * (2 * (size_t)nranks + 2));
+		double *buf = (double *)b200_scratch(3, sizeof(double) * (2 * (size_t)nranks + 4));
 		if (!buf) { free(A); return 1; }
-		std::vector<double> h(2 * (size_t)nranks + 1, 0.0);
+		std::vector<double> h(2 * (size_t)nranks + 2, 0.0);
 		h[2 * rank] = (double)cmin; h[2 * rank + 1] = (double)cmax; h[2 * nranks] = (double)nnz;
+		h[2 * nranks + 1] = bad_rows ? 1.0 : 0.0;
 		if (b200k_h2d(buf, h.data(), sizeof(double) * h.size()) || b200k_allreduce_sum(buf, h.size()) ||
 		    b200k_d2h(h.data(), buf, sizeof(double) * h.size())) { free(A); return 1; }
+		if (h[2 * nranks + 1] != 0.0) {
+			free(A);
+			return b200_fail("b200_mat_create_from_local_rows: %s", bad_rows ? ((bad_rows & 1) ? "row pointers not monotone" :
+			                 "column index out of range") : "another rank's rows are malformed");
+		}
 		for (int q = 0; q < nranks; ++q) {
 			ext_min[q] = (long long)h[2 * q]; ext_max[q] = (long long)h[2 * q + 1];
 			b200_partition_range(nrows_global, q, nranks, &rlo[q], &rhi[q]);
@@ -508,9 +522,18 @@ extern "C" int b200_mat_create_from_local_rows(int nrows_global, int row0, int n
 	}
 	int bad = 0;
 	if (b200k_local_rows_finish(A, rp_in[0], &bad)) { b200_mat_destroy(A); return 1; }
-	if (bad) {
+	int bad_any = bad;
+	if (nranks > 1) {
+		double *buf = (double *)b200_scratch(3, sizeof(double) * 2), hb = bad ? 1.0 : 0.0;
+		if (!buf || b200k_h2d(buf, &hb, sizeof(double)) || b200k_allreduce_sum(buf, 1) || b200k_d2h(&hb, buf, sizeof(double))) {
+			b200_mat_destroy(A); return 1;
+		}
+		bad_any = hb != 0.0;
+	}
+	if (bad_any) {
 		b200_mat_destroy(A);
-		return b200_fail("b200_mat_create_from_local_rows: columns of some row not ascending / out of range, or row pointers not monotone");
+		return b200_fail(bad ? "b200_mat_create_from_local_rows: columns of some row not ascending / out of range, or row pointers not monotone"
+		                     : "b200_mat_create_from_local_rows: another rank's rows are malformed");
 	}
 	if (b200k_dia_build_device(A) || b200k_lat_detect(A)) { b200_mat_destroy(A); return 1; }
 	if (nranks > 1 && p2p_register_for(A)) { b200_mat_destroy(A); return 1; }

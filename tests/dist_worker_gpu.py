@@ -103,6 +103,23 @@ check(np.array_equal(g1, gather_rows(Y2, 0, 16, nl)) and np.array_equal(g1, orac
 o1 = api.gcg_solve(Awhole, Bwhole, nev=8); o2 = api.gcg_solve(Aloc, Bloc, nev=8)
 check(o1["num_iter"] == o2["num_iter"] and np.array_equal(o1["eval"], o2["eval"]), "local-rows solve differs from whole-CCS solve")
 
+# malformed rows on ONE rank fail on EVERY rank (the construction is collective: nobody may be left waiting), and the
+# library keeps working afterwards
+rp_b, ci_b, va_b = (np.array(a, copy=True) for a in rowsA)
+if rank == world - 1:
+    r_bad = int(np.argmax(np.diff(rp_b) >= 2)); e = int(rp_b[r_bad] - rp_b[0])
+    ci_b[e], ci_b[e + 1] = ci_b[e + 1], ci_b[e]                 # columns of one row no longer ascend
+failed = False
+try:
+    api.Mat.from_local_rows(nl, (mloc // world) * rank * mloc * mloc, rp_b, ci_b, va_b)
+except RuntimeError as exc:
+    failed = True
+    check(("ascending" in str(exc)) == (rank == world - 1) and ("another rank" in str(exc)) == (rank != world - 1), f"message: {exc}")
+check(failed, "malformed rows on the last rank were accepted")
+Aagain = api.Mat.from_local_rows(nl, (mloc // world) * rank * mloc * mloc, *rowsA)
+api.mat_dot_multivec(Aagain, Xl, Y2, (0, 0), (16, 16))
+check(np.array_equal(g1, gather_rows(Y2, 0, 16, nl)), "local-rows SpMM after a rejected construction")
+
 # ---- the first slab rows lack the farthest sub-diagonal, so the halo plan's extent (from the entries
 # those rows have) is SHORTER than the reach of the diagonal image; rows further inside still need halo rows and
 # must not be multiplied before the halo has arrived ------------------------------------------------------------
