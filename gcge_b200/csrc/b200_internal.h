@@ -72,7 +72,7 @@ int b200k_spmm_lat(const b200_mat *M, const double *x, int ldx, double *y, int l
 enum { B200_OPT_NO_DIA = 0, B200_OPT_NO_LAT, B200_OPT_SPMM_OLD_DIA, B200_OPT_NO_FUSED_DOT, B200_OPT_NO_TMA_DENSE,
        B200_OPT_HOST_BUILD, B200_OPT_NO_OVERLAP, B200_OPT_NO_P2P, B200_OPT_NO_KERNEL_ALLREDUCE, B200_OPT_SYEV_PROF,
        B200_OPT_BPCG_TRACE, B200_OPT_SPMM_CTAS, B200_OPT_SPMM_NS, B200_OPT_LAT_TI, B200_OPT_LAT_TJ, B200_OPT_LAT_NS,
-       B200_OPT_LAT_EVEN_PITCH, B200_OPT_LAT_NO_VPAD, B200_OPT_LAT_VERBOSE, B200_OPT_LAT_NO_CONST, B200_OPT_ORTH_TRACE, B200_OPT_NO_AXPBY_BATCH, B200_OPT_COUNT };
+       B200_OPT_LAT_EVEN_PITCH, B200_OPT_LAT_NO_VPAD, B200_OPT_LAT_VERBOSE, B200_OPT_LAT_NO_CONST, B200_OPT_ORTH_TRACE, B200_OPT_NO_AXPBY_BATCH, B200_OPT_BPCG_CTAS, B200_OPT_COUNT };
 extern int g_b200_opt[B200_OPT_COUNT];
 static inline int b200_opt(int id) { return g_b200_opt[id]; }
 static_assert(B200_OPT_BPCG_TRACE == B200K_OPT_BPCG_TRACE && B200_OPT_ORTH_TRACE == B200K_OPT_ORTH_TRACE, "b200_dev.h option id out of step");

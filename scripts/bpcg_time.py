@@ -13,13 +13,16 @@ n = pen.A.ncols
 Bv = api.MultiVec(n, k); X = api.MultiVec(n, k)
 api.libc_srand(1); Bv.set_random(0, k)
 ws = [api.MultiVec(n, k) for _ in range(3)]
-api.block_pcg(A, Bv, X, (0, 0), (k, k), max_iter=30, rate=1e-30, tol=1e-30, ws=ws)
-api.sync()
-api.prof_enable(True)
-api.block_pcg(A, Bv, X, (0, 0), (k, k), max_iter=30, rate=1e-30, tol=1e-30, ws=ws)
-api.sync()
-pr = api.prof_report(); api.prof_enable(False)
-tot = sum(v["ms"] for v in pr.values())
-print({"m": m, "k": k, "total_ms": round(tot, 2), "per_iter_ms": round(tot / 30, 4),
-       "spmm_ms_per_call": round(pr["spmm"]["ms"] / max(pr["spmm"]["calls"], 1), 4), "spmm_GBs": round(pr["spmm"]["bytes"] / pr["spmm"]["ms"] / 1e6, 1),
-       "bpcg_ms_per_iter": round(pr["bpcg_fused"]["ms"] / 30, 4), "bpcg_GBs": round(pr["bpcg_fused"]["bytes"] / pr["bpcg_fused"]["ms"] / 1e6, 1)}, flush=True)
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]       # option bpcg_ctas (0 = default)
+for ctas in variants:
+  api.lib().b200_option_set(b"bpcg_ctas", ctas)
+  api.block_pcg(A, Bv, X, (0, 0), (k, k), max_iter=30, rate=1e-30, tol=1e-30, ws=ws)
+  api.sync()
+  api.prof_enable(True)
+  api.block_pcg(A, Bv, X, (0, 0), (k, k), max_iter=30, rate=1e-30, tol=1e-30, ws=ws)
+  api.sync()
+  pr = api.prof_report(); api.prof_enable(False)
+  tot = sum(v["ms"] for v in pr.values())
+  print({"bpcg_ctas": ctas, "m": m, "k": k, "total_ms": round(tot, 2), "per_iter_ms": round(tot / 30, 4),
+         "spmm_ms_per_call": round(pr["spmm"]["ms"] / max(pr["spmm"]["calls"], 1), 4), "spmm_GBs": round(pr["spmm"]["bytes"] / pr["spmm"]["ms"] / 1e6, 1),
+         "bpcg_ms_per_iter": round(pr["bpcg_fused"]["ms"] / 30, 4), "bpcg_GBs": round(pr["bpcg_fused"]["bytes"] / pr["bpcg_fused"]["ms"] / 1e6, 1)}, flush=True)
