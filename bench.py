@@ -451,8 +451,11 @@ def run_b200(a) -> int:
     barrier()
     api.timer_start()
     w0 = time.time()
+    step_wall = []
     for _ in range(a.steps):
+        ws0 = time.time()
         out = solve(A, B, ws)
+        step_wall.append({"wall_s": round(time.time() - ws0, 4), "solver_s": round(float(out["stats"]["time_total"]), 4)})
     ms = api.timer_stop()
     barrier()
     wall = time.time() - w0
@@ -635,7 +638,7 @@ def run_b200(a) -> int:
             "config": workload_config(a, world),
             "parity_vs_golden": par_gold,
             "parity_at_full_size": parity,
-            "same_size": same,
+            "same_size": same, "timed_steps": step_wall,
             "result": {"num_iter": int(out["num_iter"]), "nev_conv": int(out["nev_conv"]),
                        "eval_first": float(out["eval"][0]), "eval_nev": float(out["eval"][a.nev - 1]),
                        "wall_s_per_step": wall / a.steps},

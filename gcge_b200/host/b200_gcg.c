@@ -420,9 +420,7 @@ static b200_mv *gcg_second_buffer(const b200_mv *V)
 
 static void gcg_release(gcg_t *g)
 {
-	b200k_free(g->eval_d); b200k_free(g->matA_d); b200k_free(g->evec_d); b200k_free(g->t1_d);
-	b200k_free(g->ptap_d); b200k_free(g->wsE_d); b200k_free(g->res_d); b200k_free(g->scal_d);
-	b200k_free(g->idx_d);
+	/* (the device work arrays live in scratch slot 9: nothing to free) */
 	free(g->eval_h); free(g->res_h); free(g->offP); free(g->offW);
 	if (g->own_ws) {
 		b200_mv_destroy(g->V_alloc);
@@ -555,15 +553,19 @@ int b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *
 	g.Nmax = prm->nevInit + 2 * bs; if (g.Nmax < sizeVmax) g.Nmax = sizeVmax;
 	g.ldE = (g.Nmax + 3) & ~3;
 	g.bsp = (bs + 3) & ~3;
-	if (b200k_malloc((void **)&g.eval_d, sizeof(double) * (size_t)(sizeVmax + 8))) goto done;
-	if (b200k_malloc((void **)&g.matA_d, sizeof(double) * (size_t)g.Nmax * g.ldE)) goto done;
-	if (b200k_malloc((void **)&g.evec_d, sizeof(double) * (size_t)g.Nmax * g.ldE)) goto done;
-	if (b200k_malloc((void **)&g.t1_d, sizeof(double) * (size_t)g.Nmax * g.bsp)) goto done;
-	if (b200k_malloc((void **)&g.wsE_d, sizeof(double) * (size_t)g.Nmax * g.bsp)) goto done;
-	if (b200k_malloc((void **)&g.ptap_d, sizeof(double) * (size_t)bs * bs)) goto done;
-	if (b200k_malloc((void **)&g.res_d, sizeof(double) * (size_t)(bs + 64))) goto done;
-	if (b200k_malloc((void **)&g.scal_d, sizeof(double) * (size_t)(bs + 64))) goto done;
-	if (b200k_malloc((void **)&g.idx_d, sizeof(int) * (size_t)(bs + 64))) goto done;
+	{
+		/* the solver's small device arrays come out of one persistent scratch slot: cudaMalloc / cudaFree of nine
+		 * buffers per solve is milliseconds on one GPU and up to seconds in a multi-GPU process (peer mappings, IPC) */
+		const size_t cnt[9] = {(size_t)(sizeVmax + 8), (size_t)g.Nmax * g.ldE, (size_t)g.Nmax * g.ldE, (size_t)g.Nmax * g.bsp,
+		                       (size_t)g.Nmax * g.bsp, (size_t)bs * bs, (size_t)(bs + 64), (size_t)(bs + 64), (size_t)(bs + 64)};
+		size_t off[10]; off[0] = 0;
+		for (int i = 0; i < 9; ++i) off[i + 1] = off[i] + ((cnt[i] * sizeof(double) + 255) & ~(size_t)255);
+		char *slab = (char *)b200_scratch(9, off[9]);
+		if (!slab || b200k_memset(slab, 0, off[9])) goto done;
+		g.eval_d = (double *)(slab + off[0]); g.matA_d = (double *)(slab + off[1]); g.evec_d = (double *)(slab + off[2]);
+		g.t1_d = (double *)(slab + off[3]); g.wsE_d = (double *)(slab + off[4]); g.ptap_d = (double *)(slab + off[5]);
+		g.res_d = (double *)(slab + off[6]); g.scal_d = (double *)(slab + off[7]); g.idx_d = (int *)(slab + off[8]);
+	}
 	g.eval_h = (double *)calloc((size_t)sizeVmax + 8, sizeof(double));
 	g.res_h = (double *)calloc((size_t)bs + 64, sizeof(double));
 	g.offP = (int *)calloc(2 * (size_t)bs + 16, sizeof(int));
