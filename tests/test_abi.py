@@ -78,3 +78,56 @@ def test_rand_jump_ahead_matches_glibc(seed, steps):
     L.b200_rand_selfcheck.argtypes = [C.c_ulonglong]
     C.CDLL("libc.so.6").srand(C.c_uint(seed))
     assert L.b200_rand_selfcheck(steps) == 0, L.b200_last_error()
+
+
+def test_rand_exact_jump_with_binary_powers():
+    """The device fill (b200_rand.cu) gives every lane its own stream position t = column * n + row and builds the
+    generator state there as M^t S_0 from the powers M^(2^j) of the 31 x 31 step matrix over Z/2^32.  The same
+    arithmetic restated in numpy against glibc itself: rand() called t times, then the next values compared."""
+    import numpy as np
+    DEG, SEP = 31, 3
+    libc = C.CDLL("libc.so.6")
+    M = np.zeros((DEG, DEG), dtype=np.uint64)
+    for i in range(DEG - 1):
+        M[i, i + 1] = 1
+    M[DEG - 1, 0] = 1; M[DEG - 1, DEG - SEP] = 1                 # o_t = o_{t-31} + o_{t-3}
+    mask = np.uint64(0xFFFFFFFF)
+
+    def mm(a, b):
+        # 32-bit wrap-around products of 31 terms: split b into 16-bit halves so nothing overflows 64 bits
+        lo = (a @ (b & np.uint64(0xFFFF))) & mask
+        hi = (a @ (b >> np.uint64(16))) & np.uint64(0xFFFF)
+        return (lo + (hi << np.uint64(16))) & mask
+
+    powers = [M]
+    for _ in range(1, 24):
+        powers.append(mm(powers[-1], powers[-1]))
+    # S_0: the 31 outputs before position 0, recovered from glibc by running the recurrence backwards is not needed:
+    # take the history as the first 31 FULL words o_t, which rand() hides one bit of -- so start from a state we know:
+    # after srand(seed) glibc's table is r[i] (i < 34 by the LCG, then 310 discarded steps); rebuild it as glibc does.
+    seed = 12345
+    r = [0] * 34
+    r[0] = seed
+    for i in range(1, 31):
+        hi_, lo_ = divmod(r[i - 1], 127773)
+        w = 16807 * lo_ - 2836 * hi_
+        r[i] = w + 2147483647 if w < 0 else w
+    for i in range(31, 34):
+        r[i] = r[i - 31]
+    o = [(x & 0xFFFFFFFF) for x in r]
+    for i in range(34, 344):
+        o.append((o[i - 31] + o[i - 3]) & 0xFFFFFFFF)
+    S0 = np.array(o[344 - 31:344], dtype=np.uint64)               # history right before the first rand() after srand
+    for t in (0, 1, 5, 31, 1000, 65537, 3_000_001):
+        S = S0.copy()
+        for j in range(24):
+            if (t >> j) & 1:
+                S = mm(powers[j], S.reshape(DEG, 1)).reshape(DEG)
+        libc.srand(C.c_uint(seed))
+        for _ in range(t):
+            libc.rand()
+        s = [int(v) for v in S]
+        for i in range(40):                                       # the recurrence as the kernel runs it
+            nxt = (s[0] + s[DEG - SEP]) & 0xFFFFFFFF
+            s = s[1:] + [nxt]
+            assert (nxt >> 1) == libc.rand(), (t, i)
