@@ -276,7 +276,8 @@ void b200_gcg_default_params(int nevConv, b200_gcg_params *prm); /* defaults of 
  * src/ops_eig_sol_gcg.c:1561: [0] nevMax+2*block_size columns, [1..3] block_size columns).
  * nevGiven > 0: warm start from the first nevGiven columns of evec (reference :107-109).
  * The library keeps one more buffer of the shape of mv_ws[0] between solves ([X P W] is double-buffered so
- * that ComputeX, reference :458-471, is a pointer swap); b200_finalize or b200_gcg_free_cache releases it. */
+ * that ComputeX, reference :458-471, is a pointer swap) and a block_size-wide block for the unknowns of the inner
+ * solve; b200_finalize or b200_gcg_free_cache releases them. */
 void b200_gcg_free_cache(void);
 int  b200_gcg_solve(const b200_mat *A, const b200_mat *B, double *eval, b200_mv *evec,
                     int nevGiven, int *nevConv, const b200_gcg_params *prm, b200_mv **mv_ws,
